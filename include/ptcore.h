@@ -1,0 +1,177 @@
+/* ptcore.h — C ABI of the B200 path-tracing core.
+ *
+ * This is the drop-in boundary for the reference's path-tracing compute pass:
+ * `impl RenderStep for RTStep` (reference: src/render_steps/mod.rs:20-25,
+ * src/render_steps/pt.rs:341-565,732-745) as called by `Raytracer`
+ * (src/raytracer.rs:84-91,177-195,351-357).  One opaque `ptc_step` per GPU.
+ * Plain pointers and sizes only; no CUDA, torch or C++ types.  All functions
+ * return 0 (PTC_OK) or a negative `enum ptc_status`; the message for the last
+ * failure on the calling thread is `ptc_last_error()`.  Nothing here ever
+ * falls back to a CPU implementation: without a CUDA device, ptc_create
+ * fails with PTC_ERR_NO_DEVICE.
+ *
+ * The host-side helpers at the bottom (camera, scene ingest) restate
+ * src/camera.rs and src/scene.rs so a caller without the Rust crate can
+ * produce the same arrays.
+ */
+#ifndef PTCORE_H
+#define PTCORE_H
+
+#include "ptcore_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PTC_API
+#else
+#define PTC_API __attribute__((visibility("default")))
+#endif
+
+typedef struct ptc_step ptc_step;
+
+/* ---- RenderStep lifecycle ------------------------------------------------ */
+
+/* replaces RTStep::create (pt.rs:341-490) + create_static_bind_groups
+ * (pt.rs:188-337): copies the scene arrays to the device, builds this
+ * library's own BVH over every mesh (the reference builds one driver BLAS per
+ * mesh and one TLAS, pt.rs:364-468), builds the emissive-triangle list
+ * (pt.rs:206-243), creates bindless texture objects (texture.rs:232-336) and
+ * allocates the accumulation + aux planes.  The scene view is not retained. */
+PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, int cuda_device, ptc_step** out);
+
+/* replaces RTStep::update (pt.rs:492-521): latch the 112-byte Uniforms for the
+ * next render.  `num_lights` is overwritten with the step's own light count
+ * exactly as pt.rs:243 does.  Host pointer; copied before return. */
+PTC_API int ptc_update(ptc_step* step, const ptc_uniforms* uniforms);
+
+/* replaces RTStep::render (pt.rs:523-565) + rt_queue.submit (raytracer.rs:195):
+ * enqueue one frame (SAMPLES_PER_PIXEL samples for every pixel, accumulated
+ * into the COLOR plane, aux planes overwritten) on the step's stream and
+ * return immediately. */
+PTC_API int ptc_render(ptc_step* step);
+
+/* replaces rt_device.poll(Poll / Wait) (raytracer.rs:165-167,319): wait != 0
+ * blocks until every enqueued frame has finished; wait == 0 returns
+ * PTC_ERR_NOT_READY while work is in flight. */
+PTC_API int ptc_poll(ptc_step* step, int wait);
+
+/* replaces RTStep::resize (pt.rs:732-745) + the accumulation-texture
+ * re-creation in Raytracer::resize (raytracer.rs:344): reallocates and zeroes
+ * every plane. */
+PTC_API int ptc_resize(ptc_step* step, uint32_t width, uint32_t height);
+
+/* the analogue of `step.output_texture_view = ...` (raytracer.rs:86): the
+ * caller injects the accumulation target, a device pointer to width*height
+ * float4 (row-major, tightly packed).  NULL restores the step-owned buffer. */
+PTC_API int ptc_set_output(ptc_step* step, void* device_rgba32f);
+
+/* zero the accumulation plane (what recreating the texture does) */
+PTC_API int ptc_reset_accumulation(ptc_step* step);
+
+PTC_API void ptc_destroy(ptc_step* step);
+
+/* ---- results -------------------------------------------------------------- */
+
+/* synchronous device->host copy of one plane (enum ptc_plane) after all
+ * enqueued frames; dst_pitch_bytes = 0 means tightly packed. */
+PTC_API int ptc_read(ptc_step* step, int plane, void* dst, size_t dst_pitch_bytes);
+
+/* asynchronous variant for display / streaming: snapshots the plane on the
+ * render stream (device->device), then copies the snapshot to `dst_pinned` on
+ * a second stream so following frames are not held up.  Completion is
+ * observed with ptc_poll(step, 1) or ptc_read_wait. */
+PTC_API int ptc_read_async(ptc_step* step, int plane, void* dst_pinned);
+PTC_API int ptc_read_wait(ptc_step* step);
+
+/* zero-copy interop: device address of a plane (valid until resize/destroy) */
+PTC_API void* ptc_device_ptr(ptc_step* step, int plane);
+
+/* the CUDA stream frames are enqueued on (a cudaStream_t), for callers that
+ * order their own work (e.g. an NCCL reduce of the COLOR plane) after it */
+PTC_API void* ptc_stream(ptc_step* step);
+
+PTC_API int ptc_get_stats(ptc_step* step, ptc_stats* out);
+
+/* per-stage device timing with CUDA events recorded on the render stream around every launch
+ * (the reference has no counterpart: all its passes set timestamp_writes: None, pt.rs:550).
+ * ms / launches: [0] raygen, [1] trace (closest-hit traversal), [2] shade, summed since enabling. */
+PTC_API int ptc_set_profiling(ptc_step* step, int enable);
+PTC_API int ptc_get_profile(ptc_step* step, double ms[3], uint64_t launches[3]);
+PTC_API int ptc_num_lights(ptc_step* step, uint32_t* out);
+
+/* BVH facts for reports: out[0]=nodes, out[1]=triangles, out[2]=node bytes,
+ * out[3]=triangle bytes, out[4]=max depth, out[5]=build milliseconds */
+PTC_API int ptc_bvh_info(ptc_step* step, uint64_t out[8]);
+
+/* trace caller-supplied rays (closest hit) — unit-test / tooling entry point
+ * for the traversal kernel.  rays: n x 8 floats (ox,oy,oz,_,dx,dy,dz,_) host
+ * memory; hits: n x 4 words (t, b1, b2 as f32; global triangle id or
+ * 0xFFFFFFFF as u32); ids: optional n x 2 (instance_index, geometry_index). */
+PTC_API int ptc_trace_rays(ptc_step* step, const float* rays, uint64_t n, uint32_t* hits, uint32_t* ids);
+/* same through the any-hit kernel: occluded[i] = 1 iff some triangle lies in (tmin, tmax_i);
+ * rays[i*8+7] carries tmax_i (<= 0 means PT_RAY_TMAX) */
+PTC_API int ptc_trace_rays_any(ptc_step* step, const float* rays, uint64_t n, uint8_t* occluded);
+
+PTC_API const char* ptc_last_error(void);
+PTC_API const char* ptc_version(void);
+PTC_API int ptc_device_count(void);
+
+/* ---- host side: camera (reference: src/camera.rs:31-79) ------------------- */
+
+typedef struct ptc_host_camera {
+    uint32_t width, height;
+    float    fov;
+    float    position[3];
+    float    lookat[3];
+    uint32_t frame;
+    uint32_t samples_per_pixel, max_bounces;
+    float    pixel_space_x[3], pixel_space_y[3], first_pixel_pos[3];
+    float    theta_x, theta_y, camera_speed;
+} ptc_host_camera;
+
+/* Camera::new (camera.rs:31-52), including its one call to update() */
+PTC_API void ptc_camera_new(ptc_host_camera* cam, uint32_t width, uint32_t height, float fov_deg, const float position[3]);
+/* Camera::update (camera.rs:54-79): viewport basis from the CURRENT lookat, then lookat from theta */
+PTC_API void ptc_camera_update(ptc_host_camera* cam);
+/* uniforms::Uniforms::new (uniforms.rs:30-50,64-71) */
+PTC_API void ptc_camera_uniforms(const ptc_host_camera* cam, ptc_uniforms* out);
+
+/* ---- host side: scene ingest (reference: src/scene.rs:77-394) -------------- */
+
+typedef struct ptc_scene ptc_scene;
+
+enum ptc_texture_source { PTC_TEX_CONSTANT = 0, PTC_TEX_FILE = 1, PTC_TEX_TEXELS = 2 };
+
+typedef struct ptc_scene_texture_info {
+    uint32_t source;         /* enum ptc_texture_source */
+    uint32_t width, height;  /* 1x1 for constants; 0x0 for files not decoded yet */
+    uint32_t format;
+    float    color[4];       /* constants */
+    const char* path;        /* files: joined with the OBJ's directory (scene.rs:281-283) */
+} ptc_scene_texture_info;
+
+/* Scene::new (scene.rs:77-122): textures 0..8 = default constants, texture 9 =
+ * the environment map (reference: "res/knob/envmap.exr"), material 0 = default. */
+PTC_API int ptc_scene_new(const char* envmap_path, ptc_scene** out);
+/* scene.rs:202-215 computes missing normals with mesh-local indices into the global vertex array (a bug
+ * that corrupts every mesh after the first).  Default 0 = reproduce it (parity); 1 = apply the offset. */
+PTC_API int ptc_scene_set_fix_normals(ptc_scene* scene, int enable);
+/* Scene::load_obj (scene.rs:124-257) with tobj 4.0.3 GPU_LOAD_OPTIONS semantics */
+PTC_API int ptc_scene_load_obj(ptc_scene* scene, const char* obj_path);
+/* same from memory (obj_dir is used to resolve texture paths) */
+PTC_API int ptc_scene_load_obj_text(ptc_scene* scene, const char* obj_text, const char* mtl_text, const char* obj_dir);
+PTC_API uint64_t ptc_scene_num_textures(const ptc_scene* scene);
+PTC_API int ptc_scene_texture_info_at(const ptc_scene* scene, uint64_t index, ptc_scene_texture_info* out);
+/* hand decoded texels for a FILE texture (what Texture::load does with `image::open`, texture.rs:232-243);
+ * the scene copies them */
+PTC_API int ptc_scene_set_texels(ptc_scene* scene, uint64_t index, uint32_t width, uint32_t height, uint32_t format, const void* texels);
+/* borrow the arrays; every FILE texture must have texels by now */
+PTC_API int ptc_scene_get_view(const ptc_scene* scene, ptc_scene_view* out);
+PTC_API void ptc_scene_free(ptc_scene* scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTCORE_H */

@@ -1,0 +1,254 @@
+// bvh_build.cpp — binned-SAH BVH2 builder (host, multi-threaded) and device-layout emission.
+// See bvh_build.h for why the library owns this (reference: src/render_steps/pt.rs:364-468).
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <mutex>
+#include <thread>
+
+namespace ptc {
+namespace {
+
+constexpr int kBins = 16;
+constexpr float kTraversalCost = 1.2f;   // relative to one triangle test
+constexpr uint32_t kTaskGrain = 8192;    // subtrees below this many triangles are built inline by one thread
+
+struct Prim { float lo[3], hi[3], c[3]; uint32_t id; };
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
+    void grow(const float* l, const float* h) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); } }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Builder {
+    std::vector<Prim> prims;
+    std::vector<BuildNode>* nodes;
+    std::atomic<uint32_t> next_node{1};
+    std::atomic<uint32_t> max_depth{0};
+    uint32_t max_leaf;
+
+    struct Task { uint32_t node, first, count, depth; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Task> queue;
+    int pending = 0;     // tasks queued or running
+    bool done = false;
+
+    void note_depth(uint32_t d) {
+        uint32_t cur = max_depth.load(std::memory_order_relaxed);
+        while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {}
+    }
+
+    // Splits [first, first+count); returns mid or 0 when the range stays a leaf.
+    uint32_t split(uint32_t node, uint32_t first, uint32_t count) {
+        Box bounds, cb; bounds.reset(); cb.reset();
+        for (uint32_t i = first; i < first + count; ++i) { bounds.grow(prims[i].lo, prims[i].hi); cb.grow(prims[i].c, prims[i].c); }
+        BuildNode& n = (*nodes)[node];
+        std::memcpy(n.lo, bounds.lo, 12); std::memcpy(n.hi, bounds.hi, 12);
+        n.left = 0xFFFFFFFFu; n.first = first; n.count = count;
+        if (count == 1) return 0;
+
+        float best = std::numeric_limits<float>::infinity(); int best_axis = -1, best_split = -1;
+        for (int a = 0; a < 3; ++a) {
+            float ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0.0f)) continue;
+            Box bb[kBins]; uint32_t bn[kBins];
+            for (int b = 0; b < kBins; ++b) { bb[b].reset(); bn[b] = 0; }
+            float k = (float)kBins / ext;
+            for (uint32_t i = first; i < first + count; ++i) {
+                int b = (int)((prims[i].c[a] - cb.lo[a]) * k); if (b > kBins - 1) b = kBins - 1;
+                bb[b].grow(prims[i].lo, prims[i].hi); bn[b]++;
+            }
+            float right_area[kBins]; uint32_t right_n[kBins];
+            Box acc; acc.reset(); uint32_t cnt = 0;
+            for (int b = kBins - 1; b >= 1; --b) { if (bn[b]) { acc.grow(bb[b].lo, bb[b].hi); }
+                cnt += bn[b]; right_n[b] = cnt; right_area[b] = cnt ? acc.half_area() : 0.0f; }
+            acc.reset(); cnt = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                if (bn[b]) { acc.grow(bb[b].lo, bb[b].hi); }
+                cnt += bn[b];
+                if (!cnt || !right_n[b + 1]) continue;
+                float cost = acc.half_area() * (float)cnt + right_area[b + 1] * (float)right_n[b + 1];
+                if (cost < best) { best = cost; best_axis = a; best_split = b; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) {                                    // every centroid identical
+            if (count <= max_leaf) return 0;
+            mid = first + count / 2;
+        } else {
+            float parent = bounds.half_area();
+            float split_cost = kTraversalCost * parent + best;   // SAH, un-normalised by parent area
+            float leaf_cost = parent * (float)count;
+            if (count <= max_leaf && leaf_cost <= split_cost) return 0;
+            float ext = cb.hi[best_axis] - cb.lo[best_axis], k = (float)kBins / ext, base = cb.lo[best_axis];
+            auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
+                int b = (int)((p.c[best_axis] - base) * k); if (b > kBins - 1) b = kBins - 1;
+                return b <= best_split;
+            });
+            mid = (uint32_t)(it - prims.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        uint32_t left = next_node.fetch_add(2);
+        (*nodes)[node].left = left;
+        return mid;
+    }
+
+    void build_inline(uint32_t node, uint32_t first, uint32_t count, uint32_t depth) {
+        note_depth(depth);
+        uint32_t mid = split(node, first, count);
+        if (!mid) return;
+        uint32_t left = (*nodes)[node].left;
+        build_inline(left, first, mid - first, depth + 1);
+        build_inline(left + 1, mid, first + count - mid, depth + 1);
+    }
+
+    void push(Task t) { { std::lock_guard<std::mutex> l(mu); queue.push_back(t); pending++; } cv.notify_one(); }
+
+    void worker() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [&] { return done || !queue.empty(); });
+                if (queue.empty()) return;
+                t = queue.front(); queue.pop_front();
+            }
+            if (t.count <= kTaskGrain) build_inline(t.node, t.first, t.count, t.depth);
+            else {
+                note_depth(t.depth);
+                uint32_t mid = split(t.node, t.first, t.count);
+                if (mid) {
+                    uint32_t left = (*nodes)[t.node].left;
+                    push(Task{left, t.first, mid - t.first, t.depth + 1});
+                    push(Task{left + 1, mid, t.first + t.count - mid, t.depth + 1});
+                }
+            }
+            {
+                std::lock_guard<std::mutex> l(mu);
+                if (--pending == 0) { done = true; cv.notify_all(); }
+            }
+        }
+    }
+};
+
+}  // namespace
+
+void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthreads, Bvh2& out) {
+    auto t0 = std::chrono::steady_clock::now();
+    out.nodes.clear(); out.order.clear(); out.max_depth = 0; out.pad = 0.0f;
+    if (ntri == 0) { out.build_ms = 0.0; return; }
+    if (max_leaf < 1) max_leaf = 1;
+    if (max_leaf > 8) max_leaf = 8;
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads <= 0) nthreads = 1;
+
+    Builder b;
+    b.max_leaf = max_leaf;
+    b.prims.resize(ntri);
+    Box scene; scene.reset();
+    for (uint32_t i = 0; i < ntri; ++i) {
+        Prim& p = b.prims[i]; p.id = i;
+        const float* v = tri_pos + (size_t)i * 9;
+        for (int a = 0; a < 3; ++a) {
+            p.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
+            p.hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
+            p.c[a] = 0.5f * (p.lo[a] + p.hi[a]);
+        }
+        scene.grow(p.lo, p.hi);
+    }
+    // Padding that makes every box conservative with respect to pt_ray_tri: Moeller-Trumbore can accept a
+    // ray passing O(eps * distance) outside a triangle edge, so boxes grow by 2e-5 of the scene magnitude.
+    float mag = 0.0f;
+    for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::max(std::fabs(scene.lo[a]), std::fabs(scene.hi[a])), scene.hi[a] - scene.lo[a]));
+    out.pad = mag * 2e-5f + 1e-30f;
+
+    out.nodes.resize((size_t)2 * ntri);
+    b.nodes = &out.nodes;
+    b.push(Builder::Task{0, 0, ntri, 1});
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back([&b] { b.worker(); });
+    for (auto& t : th) t.join();
+
+    out.nodes.resize(b.next_node.load());
+    out.order.resize(ntri);
+    for (uint32_t i = 0; i < ntri; ++i) out.order[i] = b.prims[i].id;
+    out.max_depth = b.max_depth.load();
+    out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
+    out.nodes.clear(); out.tris.clear();
+    if (bvh.nodes.empty()) return;
+    const float inf = std::numeric_limits<float>::infinity();
+    uint32_t ntri = (uint32_t)bvh.order.size();
+    out.tris.resize(ntri);
+    for (uint32_t i = 0; i < ntri; ++i) {
+        uint32_t id = bvh.order[i];
+        const float* v = tri_pos + (size_t)id * 9;
+        DevTri& t = out.tris[i];
+        t.q[0] = v[0]; t.q[1] = v[1]; t.q[2] = v[2]; std::memcpy(&t.q[3], &id, 4);
+        t.q[4] = v[3] - v[0]; t.q[5] = v[4] - v[1]; t.q[6] = v[5] - v[2]; t.q[7] = 0.0f;
+        t.q[8] = v[6] - v[0]; t.q[9] = v[7] - v[1]; t.q[10] = v[8] - v[2]; t.q[11] = 0.0f;
+    }
+    // inner build nodes -> device node ids in depth-first order
+    std::vector<int32_t> dev_id(bvh.nodes.size(), -1);
+    std::vector<uint32_t> stack;
+    uint32_t n_inner = 0;
+    auto is_leaf = [&](uint32_t n) { return bvh.nodes[n].left == 0xFFFFFFFFu; };
+    if (is_leaf(0)) {
+        // single-leaf tree: synthesise a root whose second child is absent
+        out.nodes.resize(1);
+    } else {
+        stack.push_back(0);
+        while (!stack.empty()) {
+            uint32_t n = stack.back(); stack.pop_back();
+            dev_id[n] = (int32_t)n_inner++;
+            uint32_t l = bvh.nodes[n].left;
+            if (!is_leaf(l + 1)) stack.push_back(l + 1);
+            if (!is_leaf(l)) stack.push_back(l);
+        }
+        out.nodes.resize(n_inner);
+    }
+    auto child_ref = [&](uint32_t n) -> int32_t {
+        if (!is_leaf(n)) return dev_id[n];
+        const BuildNode& b = bvh.nodes[n];
+        uint32_t enc = (b.first << 3) | (b.count - 1);
+        return (int32_t)~enc;
+    };
+    auto put_box = [&](DevNode2& d, int c, const BuildNode* b) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = b ? b->lo[a] - bvh.pad : inf; hi[a] = b ? b->hi[a] + bvh.pad : -inf; }
+        d.q[c * 4 + 0] = lo[0]; d.q[c * 4 + 1] = hi[0]; d.q[c * 4 + 2] = lo[1]; d.q[c * 4 + 3] = hi[1];
+        d.q[8 + c * 2 + 0] = lo[2]; d.q[8 + c * 2 + 1] = hi[2];
+    };
+    if (is_leaf(0)) {
+        DevNode2& d = out.nodes[0]; std::memset(&d, 0, sizeof(d));
+        put_box(d, 0, &bvh.nodes[0]); put_box(d, 1, nullptr);
+        int32_t c0 = child_ref(0), c1 = c0;
+        std::memcpy(&d.q[12], &c0, 4); std::memcpy(&d.q[13], &c1, 4);
+        return;
+    }
+    for (uint32_t n = 0; n < bvh.nodes.size(); ++n) {
+        if (dev_id[n] < 0) continue;
+        DevNode2& d = out.nodes[dev_id[n]]; std::memset(&d, 0, sizeof(d));
+        uint32_t l = bvh.nodes[n].left;
+        put_box(d, 0, &bvh.nodes[l]); put_box(d, 1, &bvh.nodes[l + 1]);
+        int32_t c0 = child_ref(l), c1 = child_ref(l + 1);
+        std::memcpy(&d.q[12], &c0, 4); std::memcpy(&d.q[13], &c1, 4);
+    }
+}
+
+}  // namespace ptc

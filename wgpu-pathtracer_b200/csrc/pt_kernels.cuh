@@ -1,0 +1,52 @@
+// pt_kernels.cuh — the wavefront of CUDA kernels that replaces the reference's single WGSL
+// compute dispatch (src/shaders/pathtracer/pathtracer.wgsl:21-43, dispatched at
+// src/render_steps/pt.rs:547-565 as ceil(W/25) x ceil(H/25) groups of 625 threads).
+//
+// One frame = raygen -> (trace -> shade) x (MAX_BOUNCES + 1).  Paths live in SoA queues indexed by
+// queue slot; `shade` compacts survivors into the next queue with a warp ballot and accumulates
+// finished paths straight into the COLOR plane (every pixel finishes exactly once per frame, so no
+// separate accumulate pass and no atomics on the image are needed).  trace and shade are persistent:
+// a fixed grid of warps pulls 32-ray batches from a device-side cursor, so ray counts never travel
+// to the host and a frame is one uninterrupted stream of launches.
+#pragma once
+#include "pt_device.cuh"
+
+namespace ptc {
+
+#define PTC_MAX_SEGMENTS 64           // max_bounces + 1 <= 64
+
+// device counters, one block per frame in flight on the stream (reset by a memset node per frame)
+struct FrameCounters {
+    uint32_t count[PTC_MAX_SEGMENTS + 1];   // count[b] = rays alive entering segment b
+    uint32_t trace_cursor[PTC_MAX_SEGMENTS];
+    uint32_t shade_cursor[PTC_MAX_SEGMENTS];
+};
+
+struct Queue {            // SoA path state, one slot per live path
+    F4* ray_o;            // origin.xyz, pixel index (bits)
+    F4* ray_d;            // direction.xyz, rng state (bits)
+    F4* mask;             // color_mask.rgb, -
+    F4* acc;              // accumulated_color.rgb, -
+};
+
+struct Planes {
+    F4* color;            // accumulation target (`output` storage texture)
+    float* depth;         // depth_output
+    F4* normal;           // normals_output
+    F4* albedo;           // albedo_output
+    uint32_t* hit_tri;    // primary-hit global triangle id (0xFFFFFFFF = miss)
+};
+
+void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t npix);
+void launch_trace(cudaStream_t st, int grid, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
+                  unsigned long long* total_rays);
+void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
+                  FrameCounters* fc, uint32_t segment, Planes planes);
+// standalone traversal of caller rays (tests/tools)
+void launch_trace_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
+void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor);
+
+int trace_grid_size(int device);
+int shade_grid_size(int device);
+
+}  // namespace ptc

@@ -1,0 +1,492 @@
+// pt_step.cu — the RTStep lifecycle behind the C ABI (include/ptcore.h).
+// Replaces src/render_steps/pt.rs (create / update / render / resize) of the reference.
+#include "../../include/ptcore.h"
+#include "bvh_build.h"
+#include "scene_prep.h"
+#include "pt_kernels.cuh"
+#include "pt_error.h"
+
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptc;
+
+namespace ptc {
+thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+            return e_ == cudaErrorMemoryAllocation ? PTC_ERR_OOM : PTC_ERR_CUDA;                     \
+        }                                                                                            \
+    } while (0)
+
+struct ptc_step {
+    int device = 0;
+    ptc_config cfg{};
+    ptc_uniforms uniforms{};
+    bool have_uniforms = false;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t snap_ready = nullptr, copy_done = nullptr;
+
+    // scene (device)
+    F4* d_nodes = nullptr; F4* d_tris = nullptr; TriShade* d_shade = nullptr;
+    MatDev* d_mats = nullptr; TexDev* d_texs = nullptr; ptc_triangle* d_lights = nullptr;
+    std::vector<cudaArray_t> arrays; std::vector<cudaTextureObject_t> tex_objs;
+    DevScene scene{};
+    uint32_t num_lights = 0;
+    // host tables for HIT_ID conversion
+    std::vector<uint32_t> tri_mesh; std::vector<ptc_mesh> meshes;
+    uint64_t bvh_info[8] = {0};
+
+    // frame buffers
+    Queue q[2]{}; U4* d_hits = nullptr;
+    FrameCounters* d_fc = nullptr;                 // ring of kFcRing counter blocks
+    uint32_t fc_next = 0;
+    unsigned long long* d_total_rays = nullptr;
+    Planes planes{}; F4* owned_color = nullptr; F4* d_snapshot = nullptr; size_t snapshot_bytes = 0;
+    uint32_t npix = 0;
+    int trace_grid = 0, shade_grid = 0;
+    uint64_t frames = 0, launches = 0;
+    // optional per-stage timing (CUDA events on the render stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    std::vector<int> ev_tag;                       // tag of the stage that STARTS at event i (-1 = end of frame)
+    double prof_ms[3] = {0, 0, 0}; uint64_t prof_n[3] = {0, 0, 0};   // 0 raygen, 1 trace, 2 shade
+};
+
+static void prof_mark(ptc_step* s, int tag) {
+    if (!s->profiling) return;
+    if (s->ev_used == s->ev_pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; s->ev_pool.push_back(e); }
+    cudaEventRecord(s->ev_pool[s->ev_used++], s->stream);
+    s->ev_tag.push_back(tag);
+}
+static void prof_collect(ptc_step* s) {
+    if (s->ev_used == 0) return;
+    cudaStreamSynchronize(s->stream);
+    for (size_t i = 0; i + 1 < s->ev_used; ++i) {
+        int tag = s->ev_tag[i];
+        if (tag < 0) continue;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, s->ev_pool[i], s->ev_pool[i + 1]) == cudaSuccess) { s->prof_ms[tag] += ms; s->prof_n[tag]++; }
+    }
+    s->ev_used = 0; s->ev_tag.clear();
+}
+
+static const uint32_t kFcRing = 64;
+
+static void free_frame_buffers(ptc_step* s) {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->q[i].ray_o); cudaFree(s->q[i].ray_d); cudaFree(s->q[i].mask); cudaFree(s->q[i].acc);
+        s->q[i] = Queue{};
+    }
+    cudaFree(s->d_hits); s->d_hits = nullptr;
+    cudaFree(s->owned_color); s->owned_color = nullptr;
+    cudaFree(s->planes.depth); cudaFree(s->planes.normal); cudaFree(s->planes.albedo); cudaFree(s->planes.hit_tri);
+    cudaFree(s->d_snapshot); s->d_snapshot = nullptr; s->snapshot_bytes = 0;
+    s->planes = Planes{};
+}
+
+static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
+    if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull) { set_error("bad frame size"); return PTC_ERR_INVALID; }
+    uint32_t n = w * h;
+    s->npix = n; s->cfg.width = w; s->cfg.height = h;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&s->q[i].ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->q[i].ray_d, (size_t)n * 16));
+        CK(cudaMalloc(&s->q[i].mask, (size_t)n * 16)); CK(cudaMalloc(&s->q[i].acc, (size_t)n * 16));
+    }
+    CK(cudaMalloc(&s->d_hits, (size_t)n * 16));
+    CK(cudaMalloc(&s->owned_color, (size_t)n * 16));
+    CK(cudaMalloc(&s->planes.depth, (size_t)n * 4));
+    CK(cudaMalloc(&s->planes.normal, (size_t)n * 16));
+    CK(cudaMalloc(&s->planes.albedo, (size_t)n * 16));
+    CK(cudaMalloc(&s->planes.hit_tri, (size_t)n * 4));
+    s->planes.color = s->owned_color;
+    CK(cudaMemsetAsync(s->owned_color, 0, (size_t)n * 16, s->stream));
+    CK(cudaMemsetAsync(s->planes.depth, 0, (size_t)n * 4, s->stream));
+    CK(cudaMemsetAsync(s->planes.normal, 0, (size_t)n * 16, s->stream));
+    CK(cudaMemsetAsync(s->planes.albedo, 0, (size_t)n * 16, s->stream));
+    CK(cudaMemsetAsync(s->planes.hit_tri, 0xFF, (size_t)n * 4, s->stream));
+    return PTC_OK;
+}
+
+static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
+    PreparedScene ps;
+    int rc = prepare_scene(v, s->cfg, ps);
+    if (rc != PTC_OK) return rc;
+    s->meshes = ps.meshes; s->tri_mesh = ps.tri_mesh;
+    const DevBvh2& dev = ps.bvh;
+    s->bvh_info[0] = dev.nodes.size(); s->bvh_info[1] = dev.tris.size();
+    s->bvh_info[2] = dev.nodes.size() * sizeof(DevNode2); s->bvh_info[3] = dev.tris.size() * sizeof(DevTri);
+    s->bvh_info[4] = ps.max_depth; s->bvh_info[5] = (uint64_t)ps.build_ms;
+    if (!dev.nodes.empty()) {
+        CK(cudaMalloc(&s->d_nodes, dev.nodes.size() * sizeof(DevNode2)));
+        CK(cudaMemcpy(s->d_nodes, dev.nodes.data(), dev.nodes.size() * sizeof(DevNode2), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&s->d_tris, dev.tris.size() * sizeof(DevTri)));
+        CK(cudaMemcpy(s->d_tris, dev.tris.data(), dev.tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
+    }
+    if (!ps.shade.empty()) {
+        CK(cudaMalloc(&s->d_shade, ps.shade.size() * sizeof(TriShade)));
+        CK(cudaMemcpy(s->d_shade, ps.shade.data(), ps.shade.size() * sizeof(TriShade), cudaMemcpyHostToDevice));
+    }
+
+    // textures: bindless table of texture objects over cudaArrays (texture.rs:232-336)
+    std::vector<TexDev> texs(v->num_textures);
+    s->arrays.assign(v->num_textures, nullptr); s->tex_objs.assign(v->num_textures, 0);
+    for (uint64_t i = 0; i < v->num_textures; ++i) {
+        const ptc_texture_desc& t = v->textures[i];
+        TexDev& d = texs[i]; std::memset(&d, 0, sizeof(d));
+        d.w = t.width; d.h = t.height; d.fmt = t.format;
+        cudaChannelFormatDesc cd = t.format == PTC_TEXEL_RGBA8 ? cudaCreateChannelDesc<uchar4>() : cudaCreateChannelDesc<float4>();
+        size_t texel_bytes = t.format == PTC_TEXEL_RGBA8 ? 4 : 16;
+        CK(cudaMallocArray(&s->arrays[i], &cd, t.width, t.height));
+        CK(cudaMemcpy2DToArray(s->arrays[i], 0, 0, t.texels, (size_t)t.width * texel_bytes, (size_t)t.width * texel_bytes, t.height, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = s->arrays[i];
+        cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;   // Repeat is applied in integer texel space (pt_bilinear_axis)
+        td.filterMode = cudaFilterModePoint;                             // fp32 bilinear weights are applied in the kernel
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&s->tex_objs[i], &rd, &td, nullptr));
+        d.obj = (unsigned long long)s->tex_objs[i];
+    }
+    if (!texs.empty()) {
+        CK(cudaMalloc(&s->d_texs, texs.size() * sizeof(TexDev)));
+        CK(cudaMemcpy(s->d_texs, texs.data(), texs.size() * sizeof(TexDev), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&s->d_mats, ps.mats.size() * sizeof(MatDev)));
+    CK(cudaMemcpy(s->d_mats, ps.mats.data(), ps.mats.size() * sizeof(MatDev), cudaMemcpyHostToDevice));
+    s->num_lights = (uint32_t)ps.lights.size();
+    CK(cudaMalloc(&s->d_lights, ps.lights.size() * sizeof(ptc_triangle)));
+    CK(cudaMemcpy(s->d_lights, ps.lights.data(), ps.lights.size() * sizeof(ptc_triangle), cudaMemcpyHostToDevice));
+
+    DevScene& ds = s->scene;
+    ds.nodes = s->d_nodes; ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
+    ds.num_nodes = (uint32_t)dev.nodes.size(); ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
+    return PTC_OK;
+}
+
+static void destroy_step(ptc_step* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    free_frame_buffers(s);
+    for (auto o : s->tex_objs) if (o) cudaDestroyTextureObject(o);
+    for (auto a : s->arrays) if (a) cudaFreeArray(a);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_shade); cudaFree(s->d_mats); cudaFree(s->d_texs); cudaFree(s->d_lights);
+    cudaFree(s->d_fc); cudaFree(s->d_total_rays);
+    for (auto e : s->ev_pool) cudaEventDestroy(e);
+    if (s->snap_ready) cudaEventDestroy(s->snap_ready);
+    if (s->copy_done) cudaEventDestroy(s->copy_done);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    delete s;
+}
+
+extern "C" {
+
+PTC_API int ptc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, int cuda_device, ptc_step** out) {
+    if (!scene || !config || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
+    *out = nullptr;
+    if (config->samples_per_pixel != 1) { set_error("samples_per_pixel must be 1 (SAMPLES_PER_PIXEL, shader_definitions.rs:17); call ptc_render once per sample"); return PTC_ERR_INVALID; }
+    if (config->max_bounces + 1 > PTC_MAX_SEGMENTS) { set_error("max_bounces too large"); return PTC_ERR_INVALID; }
+    if (config->accum_mode > PTC_ACCUM_SUM) { set_error("bad accum_mode"); return PTC_ERR_INVALID; }
+    int ndev = ptc_device_count();
+    if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
+    if (cuda_device < 0 || cuda_device >= ndev) { set_error("cuda_device out of range"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(cuda_device));
+    ptc_step* s = new ptc_step();
+    s->device = cuda_device; s->cfg = *config;
+    int rc = PTC_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
+        if ((rc = upload_scene(s, scene)) != PTC_OK) break;
+        if ((rc = alloc_frame_buffers(s, config->width, config->height)) != PTC_OK) break;
+        if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
+        cudaMemsetAsync(s->d_total_rays, 0, 8, s->stream);
+        s->trace_grid = trace_grid_size(cuda_device);
+        s->shade_grid = shade_grid_size(cuda_device);
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
+    } while (0);
+    if (rc != PTC_OK) { destroy_step(s); return rc; }
+    *out = s;
+    return PTC_OK;
+}
+
+PTC_API int ptc_update(ptc_step* s, const ptc_uniforms* u) {
+    if (!s || !u) { set_error("null argument"); return PTC_ERR_INVALID; }
+    s->uniforms = *u;
+    s->uniforms.num_lights = s->num_lights;            // pt.rs:243
+    s->have_uniforms = true;
+    return PTC_OK;
+}
+
+PTC_API int ptc_render(ptc_step* s) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    if (!s->have_uniforms) { set_error("ptc_render before ptc_update"); return PTC_ERR_INVALID; }
+    if (s->uniforms.camera.width != s->cfg.width || s->uniforms.camera.height != s->cfg.height) { set_error("uniform size differs from step size; call ptc_resize"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    FrameCounters* fc = s->d_fc + (s->fc_next++ % kFcRing);
+    CK(cudaMemsetAsync(fc, 0, sizeof(FrameCounters), s->stream));
+    PathCfg pc; pc.width = s->cfg.width; pc.height = s->cfg.height; pc.max_bounces = s->cfg.max_bounces;
+    pc.send_to_light_probability = s->cfg.send_to_light_probability; pc.accum_mode = s->cfg.accum_mode; pc.is_grabbed = s->uniforms.is_grabbed;
+    if (s->profiling && s->ev_used > 60000) prof_collect(s);
+    prof_mark(s, 0);
+    launch_raygen(s->stream, s->uniforms, s->q[0], fc, s->npix);
+    s->launches++;
+    for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
+        prof_mark(s, 1);
+        launch_trace(s->stream, s->trace_grid, s->scene, s->q[seg & 1], s->d_hits, fc, seg, s->d_total_rays);
+        prof_mark(s, 2);
+        launch_shade(s->stream, s->shade_grid, s->scene, pc, s->q[seg & 1], s->q[(seg + 1) & 1], s->d_hits, fc, seg, s->planes);
+        s->launches += 2;
+    }
+    prof_mark(s, -1);
+    CK(cudaGetLastError());
+    s->frames++;
+    return PTC_OK;
+}
+
+PTC_API int ptc_poll(ptc_step* s, int wait) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    if (wait) { CK(cudaStreamSynchronize(s->stream)); CK(cudaStreamSynchronize(s->copy_stream)); return PTC_OK; }
+    cudaError_t e = cudaStreamQuery(s->stream);
+    if (e == cudaErrorNotReady) return PTC_ERR_NOT_READY;
+    CK(e);
+    e = cudaStreamQuery(s->copy_stream);
+    if (e == cudaErrorNotReady) return PTC_ERR_NOT_READY;
+    CK(e);
+    return PTC_OK;
+}
+
+PTC_API int ptc_resize(ptc_step* s, uint32_t w, uint32_t h) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream)); CK(cudaStreamSynchronize(s->copy_stream));
+    free_frame_buffers(s);
+    int rc = alloc_frame_buffers(s, w, h);
+    if (rc != PTC_OK) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    return PTC_OK;
+}
+
+PTC_API int ptc_set_output(ptc_step* s, void* device_rgba32f) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->planes.color = device_rgba32f ? (F4*)device_rgba32f : s->owned_color;
+    return PTC_OK;
+}
+
+PTC_API int ptc_reset_accumulation(ptc_step* s) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->planes.color, 0, (size_t)s->npix * 16, s->stream));
+    return PTC_OK;
+}
+
+PTC_API void ptc_destroy(ptc_step* s) { destroy_step(s); }
+
+static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
+    switch (plane) {
+        case PTC_PLANE_COLOR: *p = s->planes.color; *px_bytes = 16; return true;
+        case PTC_PLANE_DEPTH: *p = s->planes.depth; *px_bytes = 4; return true;
+        case PTC_PLANE_NORMAL: *p = s->planes.normal; *px_bytes = 16; return true;
+        case PTC_PLANE_ALBEDO: *p = s->planes.albedo; *px_bytes = 16; return true;
+        case PTC_PLANE_HIT_ID: *p = s->planes.hit_tri; *px_bytes = 4; return true;
+    }
+    return false;
+}
+
+PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
+    if (!s || !dst) { set_error("null argument"); return PTC_ERR_INVALID; }
+    void* src; size_t pb;
+    if (!plane_ptr(s, plane, &src, &pb)) { set_error("unknown plane"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const uint32_t W = s->cfg.width, H = s->cfg.height;
+    if (plane == PTC_PLANE_HIT_ID) {
+        // device keeps the global triangle id; (instance_index, geometry_index) = (mesh, triangle inside the mesh), pt.rs:409-427,527-542
+        std::vector<uint32_t> tri((size_t)s->npix);
+        CK(cudaMemcpyAsync(tri.data(), src, (size_t)s->npix * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        size_t row = pitch ? pitch : (size_t)W * 8;
+        for (uint32_t y = 0; y < H; ++y) {
+            uint32_t* o = (uint32_t*)((char*)dst + (size_t)y * row);
+            for (uint32_t x = 0; x < W; ++x) {
+                uint32_t t = tri[(size_t)y * W + x];
+                if (t == 0xFFFFFFFFu || t >= s->tri_mesh.size()) { o[x * 2] = o[x * 2 + 1] = 0xFFFFFFFFu; continue; }
+                uint32_t m = s->tri_mesh[t];
+                o[x * 2] = m; o[x * 2 + 1] = t - s->meshes[m].index_offset / 3;
+            }
+        }
+        return PTC_OK;
+    }
+    size_t row = (size_t)W * pb;
+    CK(cudaMemcpy2DAsync(dst, pitch ? pitch : row, src, row, row, H, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return PTC_OK;
+}
+
+PTC_API int ptc_read_async(ptc_step* s, int plane, void* dst_pinned) {
+    if (!s || !dst_pinned) { set_error("null argument"); return PTC_ERR_INVALID; }
+    void* src; size_t pb;
+    if (plane == PTC_PLANE_HIT_ID || !plane_ptr(s, plane, &src, &pb)) { set_error("plane not readable asynchronously"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    size_t bytes = (size_t)s->npix * pb;
+    if (s->snapshot_bytes < bytes) {
+        CK(cudaStreamSynchronize(s->copy_stream));
+        cudaFree(s->d_snapshot); s->d_snapshot = nullptr; s->snapshot_bytes = 0;
+        CK(cudaMalloc(&s->d_snapshot, bytes)); s->snapshot_bytes = bytes;
+    }
+    // the previous host copy must have drained the snapshot before it is overwritten
+    CK(cudaStreamWaitEvent(s->stream, s->copy_done, 0));
+    CK(cudaMemcpyAsync(s->d_snapshot, src, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaEventRecord(s->snap_ready, s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->snap_ready, 0));
+    CK(cudaMemcpyAsync(dst_pinned, s->d_snapshot, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->copy_done, s->copy_stream));
+    return PTC_OK;
+}
+
+PTC_API int ptc_read_wait(ptc_step* s) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->copy_stream));
+    return PTC_OK;
+}
+
+PTC_API void* ptc_device_ptr(ptc_step* s, int plane) {
+    if (!s) return nullptr;
+    void* p; size_t pb;
+    return plane_ptr(s, plane, &p, &pb) ? p : nullptr;
+}
+
+PTC_API void* ptc_stream(ptc_step* s) { return s ? (void*)s->stream : nullptr; }
+
+PTC_API int ptc_get_stats(ptc_step* s, ptc_stats* out) {
+    if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    std::memset(out, 0, sizeof(*out));
+    unsigned long long rays = 0;
+    CK(cudaMemcpyAsync(&rays, s->d_total_rays, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    out->rays_traced = rays; out->frames_rendered = s->frames; out->kernel_launches = s->launches;
+    return PTC_OK;
+}
+
+PTC_API int ptc_set_profiling(ptc_step* s, int enable) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    prof_collect(s);
+    s->profiling = enable != 0;
+    for (int k = 0; k < 3; ++k) { s->prof_ms[k] = 0.0; s->prof_n[k] = 0; }
+    return PTC_OK;
+}
+
+PTC_API int ptc_get_profile(ptc_step* s, double ms[3], uint64_t launches[3]) {
+    if (!s || !ms || !launches) { set_error("null argument"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    prof_collect(s);
+    for (int k = 0; k < 3; ++k) { ms[k] = s->prof_ms[k]; launches[k] = s->prof_n[k]; }
+    return PTC_OK;
+}
+
+PTC_API int ptc_num_lights(ptc_step* s, uint32_t* out) {
+    if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
+    *out = s->num_lights; return PTC_OK;
+}
+
+PTC_API int ptc_bvh_info(ptc_step* s, uint64_t out[8]) {
+    if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
+    std::memcpy(out, s->bvh_info, sizeof(s->bvh_info)); return PTC_OK;
+}
+
+static int upload_rays(ptc_step* s, const float* rays, uint64_t n, F4** d_o, F4** d_d) {
+    std::vector<F4> o(n), d(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        o[i] = F4{rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2], rays[i * 8 + 3]};
+        d[i] = F4{rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6], rays[i * 8 + 7]};
+    }
+    CK(cudaMalloc(d_o, n * 16)); CK(cudaMalloc(d_d, n * 16));
+    CK(cudaMemcpyAsync(*d_o, o.data(), n * 16, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(*d_d, d.data(), n * 16, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return PTC_OK;
+}
+
+PTC_API int ptc_trace_rays(ptc_step* s, const float* rays, uint64_t n, uint32_t* hits, uint32_t* ids) {
+    if (!s || !rays || !hits) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (n == 0) return PTC_OK;
+    if (n > 0x7fffffffull) { set_error("too many rays"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    F4 *d_o = nullptr, *d_d = nullptr; U4* d_h = nullptr; uint32_t* d_cur = nullptr;
+    int rc = upload_rays(s, rays, n, &d_o, &d_d);
+    if (rc == PTC_OK) {
+        do {
+            if (cudaMalloc(&d_h, n * 16) != cudaSuccess || cudaMalloc(&d_cur, 8) != cudaSuccess) { set_error("trace_rays: allocation failed"); rc = PTC_ERR_OOM; break; }
+            cudaMemsetAsync(d_cur, 0, 8, s->stream);
+            launch_trace_n(s->stream, s->trace_grid, s->scene, d_o, d_d, d_h, (uint32_t)n, d_cur);
+            s->launches += 2;
+            if (cudaMemcpyAsync(hits, d_h, n * 16, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+                set_error(std::string("trace_rays: ") + cudaGetErrorString(cudaGetLastError())); rc = PTC_ERR_CUDA; break;
+            }
+        } while (0);
+    }
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_h); cudaFree(d_cur);
+    if (rc != PTC_OK) return rc;
+    if (ids) {
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t t = hits[i * 4 + 3];
+            if (t == 0xFFFFFFFFu || t >= s->tri_mesh.size()) { ids[i * 2] = ids[i * 2 + 1] = 0xFFFFFFFFu; continue; }
+            uint32_t m = s->tri_mesh[t]; ids[i * 2] = m; ids[i * 2 + 1] = t - s->meshes[m].index_offset / 3;
+        }
+    }
+    for (uint64_t i = 0; i < n; ++i)
+        if (hits[i * 4 + 3] == 0xFFFFFFFFu) hits[i * 4] = hits[i * 4 + 1] = hits[i * 4 + 2] = 0;   // miss: t,b1,b2 reported as 0
+    return PTC_OK;
+}
+
+PTC_API int ptc_trace_rays_any(ptc_step* s, const float* rays, uint64_t n, uint8_t* occluded) {
+    if (!s || !rays || !occluded) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (n == 0) return PTC_OK;
+    if (n > 0x7fffffffull) { set_error("too many rays"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    F4 *d_o = nullptr, *d_d = nullptr; uint8_t* d_occ = nullptr; uint32_t* d_cur = nullptr;
+    int rc = upload_rays(s, rays, n, &d_o, &d_d);
+    if (rc == PTC_OK) {
+        do {
+            if (cudaMalloc(&d_occ, n) != cudaSuccess || cudaMalloc(&d_cur, 8) != cudaSuccess) { set_error("trace_rays_any: allocation failed"); rc = PTC_ERR_OOM; break; }
+            cudaMemsetAsync(d_cur, 0, 8, s->stream);
+            launch_trace_any_n(s->stream, s->trace_grid, s->scene, d_o, d_d, d_occ, (uint32_t)n, d_cur);
+            s->launches += 1;
+            if (cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+                set_error(std::string("trace_rays_any: ") + cudaGetErrorString(cudaGetLastError())); rc = PTC_ERR_CUDA; break;
+            }
+        } while (0);
+    }
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_occ); cudaFree(d_cur);
+    return rc;
+}
+
+PTC_API const char* ptc_last_error(void) { return g_last_error.c_str(); }
+PTC_API const char* ptc_version(void) { return "ptcore 0.1 (sm_100a)"; }
+
+}  // extern "C"

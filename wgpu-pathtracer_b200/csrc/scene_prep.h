@@ -1,0 +1,31 @@
+// scene_prep.h — host-side preparation of the device scene: validation, BVH build, per-triangle
+// shading records, constant-folded materials, emissive-triangle list.  Produces host vectors that
+// pt_step.cu uploads verbatim (and that the CPU-only test harness in tests/hostemu consumes directly).
+// Restates the host half of RTStep::create / create_static_bind_groups (reference:
+// src/render_steps/pt.rs:188-243,341-433).
+#pragma once
+#include "../../include/ptcore_types.h"
+#include "bvh_build.h"
+#include "pt_device.cuh"
+
+#include <string>
+#include <vector>
+
+namespace ptc {
+
+struct PreparedScene {
+    DevBvh2 bvh;                          // device-layout nodes + leaf-ordered triangles
+    std::vector<TriShade> shade;          // global triangle order
+    std::vector<MatDev> mats;
+    std::vector<ptc_triangle> lights;     // never empty (dummy entry, pt.rs:232-239)
+    std::vector<uint32_t> tri_mesh;       // global triangle -> mesh (instance_index)
+    std::vector<ptc_mesh> meshes;
+    uint32_t num_tris = 0;
+    uint32_t max_depth = 0;
+    double build_ms = 0.0;
+};
+
+// returns PTC_OK or a negative ptc_status with set_error() called
+int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene& out);
+
+}  // namespace ptc
