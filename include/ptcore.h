@@ -114,6 +114,12 @@ PTC_API int ptc_trace_rays(ptc_step* step, const float* rays, uint64_t n, uint32
  * rays[i*8+7] carries tmax_i (<= 0 means PT_RAY_TMAX) */
 PTC_API int ptc_trace_rays_any(ptc_step* step, const float* rays, uint64_t n, uint8_t* occluded);
 
+/* evaluate one of the shared numerics primitives of include/ptmath.h ON THE DEVICE for n inputs (unit-test
+ * entry: device results must equal the host's bit for bit).  fn: 0 sin, 1 cos, 2 atan, 3 acos, 4 atan2(a,b),
+ * 5 a/b, 6 sqrt, 7 fma(a,b,a), 8 rand_float of state bits a, 9 normalize probe, 10 refract probe,
+ * 11 a*b+a (uncontracted), 12 bilinear address probe. */
+PTC_API int ptc_debug_math(int cuda_device, int fn, const float* a, const float* b, float* out, uint64_t n);
+
 PTC_API const char* ptc_last_error(void);
 PTC_API const char* ptc_version(void);
 PTC_API int ptc_device_count(void);

@@ -149,6 +149,6 @@ def math_fn(fn, a, b=None):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b if b is not None else np.zeros_like(a), dtype=np.float32)
     out = np.zeros_like(a)
-    code = {"sin": 0, "cos": 1, "atan": 2, "acos": 3, "atan2": 4}[fn]
+    code = fn if isinstance(fn, int) else {"sin": 0, "cos": 1, "atan": 2, "acos": 3, "atan2": 4}[fn]
     lib().orc_math(code, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), a.size)
     return out

@@ -775,6 +775,14 @@ void orc_math(int fn, const float* a, const float* b, float* out, uint64_t n) {
             case 2: out[i] = pt_atan(a[i]); break;
             case 3: out[i] = pt_acos(a[i]); break;
             case 4: out[i] = pt_atan2(a[i], b[i]); break;
+            case 5: out[i] = pt_div(a[i], b[i]); break;
+            case 6: out[i] = pt_sqrt(a[i]); break;
+            case 7: out[i] = pt_fma(a[i], b[i], a[i]); break;
+            case 8: { Rng r; std::memcpy(&r.state, &a[i], 4); out[i] = rand_float(r); break; }
+            case 9: { pt_v3 v = pt_normalize(pt_mk3(a[i], b[i], a[i] * b[i])); out[i] = v.x + v.y + v.z; break; }
+            case 10: { pt_v3 v = pt_refract(pt_normalize(pt_mk3(a[i], b[i], 0.5f)), pt_normalize(pt_mk3(b[i], -a[i], 1.0f)), 1.5f); out[i] = v.x + v.y + v.z; break; }
+            case 11: out[i] = a[i] * b[i] + a[i]; break;
+            case 12: { int i0, i1; float f; pt_bilinear_axis(a[i], 37, &i0, &i1, &f); out[i] = f + (float)i0 + 64.0f * (float)i1; break; }
             default: out[i] = 0.0f;
         }
     }

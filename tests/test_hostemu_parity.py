@@ -1,0 +1,114 @@
+"""CPU-only parity: the product's device functions (csrc/pt_device.cuh compiled for the host by tests/hostemu) and
+its BVH builder against the oracle.  Bit-exact on every plane — what the -m gpu tests then confirm for the kernels."""
+import numpy as np
+import pytest
+
+
+def both(ptc, standins, oracle, hostemu, scene, cam, W, H, frames, **kw):
+    cfg = ptc.make_config(W, H, **kw)
+    camera = standins.make_camera(cam, W, H)
+    orc, emu = oracle.OracleScene(scene, cfg), hostemu.scene(scene, cfg)
+    ro = re = None
+    for f in range(1, frames + 1):
+        u = camera.uniforms(frame=f)
+        ro = orc.render_frame(u, None if ro is None else ro["color"])
+        re = emu.render_frame(u, None if re is None else re["color"])
+    return ro, re
+
+
+def assert_identical(ro, re):
+    for k in ("hit_id", "color", "depth", "normal", "albedo"):
+        assert np.array_equal(ro[k], re[k], equal_nan=True), k
+    assert ro["rays"] == re["rays"]
+
+
+def test_cornell_depth8(ptc, standins, oracle, hostemu):
+    scene, cam = standins.cornell()
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 160, 160, 3, max_bounces=8)
+    assert_identical(ro, re)
+    assert ro["rays"] > 160 * 160 * 3
+
+
+def test_cornell_without_normals_reference_bug(ptc, standins, oracle, hostemu):
+    """OBJ without vn: scene.rs:202-215 corrupts normals -> NaN radiance in both, at the same pixels."""
+    scene, cam = standins.cornell(with_normals=False)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 64, 64, 1)
+    assert_identical(ro, re)
+    fixed, _ = standins.cornell(with_normals=False, fix_normals=True)
+    ro2, re2 = both(ptc, standins, oracle, hostemu, fixed, cam, 64, 64, 1)
+    assert_identical(ro2, re2)
+    assert np.isfinite(ro2["color"]).all()
+    assert np.array_equal(ro["hit_id"], ro2["hit_id"])                 # geometry identical, only normals differ
+
+
+@pytest.mark.parametrize("nee", [0.0, 0.5, 1.0])
+def test_soup_textured_all_branches(ptc, standins, oracle, hostemu, nee):
+    scene, cam = standins.random_soup(5000, seed=7, textured=True)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 200, 120, 2, max_bounces=6, send_to_light_probability=nee)
+    assert_identical(ro, re)
+
+
+def test_sum_mode(ptc, standins, oracle, hostemu):
+    scene, cam = standins.cornell()
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 48, 48, 3, accum_mode=ptc.types.ACCUM_SUM)
+    assert_identical(ro, re)
+    assert (ro["color"][..., 3] == 3).all()
+
+
+def test_sponza_standin_band(ptc, standins, oracle, hostemu):
+    scene, cam = standins.sponza(tex_size=128)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 384, 216, 2)
+    assert_identical(ro, re)
+    assert (ro["hit_id"][..., 0] != 0xFFFFFFFF).mean() > 0.9
+
+
+def test_trace_rays_product_bvh_vs_brute(ptc, standins, oracle, hostemu):
+    from conftest import random_rays
+    scene, _ = standins.random_soup(30000, seed=11, textured=False, tri_size=0.12)
+    cfg = ptc.make_config(4, 4)
+    orc, emu = oracle.OracleScene(scene, cfg), hostemu.scene(scene, cfg)
+    rays = random_rays(60000, 21)
+    he, ie = emu.trace_rays(rays)
+    ho, io, _ = orc.trace_rays(rays[:3000], brute=True)                 # brute force on a subset, BVH oracle on all
+    assert np.array_equal(he[:3000], ho) and np.array_equal(ie[:3000], io)
+    hv, iv, _ = orc.trace_rays(rays)
+    assert np.array_equal(he, hv) and np.array_equal(ie, iv)
+    assert np.array_equal(emu.trace_rays_any(rays), (hv[:, 3] != 0xFFFFFFFF).astype(np.uint8))
+    info = emu.bvh_info()
+    assert info["triangles"] == 30000 and info["max_depth"] < 64
+
+
+def test_axis_parallel_and_degenerate_rays(ptc, standins, oracle, hostemu):
+    """Direction components that are exactly 0, -0 or tiny: the fma slab test must stay conservative."""
+    scene, _ = standins.sponza(tex_size=16)
+    cfg = ptc.make_config(4, 4)
+    orc, emu = oracle.OracleScene(scene, cfg), hostemu.scene(scene, cfg)
+    rng = np.random.RandomState(3)
+    n = 6000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform([-14, 0.2, -5.5], [14, 13, 5.5], size=(n, 3))
+    d = rng.randn(n, 3)
+    kind = rng.randint(0, 6, n)
+    for k in range(n):
+        ax = rng.randint(0, 3)
+        if kind[k] == 0: d[k, ax] = 0.0
+        elif kind[k] == 1: d[k, ax] = -0.0
+        elif kind[k] == 2: d[k, ax] = 1e-30
+        elif kind[k] == 3: d[k, ax] = 1e-7 * rng.randn()
+        elif kind[k] == 4: d[k] = 0; d[k, ax] = rng.choice([-1.0, 1.0])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d
+    he, ie = emu.trace_rays(rays)
+    hv, iv, _ = orc.trace_rays(rays, brute=True)
+    assert np.array_equal(he, hv) and np.array_equal(ie, iv)
+
+
+def test_empty_and_single_triangle_scenes(ptc, standins, oracle, hostemu):
+    scene, cam = standins.empty()
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 32, 24, 1)
+    assert_identical(ro, re)
+    sc = ptc.Scene(standins.make_envmap(32, 16))
+    sc.add_mesh(np.array([[2, -1, -1], [2, 1, -1], [2, 0, 1.5]], np.float32), np.tile([-1, 0, 0], (3, 1)), None, [0, 1, 2], 0)
+    ro, re = both(ptc, standins, oracle, hostemu, sc, {"position": (0, 0, 0), "fov": 60.0, "target": (1, 0, 0)}, 32, 24, 2)
+    assert_identical(ro, re)
+    assert (ro["hit_id"][..., 0] == 0).any()

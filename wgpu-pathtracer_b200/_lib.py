@@ -51,6 +51,7 @@ def lib():
         "ptc_bvh_info": (i32, [vp, P(u64)]),
         "ptc_trace_rays": (i32, [vp, vp, u64, vp, vp]),
         "ptc_trace_rays_any": (i32, [vp, vp, u64, vp]),
+        "ptc_debug_math": (i32, [i32, i32, vp, vp, vp, u64]),
         "ptc_last_error": (C.c_char_p, []),
         "ptc_version": (C.c_char_p, []),
         "ptc_device_count": (i32, []),

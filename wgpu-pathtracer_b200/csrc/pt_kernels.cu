@@ -135,6 +135,33 @@ void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* 
     k_trace_any<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, occluded, n, cursor);
 }
 
+// ---- device evaluation of the shared numerics primitives (unit-test entry: host and device must agree bit for bit) ----
+__global__ void k_math(int fn, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = a[i], y = b[i], r = 0.0f;
+    switch (fn) {
+        case 0: r = pt_sin(x); break;
+        case 1: r = pt_cos(x); break;
+        case 2: r = pt_atan(x); break;
+        case 3: r = pt_acos(x); break;
+        case 4: r = pt_atan2(x, y); break;
+        case 5: r = pt_div(x, y); break;
+        case 6: r = pt_sqrt(x); break;
+        case 7: r = pt_fma(x, y, x); break;
+        case 8: { uint32_t s = __float_as_uint(x); r = rng_next_f32(s); break; }
+        case 9: { pt_v3 v = pt_normalize(pt_mk3(x, y, x * y)); r = v.x + v.y + v.z; break; }
+        case 10: { pt_v3 v = pt_refract(pt_normalize(pt_mk3(x, y, 0.5f)), pt_normalize(pt_mk3(y, -x, 1.0f)), 1.5f); r = v.x + v.y + v.z; break; }
+        case 11: r = x * y + x; break;                 /* must NOT be contracted (-fmad=false) */
+        case 12: { int i0, i1; float f; pt_bilinear_axis(x, 37, &i0, &i1, &f); r = f + (float)i0 + 64.0f * (float)i1; break; }
+        default: break;
+    }
+    out[i] = r;
+}
+void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n) {
+    k_math<<<(n + 255) / 256, 256, 0, st>>>(fn, a, b, out, n);
+}
+
 static int persistent_grid(const void* kernel, int threads, int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

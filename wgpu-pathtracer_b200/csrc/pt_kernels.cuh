@@ -46,6 +46,8 @@ void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& c
 void launch_trace_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor);
 
+void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n);
+
 int trace_grid_size(int device);
 int shade_grid_size(int device);
 

@@ -7,6 +7,8 @@
 #include "pt_error.h"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,7 +76,10 @@ static void prof_collect(ptc_step* s) {
         int tag = s->ev_tag[i];
         if (tag < 0) continue;
         float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, s->ev_pool[i], s->ev_pool[i + 1]) == cudaSuccess) { s->prof_ms[tag] += ms; s->prof_n[tag]++; }
+        if (cudaEventElapsedTime(&ms, s->ev_pool[i], s->ev_pool[i + 1]) == cudaSuccess) {
+            s->prof_ms[tag] += ms; s->prof_n[tag]++;
+            if (getenv("PTC_DEBUG_LAUNCH_TIMES")) fprintf(stderr, "[ptc] stage %d: %.3f ms\n", tag, ms);
+        }
     }
     s->ev_used = 0; s->ev_tag.clear();
 }
@@ -483,6 +488,22 @@ PTC_API int ptc_trace_rays_any(ptc_step* s, const float* rays, uint64_t n, uint8
         } while (0);
     }
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_occ); cudaFree(d_cur);
+    return rc;
+}
+
+PTC_API int ptc_debug_math(int cuda_device, int fn, const float* a, const float* b, float* out, uint64_t n) {
+    if (!a || !b || !out || n == 0 || n > 0x7fffffffull) { set_error("bad argument"); return PTC_ERR_INVALID; }
+    if (ptc_device_count() <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
+    CK(cudaSetDevice(cuda_device));
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    int rc = PTC_OK;
+    if (cudaMalloc(&da, n * 4) != cudaSuccess || cudaMalloc(&db, n * 4) != cudaSuccess || cudaMalloc(&dout, n * 4) != cudaSuccess) { set_error("debug_math: allocation failed"); rc = PTC_ERR_OOM; }
+    if (rc == PTC_OK) {
+        cudaMemcpy(da, a, n * 4, cudaMemcpyHostToDevice); cudaMemcpy(db, b, n * 4, cudaMemcpyHostToDevice);
+        launch_math(nullptr, fn, da, db, dout, (uint32_t)n);
+        if (cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error(std::string("debug_math: ") + cudaGetErrorString(cudaGetLastError())); rc = PTC_ERR_CUDA; }
+    }
+    cudaFree(da); cudaFree(db); cudaFree(dout);
     return rc;
 }
 
