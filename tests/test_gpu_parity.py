@@ -53,6 +53,22 @@ def test_device_present(ptc):
     assert ptc.lib().ptc_device_count() >= 1
 
 
+def test_device_primitives_match_host(ptc, oracle):
+    """include/ptmath.h evaluated on the device (nvcc -fmad=false) equals the host build (g++ -ffp-contract=off) bit for bit."""
+    import ctypes as C
+    rng = np.random.RandomState(0)
+    n = 1 << 18
+    sets = [(rng.uniform(-8, 8, n), rng.uniform(-8, 8, n), range(13)), (rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), range(13)),
+            (rng.randint(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32), rng.uniform(0.1, 3, n), [8])]
+    for a, b, fns in sets:
+        a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+        for fn in fns:
+            out = np.zeros(n, np.float32)
+            assert ptc.lib().ptc_debug_math(0, fn, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n) == 0
+            ref = oracle.math_fn(fn, a, b)
+            assert np.array_equal(out, ref, equal_nan=True), f"primitive {fn} differs between device and host"
+
+
 def test_trace_rays_soup_bit_exact(ptc, standins, oracle):
     from conftest import random_rays
     scene, _ = standins.random_soup(20000, seed=5, textured=False)
@@ -74,7 +90,6 @@ def test_cornell_config_c1(ptc, standins, oracle):
     scene, cam = standins.cornell()
     step, ref = render_both(ptc, standins, oracle, scene, cam, 512, 512, 4, max_bounces=8)
     check_all_planes(ptc, step, ref)
-    assert step.stats()["rays_traced"] == 0 or True
     step.destroy()
 
 
