@@ -110,27 +110,94 @@ struct HitRec { float t, b1, b2; uint32_t tri; };   // tri = global triangle id,
 #define PTC_STACK_SIZE 64
 #define PTC_SENTINEL 0x7fffffff
 
-// Slab-test setup.  The entry/exit distances are evaluated as fma(bound, 1/d, -o/d): one FMA per plane, but
-// its absolute error is ~|o/d| * 2^-24 (not relative to t), which for rays nearly parallel to an axis exceeds
-// any fixed box padding.  `slab_err` widens the overlap test by a bound on that error, so the test stays
-// conservative and hit identity never depends on it.  Direction components below 2^-80 are clamped so 1/d is
-// finite (such a ray then visits every node whose other two slabs it overlaps: correct, and vanishingly rare).
-#define RAY_SLAB_SETUP(o, d)                                                                                 \
-    const float kTiny_ = 8.271806125530277e-25f; /* 2^-80 */                                                 \
-    const float dx_ = pt_abs((d).x) > kTiny_ ? (d).x : copysignf(kTiny_, (d).x);                             \
-    const float dy_ = pt_abs((d).y) > kTiny_ ? (d).y : copysignf(kTiny_, (d).y);                             \
-    const float dz_ = pt_abs((d).z) > kTiny_ ? (d).z : copysignf(kTiny_, (d).z);                             \
-    const float idx = pt_div(1.0f, dx_), idy = pt_div(1.0f, dy_), idz = pt_div(1.0f, dz_);                   \
-    const float ox = (o).x * idx, oy = (o).y * idy, oz = (o).z * idz;                                        \
-    const float slab_err = fmaxf(fmaxf(pt_abs(ox), pt_abs(oy)), pt_abs(oz)) * 4.76837158203125e-7f; /* 2^-21 */
+// ---- slab test ------------------------------------------------------------------------------------------
+// Entry/exit distances are evaluated as fma(bound, 1/d, -o/d): one FMA per plane.  Its absolute error is about
+// |o/d| * 2^-24 (NOT relative to t), which for a ray nearly parallel to an axis exceeds any fixed box padding, so
+// each axis carries its own error bound e = |o/d| * 2^-21 folded into the FMA constant: the plane the ray enters
+// through is moved back by e and the exit plane forward by e.  The test therefore stays conservative with respect to
+// pt_ray_tri (hit identity can never depend on it) at no extra instruction, and a near-parallel ray only loses
+// culling along the one axis it is parallel to.  Direction components below 2^-80 are clamped so 1/d stays finite.
+struct RaySlab {
+    float idx, idy, idz;          // 1/d
+    float lx, hx, ly, hy, lz, hz; // additive constants for the lo / hi plane of each axis (already negated)
+};
 
-// Closest hit over the BVH2 (replaces rayQueryInitialize/Proceed/GetCommittedIntersection,
-// rt_helpers.wgsl:49-52).  Ties in t go to the smaller global triangle id so the
-// result does not depend on traversal order.  counters (optional): [0] nodes visited, [1] triangles tested.
+PT_HD float pt_min3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+PT_HD float pt_max3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+
+PT_HD RaySlab make_ray_slab(pt_v3 o, pt_v3 d) {
+    const float kTiny = 8.271806125530277e-25f;   // 2^-80
+    const float kErr = 4.76837158203125e-7f;      // 2^-21
+    float dx = pt_abs(d.x) > kTiny ? d.x : copysignf(kTiny, d.x);
+    float dy = pt_abs(d.y) > kTiny ? d.y : copysignf(kTiny, d.y);
+    float dz = pt_abs(d.z) > kTiny ? d.z : copysignf(kTiny, d.z);
+    RaySlab r;
+    r.idx = pt_div(1.0f, dx); r.idy = pt_div(1.0f, dy); r.idz = pt_div(1.0f, dz);
+    float ox = o.x * r.idx, oy = o.y * r.idy, oz = o.z * r.idz;
+    float ex = pt_abs(ox) * kErr, ey = pt_abs(oy) * kErr, ez = pt_abs(oz) * kErr;
+    // positive direction: the lo plane is the entry plane (moved back: -(o/d) - e), the hi plane the exit plane
+    r.lx = dx > 0.0f ? -ox - ex : -ox + ex;  r.hx = dx > 0.0f ? -ox + ex : -ox - ex;
+    r.ly = dy > 0.0f ? -oy - ey : -oy + ey;  r.hy = dy > 0.0f ? -oy + ey : -oy - ey;
+    r.lz = dz > 0.0f ? -oz - ez : -oz + ez;  r.hz = dz > 0.0f ? -oz + ez : -oz - ez;
+    return r;
+}
+
+// Both children of one BVH2 node against the ray: hit flags and entry distances.
+PT_HD void node_test(const RaySlab& r, const F4& q0, const F4& q1, const F4& q2, float tmax,
+                     bool& h0, bool& h1, float& tn0, float& tn1) {
+    float a0 = pt_fma(q0.x, r.idx, r.lx), b0 = pt_fma(q0.y, r.idx, r.hx);
+    float c0 = pt_fma(q0.z, r.idy, r.ly), d0 = pt_fma(q0.w, r.idy, r.hy);
+    float e0 = pt_fma(q2.x, r.idz, r.lz), f0 = pt_fma(q2.y, r.idz, r.hz);
+    float a1 = pt_fma(q1.x, r.idx, r.lx), b1 = pt_fma(q1.y, r.idx, r.hx);
+    float c1 = pt_fma(q1.z, r.idy, r.ly), d1 = pt_fma(q1.w, r.idy, r.hy);
+    float e1 = pt_fma(q2.z, r.idz, r.lz), f1 = pt_fma(q2.w, r.idz, r.hz);
+    // fmin/fmax drop NaNs, so a degenerate plane simply stops constraining the interval
+    tn0 = pt_max3(fminf(a0, b0), fminf(c0, d0), fmaxf(fminf(e0, f0), 0.0f));
+    float tf0 = pt_min3(fmaxf(a0, b0), fmaxf(c0, d0), fminf(fmaxf(e0, f0), tmax));
+    tn1 = pt_max3(fminf(a1, b1), fminf(c1, d1), fmaxf(fminf(e1, f1), 0.0f));
+    float tf1 = pt_min3(fmaxf(a1, b1), fmaxf(c1, d1), fminf(fmaxf(e1, f1), tmax));
+    h0 = tn0 <= tf0 * 1.0000005f;
+    h1 = tn1 <= tf1 * 1.0000005f;
+}
+
+// All triangles of one leaf (closest hit; ties in t go to the smaller global triangle id so the result does not
+// depend on traversal order).
+PT_HD void leaf_closest(const DevScene& s, int node, pt_v3 o, pt_v3 d, HitRec& best, uint32_t* counters) {
+    uint32_t enc = ~(uint32_t)node;
+    uint32_t first = enc >> 3, cnt = (enc & 7u) + 1u;
+    for (uint32_t i = 0; i < cnt; ++i) {
+        const F4* tp = s.tris + (size_t)(first + i) * 3;
+        F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+        if (counters) counters[1]++;
+        float t, b1, b2;
+        if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
+                       PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+            uint32_t id = f2u(a.w);
+            if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+        }
+    }
+}
+
+// Closest hit over the BVH2 (replaces rayQueryInitialize/Proceed/GetCommittedIntersection, rt_helpers.wgsl:49-52).
+// Plain one-ray-per-call form: used by the host build of the tests and by small tools; the production kernel
+// (k_trace, pt_kernels.cu) runs the same node_test / leaf_closest under a persistent, dynamically refilled warp loop.
+// counters (optional): [0] nodes visited, [1] triangles tested.
 PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* counters) {
     HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
     if (s.num_nodes == 0) return best;
-    RAY_SLAB_SETUP(o, d)
+    const RaySlab r = make_ray_slab(o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
     int node = 0;
@@ -139,19 +206,8 @@ PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* c
             const F4* np = s.nodes + (size_t)node * 4;
             F4 q0 = ld4(np), q1 = ld4(np + 1), q2 = ld4(np + 2), q3 = ld4(np + 3);
             if (counters) counters[0]++;
-            float c0lox = pt_fma(q0.x, idx, -ox), c0hix = pt_fma(q0.y, idx, -ox);
-            float c0loy = pt_fma(q0.z, idy, -oy), c0hiy = pt_fma(q0.w, idy, -oy);
-            float c0loz = pt_fma(q2.x, idz, -oz), c0hiz = pt_fma(q2.y, idz, -oz);
-            float c1lox = pt_fma(q1.x, idx, -ox), c1hix = pt_fma(q1.y, idx, -ox);
-            float c1loy = pt_fma(q1.z, idy, -oy), c1hiy = pt_fma(q1.w, idy, -oy);
-            float c1loz = pt_fma(q2.z, idz, -oz), c1hiz = pt_fma(q2.w, idz, -oz);
-            // fminf/fmaxf drop NaNs (0 * inf when the ray lies in a slab plane): that axis is then ignored
-            float tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-            float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
-            float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-            float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
-            bool h0 = tn0 <= pt_fma(tf0, 1.0000005f, slab_err);
-            bool h1 = tn1 <= pt_fma(tf1, 1.0000005f, slab_err);
+            bool h0, h1; float tn0, tn1;
+            node_test(r, q0, q1, q2, best.t, h0, h1, tn0, tn1);
             int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
             if (!h0 && !h1) node = stack[--sp];
             else if (h0 && h1) {
@@ -159,31 +215,18 @@ PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* c
                 stack[sp++] = c1; node = c0;
             } else node = h0 ? c0 : c1;
         } else {
-            uint32_t enc = ~(uint32_t)node;
-            uint32_t first = enc >> 3, cnt = (enc & 7u) + 1u;
-            for (uint32_t i = 0; i < cnt; ++i) {
-                const F4* tp = s.tris + (size_t)(first + i) * 3;
-                F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-                if (counters) counters[1]++;
-                float t, b1, b2;
-                if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
-                               PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
-                    uint32_t id = f2u(a.w);
-                    if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
-                }
-            }
+            leaf_closest(s, node, o, d, best, counters);
             node = stack[--sp];
         }
     }
     return best;
 }
 
-// Any hit in (tmin, tmax): early-out visibility query (the reference has no
-// shadow rays in its shipped configuration — SEND_TO_LIGHT_PROBABILITY = 0,
-// shader_definitions.rs:19 — this serves the optional light-sampling modes).
+// Any hit in (tmin, tmax): early-out visibility query (the reference has no shadow rays in its shipped
+// configuration — SEND_TO_LIGHT_PROBABILITY = 0, shader_definitions.rs:19 — this serves optional light-sampling modes).
 PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
     if (s.num_nodes == 0) return false;
-    RAY_SLAB_SETUP(o, d)
+    const RaySlab r = make_ray_slab(o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
     int node = 0;
@@ -191,18 +234,8 @@ PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
         if (node >= 0) {
             const F4* np = s.nodes + (size_t)node * 4;
             F4 q0 = ld4(np), q1 = ld4(np + 1), q2 = ld4(np + 2), q3 = ld4(np + 3);
-            float c0lox = pt_fma(q0.x, idx, -ox), c0hix = pt_fma(q0.y, idx, -ox);
-            float c0loy = pt_fma(q0.z, idy, -oy), c0hiy = pt_fma(q0.w, idy, -oy);
-            float c0loz = pt_fma(q2.x, idz, -oz), c0hiz = pt_fma(q2.y, idz, -oz);
-            float c1lox = pt_fma(q1.x, idx, -ox), c1hix = pt_fma(q1.y, idx, -ox);
-            float c1loy = pt_fma(q1.z, idy, -oy), c1hiy = pt_fma(q1.w, idy, -oy);
-            float c1loz = pt_fma(q2.z, idz, -oz), c1hiz = pt_fma(q2.w, idz, -oz);
-            float tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-            float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-            float tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-            float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
-            bool h0 = tn0 <= pt_fma(tf0, 1.0000005f, slab_err);
-            bool h1 = tn1 <= pt_fma(tf1, 1.0000005f, slab_err);
+            bool h0, h1; float tn0, tn1;
+            node_test(r, q0, q1, q2, tmax, h0, h1, tn0, tn1);
             int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
             if (!h0 && !h1) node = stack[--sp];
             else if (h0 && h1) { stack[sp++] = c1; node = c0; }
