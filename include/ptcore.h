@@ -120,6 +120,18 @@ PTC_API int ptc_trace_rays_any(ptc_step* step, const float* rays, uint64_t n, ui
  * 11 a*b+a (uncontracted), 12 bilinear address probe. */
 PTC_API int ptc_debug_math(int cuda_device, int fn, const float* a, const float* b, float* out, uint64_t n);
 
+/* evaluate the kernels' texture lookup on the device (unit-test entry): texture_index >= 0 samples that texture at
+ * n (u, v) pairs (`in` = n x 2 floats) exactly as sample_texture_rgba does (helpers.wgsl:35-37); texture_index < 0
+ * evaluates sky_color (sky.wgsl:1-12) for n directions (`in` = n x 3 floats).  rgba = n x 4 floats.  per_lane != 0:
+ * lookup i uses texture (texture_index + i) mod num_textures, so the lanes of a warp hold different texture handles,
+ * as they do in the shading kernel. */
+PTC_API int ptc_debug_sample(ptc_step* step, int texture_index, const float* in, uint64_t n, float* rgba, int per_lane);
+
+/* the texture unit's u8 -> f32 conversion (cudaReadModeNormalizedFloat) for a 256x1 RGBA8 ramp: out[i] = .x of texel i
+ * (value i), out[256+i] = .w (value 255-i).  Returns 1 when the library reads 8-bit textures through it (every value
+ * equals i/255 rounded to nearest, the reference's to_rgba32f, texture.rs:241), 0 when it divides in the kernel, < 0 on error. */
+PTC_API int ptc_debug_unorm8(int cuda_device, float* out512);
+
 PTC_API const char* ptc_last_error(void);
 PTC_API const char* ptc_version(void);
 PTC_API int ptc_device_count(void);

@@ -69,6 +69,67 @@ def test_device_primitives_match_host(ptc, oracle):
             assert np.array_equal(out, ref, equal_nan=True), f"primitive {fn} differs between device and host"
 
 
+def test_unorm8_texture_conversion(ptc):
+    """8-bit texels must reach the kernels as rn(v / 255) (texture.rs:241 to_rgba32f).  The library reads them through the
+    texture unit's normalised-float mode only if that conversion is exact for all 256 values (self-test at ptc_create);
+    report which path this box uses and check the claim."""
+    import ctypes as C
+    out = np.zeros(512, np.float32)
+    rc = ptc.lib().ptc_debug_unorm8(0, out.ctypes.data_as(C.c_void_p))
+    assert rc in (0, 1)
+    want = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
+    exact = np.array_equal(out[:256], want) and np.array_equal(out[256:], want[::-1])
+    assert bool(rc) == exact
+    print("unorm8 via texture unit exact:", exact)
+
+
+@pytest.mark.parametrize("which", ["soup", "sponza"])
+def test_texture_and_sky_lookup_bit_exact(ptc, standins, oracle, which):
+    """Every texture of the scene (8-bit and float, 1x1 constants included) sampled on the device at random uv —
+    wrapping, negative and texel-edge coordinates — equals the oracle's sample_texture_rgba bit for bit; same for sky_color."""
+    scene, _ = standins.random_soup(600, seed=2) if which == "soup" else standins.sponza()
+    cfg = ptc.make_config(8, 8)
+    step = ptc.RTStep.create(scene, cfg)
+    orc = oracle.OracleScene(scene, cfg)
+    rng = np.random.RandomState(4)
+    uv = (rng.rand(20000, 2) * 6 - 3).astype(np.float32)
+    uv[:64] = (rng.randint(-8, 9, (64, 2)) / 4.0).astype(np.float32)          # exact texel-grid fractions
+    ntex = len(scene.textures)
+    for idx in range(ntex):
+        got, ref = step.sample_texture(idx, uv), orc.sample_texture(idx, uv)
+        assert np.array_equal(got, ref), f"texture {idx} of {ntex}: {int((got != ref).any(axis=1).sum())} lookups differ"
+    # a different texture in every lane of a warp (what the shading kernel does)
+    got = step.sample_texture(3, uv, per_lane=True)
+    ref = np.zeros_like(got)
+    for idx in range(ntex):
+        sel = (3 + np.arange(len(uv))) % ntex == idx
+        ref[sel] = orc.sample_texture(idx, uv[sel])
+    assert np.array_equal(got, ref), f"per-lane texture handles: {int((got != ref).any(axis=1).sum())} lookups differ"
+    d = rng.randn(50000, 3).astype(np.float32)
+    d[:6] = np.array([[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]], np.float32)
+    assert np.array_equal(step.sky(d), orc.sky(d))
+    step.destroy()
+
+
+def test_non_finite_rays_miss(ptc, standins, oracle):
+    """A ray with a NaN/inf component hits nothing (and must not walk the whole tree: fmin/fmax drop NaNs)."""
+    from conftest import random_rays
+    scene, _ = standins.random_soup(20000, seed=5, textured=False)
+    cfg = ptc.make_config(8, 8)
+    step = ptc.RTStep.create(scene, cfg)
+    orc = oracle.OracleScene(scene, cfg)
+    rays = random_rays(4096, 11)
+    bad = np.arange(0, 4096, 7)
+    rays[bad[0::3], 4] = np.nan
+    rays[bad[1::3], 1] = np.inf
+    rays[bad[2::3], 6] = -np.inf
+    hits, ids = step.trace_rays(rays)
+    rh, rids, _ = orc.trace_rays(rays)
+    assert (hits[bad, 3] == 0xFFFFFFFF).all()
+    assert np.array_equal(hits, rh) and np.array_equal(ids, rids)
+    assert (step.trace_rays_any(rays)[bad] == 0).all()
+
+
 def test_trace_rays_soup_bit_exact(ptc, standins, oracle):
     from conftest import random_rays
     scene, _ = standins.random_soup(20000, seed=5, textured=False)

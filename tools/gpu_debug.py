@@ -104,6 +104,8 @@ if __name__ == "__main__":
     if "sweep" in which:
         bounce_sweep("cornell", 512, 512, frames=1)
         bounce_sweep("cornell", 512, 512, frames=4, depths=(8,))
+    if "sponza" in which:
+        bounce_sweep("sponza", int(os.environ.get("DBG_W", 480)), int(os.environ.get("DBG_H", 270)), frames=1, depths=tuple(int(x) for x in os.environ.get("DBG_DEPTHS", "0,1,2,4").split(",")))
     if "b2b" in which:
         back_to_back("sponza", 1920, 1080, 3)
         back_to_back("sponza", 1920, 1080, 3, use_torch=True)

@@ -10,7 +10,9 @@ import os
 from . import _types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libptcore.so")
+# PTC_LIB: development override used to A/B-time kernel variants built by tools/build_variant.sh (still a CUDA build of
+# the same sources; there is no non-CUDA library to point it at)
+LIB_PATH = os.environ.get("PTC_LIB") or os.path.join(_HERE, "csrc", "libptcore.so")
 _lib = None
 
 
@@ -52,6 +54,8 @@ def lib():
         "ptc_trace_rays": (i32, [vp, vp, u64, vp, vp]),
         "ptc_trace_rays_any": (i32, [vp, vp, u64, vp]),
         "ptc_debug_math": (i32, [i32, i32, vp, vp, vp, u64]),
+        "ptc_debug_unorm8": (i32, [i32, vp]),
+        "ptc_debug_sample": (i32, [vp, i32, vp, u64, vp, i32]),
         "ptc_last_error": (C.c_char_p, []),
         "ptc_version": (C.c_char_p, []),
         "ptc_device_count": (i32, []),

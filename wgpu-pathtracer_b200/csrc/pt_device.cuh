@@ -34,15 +34,20 @@ PT_HD F4 ld4(const F4* p) { return *p; }
 
 // ---- device scene ----------------------------------------------------------
 
-// per-texture record (bindless table).  `obj` is a cudaTextureObject_t over a
-// cudaArray (point filter, unnormalised coordinates, element read mode);
-// `linear` is the same texels in linear memory (host emulation; also the
-// fallback-free debug path of tests).
-struct TexDev {
-    unsigned long long obj;
+// per-texture record (bindless table).  On the device every texture lives inside an ATLAS PAGE: one cudaArray +
+// one cudaTextureObject_t (point filter, unnormalised coordinates) per page, textures shelf-packed into it, `page`
+// selecting the page and (ax, ay) the texture's origin inside it.  The handful of page handles travel as kernel
+// parameters (DevScene::page_obj), so the handle of every TEX instruction is warp-uniform.  One texture object per
+// texture would not be: lanes of a warp shade different materials, and for a per-lane handle the compiler wraps
+// each TEX in a loop over the distinct handles of the warp (R2UR ... BRA.U.ANY in SASS) — one pass per texture.
+// `linear` is the same texels in linear host memory (tests/hostemu only).
+struct alignas(16) TexDev {
     const void* linear;
-    uint32_t w, h, fmt, _pad;
+    uint32_t w, h, fmt, page;
+    uint32_t ax, ay;
 };
+static_assert(sizeof(TexDev) == 32, "TexDev is read as two 128-bit words");
+#define PTC_MAX_TEX_PAGES 8
 
 // One slot per material input that influences the result (specular and sheen
 // taps of rt_helpers.wgsl:17-42 are dead: no consumer).  Slots whose texture is
@@ -70,6 +75,8 @@ struct DevScene {
     const TexDev* texs;
     const ptc_triangle* lights;
     uint32_t num_nodes, num_tris, num_lights, env_tex;
+    uint32_t num_pages, _pad;
+    unsigned long long page_obj[PTC_MAX_TEX_PAGES];   // cudaTextureObject_t per atlas page (device build only)
 };
 
 struct PathCfg {
@@ -123,14 +130,14 @@ struct RaySlab {
 };
 
 PT_HD float pt_min3(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(PTC_NO_MINMAX3)
     float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
 #else
     return fminf(fminf(a, b), c);
 #endif
 }
 PT_HD float pt_max3(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(PTC_NO_MINMAX3)
     float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
 #else
     return fmaxf(fmaxf(a, b), c);
@@ -152,6 +159,15 @@ PT_HD RaySlab make_ray_slab(pt_v3 o, pt_v3 d) {
     r.ly = dy > 0.0f ? -oy - ey : -oy + ey;  r.hy = dy > 0.0f ? -oy + ey : -oy - ey;
     r.lz = dz > 0.0f ? -oz - ez : -oz + ez;  r.hz = dz > 0.0f ? -oz + ez : -oz - ez;
     return r;
+}
+
+// A ray with a non-finite origin or direction hits nothing (this project's definition; the reference leaves it to
+// the Vulkan driver).  pt_ray_tri already rejects every triangle for such a ray (NaN fails each comparison), so this
+// is an early-out, not a change of result — but an essential one: fmin/fmax drop NaNs, so a NaN slab would stop
+// culling altogether and one such ray would walk the whole tree (measured: a 37 ms straggler per launch).
+PT_HD bool ray_is_finite(pt_v3 o, pt_v3 d) {
+    float z = ((o.x * 0.0f + o.y * 0.0f) + (o.z * 0.0f + d.x * 0.0f)) + (d.y * 0.0f + d.z * 0.0f);   // 0 iff all six are finite
+    return z == 0.0f;
 }
 
 // Both children of one BVH2 node against the ray: hit flags and entry distances.
@@ -196,7 +212,7 @@ PT_HD void leaf_closest(const DevScene& s, int node, pt_v3 o, pt_v3 d, HitRec& b
 // counters (optional): [0] nodes visited, [1] triangles tested.
 PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* counters) {
     HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
-    if (s.num_nodes == 0) return best;
+    if (s.num_nodes == 0 || !ray_is_finite(o, d)) return best;
     const RaySlab r = make_ray_slab(o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
@@ -225,7 +241,7 @@ PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* c
 // Any hit in (tmin, tmax): early-out visibility query (the reference has no shadow rays in its shipped
 // configuration — SEND_TO_LIGHT_PROBABILITY = 0, shader_definitions.rs:19 — this serves optional light-sampling modes).
 PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
-    if (s.num_nodes == 0) return false;
+    if (s.num_nodes == 0 || !ray_is_finite(o, d)) return false;
     const RaySlab r = make_ray_slab(o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
@@ -257,46 +273,79 @@ PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
 }
 
 // ---- textures: helpers.wgsl:35-48, sampler texture.rs:312-322 -----------------
-PT_HD pt_v4 fetch_texel(const TexDev& t, int x, int y) {
-#if defined(__CUDA_ARCH__)
-    if (t.fmt == PTC_TEXEL_RGBA8) {
-        uchar4 p = tex2D<uchar4>((cudaTextureObject_t)t.obj, (float)x + 0.5f, (float)y + 0.5f);
-        return pt_mk4(pt_div((float)p.x, 255.0f), pt_div((float)p.y, 255.0f), pt_div((float)p.z, 255.0f), pt_div((float)p.w, 255.0f));
-    }
-    float4 p = tex2D<float4>((cudaTextureObject_t)t.obj, (float)x + 0.5f, (float)y + 0.5f);
-    return pt_mk4(p.x, p.y, p.z, p.w);
-#else
-    size_t i = (size_t)y * t.w + (size_t)x;
-    if (t.fmt == PTC_TEXEL_RGBA8) {
-        const uint8_t* p = (const uint8_t*)t.linear + i * 4;
-        return pt_mk4(pt_div((float)p[0], 255.0f), pt_div((float)p[1], 255.0f), pt_div((float)p[2], 255.0f), pt_div((float)p[3], 255.0f));
-    }
-    const float* p = (const float*)t.linear + i * 4;
-    return pt_mk4(p[0], p[1], p[2], p[3]);
-#endif
-}
+// Device: atlas pages are point-sampled with unnormalised coordinates; the four taps of one bilinear lookup are
+// issued back to back (one exposed round trip, not four) and the fp32 weights of pt_bilinear_axis applied in
+// registers.  8-bit pages are read through cudaReadModeNormalizedFloat: the texture unit's u8 -> f32 conversion is
+// checked once per process (pt_step.cu: unorm8_hw_exact) to equal rn(v / 255) for all 256 values — the reference's
+// to_rgba32f (texture.rs:241) — and if it ever did not, 8-bit textures would be expanded to f32 pages on upload.
+// shade_bounce calls sample_tex from ONE place (a loop over the lookups a path needs), so the kernel holds one inlined
+// copy: eight copies made k_shade 84 KB of SASS with instruction-fetch stalls as its second largest stall reason.
 PT_HD float bilerp(float a, float b, float c, float d, float fx, float fy) {
     float wx = 1.0f - fx;
     float top = pt_fma(b, fx, a * wx);
     float bot = pt_fma(d, fx, c * wx);
     return pt_fma(bot, fy, top * (1.0f - fy));
 }
-PT_HD pt_v4 sample_tex(const TexDev& t, float u, float v) {
-    if (t.w == 1 && t.h == 1) return fetch_texel(t, 0, 0);
-    int x0, x1, y0, y1; float fx, fy;
-    pt_bilinear_axis(u, (int)t.w, &x0, &x1, &fx);
-    pt_bilinear_axis(v, (int)t.h, &y0, &y1, &fy);
-    pt_v4 a = fetch_texel(t, x0, y0), b = fetch_texel(t, x1, y0), c = fetch_texel(t, x0, y1), d = fetch_texel(t, x1, y1);
+PT_HD pt_v4 unorm8_to_f32(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    return pt_mk4(pt_div((float)x, 255.0f), pt_div((float)y, 255.0f), pt_div((float)z, 255.0f), pt_div((float)w, 255.0f));
+}
+// the four texels (x0,y0) (x1,y0) (x0,y1) (x1,y1) of texture t
+PT_HD void fetch_quad(const DevScene& s, const TexDev& t, int x0, int x1, int y0, int y1, pt_v4& a, pt_v4& b, pt_v4& c, pt_v4& d) {
+#if defined(__CUDA_ARCH__)
+    const float fx0 = (float)(t.ax + (uint32_t)x0) + 0.5f, fx1 = (float)(t.ax + (uint32_t)x1) + 0.5f;
+    const float fy0 = (float)(t.ay + (uint32_t)y0) + 0.5f, fy1 = (float)(t.ay + (uint32_t)y1) + 0.5f;
+    float4 pa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pb = pa, pc = pa, pd = pa;
+    for (uint32_t p = 0; p < s.num_pages; ++p) {             // uniform trip count, uniform handle
+        if (t.page == p) {
+            const cudaTextureObject_t obj = (cudaTextureObject_t)s.page_obj[p];
+            pa = tex2D<float4>(obj, fx0, fy0); pb = tex2D<float4>(obj, fx1, fy0);
+            pc = tex2D<float4>(obj, fx0, fy1); pd = tex2D<float4>(obj, fx1, fy1);
+        }
+    }
+    a = pt_mk4(pa.x, pa.y, pa.z, pa.w); b = pt_mk4(pb.x, pb.y, pb.z, pb.w);
+    c = pt_mk4(pc.x, pc.y, pc.z, pc.w); d = pt_mk4(pd.x, pd.y, pd.z, pd.w);
+#else
+    (void)s;
+    const int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+    pt_v4 out[4];
+    for (int k = 0; k < 4; ++k) {
+        size_t i = (size_t)ys[k] * t.w + (size_t)xs[k];
+        if (t.fmt == PTC_TEXEL_RGBA8) { const uint8_t* p = (const uint8_t*)t.linear + i * 4; out[k] = unorm8_to_f32(p[0], p[1], p[2], p[3]); }
+        else { const float* p = (const float*)t.linear + i * 4; out[k] = pt_mk4(p[0], p[1], p[2], p[3]); }
+    }
+    a = out[0]; b = out[1]; c = out[2]; d = out[3];
+#endif
+}
+PT_HD pt_v4 sample_tex(const DevScene& s, uint32_t idx, float u, float v) {
+#if defined(__CUDA_ARCH__)
+    // the 32-byte record as two 128-bit loads
+    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(s.texs + idx)), r1 = __ldg(reinterpret_cast<const uint4*>(s.texs + idx) + 1);
+    TexDev t; t.linear = nullptr; t.w = r0.z; t.h = r0.w; t.fmt = r1.x; t.page = r1.y; t.ax = r1.z; t.ay = r1.w;
+#else
+    const TexDev& t = s.texs[idx];
+#endif
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0; float fx = 0.0f, fy = 0.0f;
+    const bool single = t.w == 1 && t.h == 1;          // a 1x1 texture returns its texel for every uv
+    if (!single) {
+        pt_bilinear_axis(u, (int)t.w, &x0, &x1, &fx);
+        pt_bilinear_axis(v, (int)t.h, &y0, &y1, &fy);
+    }
+    pt_v4 a, b, c, d;
+    fetch_quad(s, t, x0, x1, y0, y1, a, b, c, d);
+    if (single) return a;
     return pt_mk4(bilerp(a.x, b.x, c.x, d.x, fx, fy), bilerp(a.y, b.y, c.y, d.y, fx, fy),
                   bilerp(a.z, b.z, c.z, d.z, fx, fy), bilerp(a.w, b.w, c.w, d.w, fx, fy));
 }
 
-// sky.wgsl:1-12
-PT_HD pt_v3 sky_radiance(const DevScene& s, pt_v3 rd) {
+// sky.wgsl:1-12: direction -> equirectangular (u, v) of texture `env_tex`
+PT_HD void sky_uv(pt_v3 rd, float& u, float& v) {
     pt_v3 d = pt_normalize(rd);
-    float v = pt_div(pt_acos(d.y), PT_PI);
-    float u = pt_div(pt_atan2(d.z, d.x) + PT_PI, 2.0f * PT_PI);
-    pt_v4 c = sample_tex(s.texs[s.env_tex], u, v);
+    v = pt_div(pt_acos(d.y), PT_PI);
+    u = pt_div(pt_atan2(d.z, d.x) + PT_PI, 2.0f * PT_PI);
+}
+PT_HD pt_v3 sky_radiance(const DevScene& s, pt_v3 rd) {
+    float u, v; sky_uv(rd, u, v);
+    pt_v4 c = sample_tex(s, s.env_tex, u, v);
     return pt_mk3(c.x, c.y, c.z);
 }
 
@@ -318,27 +367,14 @@ struct BounceOut {
 // The resolved material at a hit (rt_helpers.wgsl:17-42 minus its dead taps).
 struct MatEval { pt_v3 albedo, tsn, emissive; float roughness, metallic, transmission, ior, anisotropy; };
 
-PT_HD MatEval eval_material(const DevScene& s, uint32_t mat_id, float u, float v) {
-    const MatDev& m = s.mats[mat_id];
-    MatEval e;
-    e.albedo = pt_mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
-    e.tsn = pt_mk3(m.tsn[0], m.tsn[1], m.tsn[2]);
-    e.emissive = pt_mk3(m.emissive[0], m.emissive[1], m.emissive[2]);
-    e.roughness = m.roughness; e.metallic = m.metallic; e.transmission = m.transmission; e.ior = m.ior; e.anisotropy = m.anisotropy;
-    uint32_t mask = m.tex_mask;
-    if (mask) {
-        if (mask & (1u << SLOT_ALBEDO)) { pt_v4 c = sample_tex(s.texs[m.tex[SLOT_ALBEDO]], u, v); e.albedo = pt_mk3(c.x, c.y, c.z); }
-        if (mask & (1u << SLOT_NORMAL)) {
-            pt_v4 c = sample_tex(s.texs[m.tex[SLOT_NORMAL]], u, v);
-            e.tsn = pt_mk3(c.x * 2.0f - 1.0f, c.y * 2.0f - 1.0f, c.z * 2.0f - 1.0f);
-        }
-        if (mask & (1u << SLOT_ROUGHNESS)) e.roughness = sample_tex(s.texs[m.tex[SLOT_ROUGHNESS]], u, v).x;
-        if (mask & (1u << SLOT_METALLIC)) e.metallic = sample_tex(s.texs[m.tex[SLOT_METALLIC]], u, v).x;
-        if (mask & (1u << SLOT_EMISSIVE)) { pt_v4 c = sample_tex(s.texs[m.tex[SLOT_EMISSIVE]], u, v); e.emissive = pt_mk3(c.x, c.y, c.z); }
-        if (mask & (1u << SLOT_TRANSMISSION)) e.transmission = sample_tex(s.texs[m.tex[SLOT_TRANSMISSION]], u, v).x;
-        if (mask & (1u << SLOT_IOR)) e.ior = sample_tex(s.texs[m.tex[SLOT_IOR]], u, v).x;
-    }
-    return e;
+#define SLOT_SKY SLOT_COUNT      // pseudo-slot: the environment lookup of a path that escaped
+
+PT_HD uint32_t pt_ctz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
 }
 
 // scatter + disney_bsdf: pathtracer/pathtracer.wgsl:76-101, bsdf.wgsl:39-87,120-231.
@@ -387,23 +423,62 @@ PT_HD void scatter_regular(uint32_t& rng, pt_v3 ro, pt_v3 rd, float t, pt_v3 n, 
 
 // One iteration of ray_color's loop body (pathtracer/pathtracer.wgsl:159-233) for a
 // path whose segment has been traced to `hit`.
+//
+// Texture work is gathered into one loop: a path that hit needs the lookups named by its material's tex_mask
+// (sample_material, rt_helpers.wgsl:17-42; 1x1 textures were folded to constants at upload), a path that escaped
+// needs the environment lookup (sky.wgsl:1-12).  Each lane walks its own list, so in a warp the lanes sample
+// different slots of different materials in the same pass instead of each `if (slot)` serialising the warp.
 PT_HD BounceOut shade_bounce(const DevScene& s, const PathCfg& cfg, const PathState& ps, const HitRec& hit, uint32_t bounce) {
     BounceOut out;
     out.alive = false;
     out.first_t = 0.0f; out.first_normal = pt_mk3(0.0f, 0.0f, 0.0f); out.first_albedo = pt_mk3(0.0f, 0.0f, 0.0f);
     out.next = ps;
-    if (hit.tri == 0xFFFFFFFFu) {                                          // :229-232
-        out.radiance = pt_add(ps.acc, pt_mul(sky_radiance(s, ps.d), ps.mask));
+    const bool miss = hit.tri == 0xFFFFFFFFu;
+    F4 q0 = {0, 0, 0, 0}, q1 = q0, q2 = q0;
+    float w0 = 0.0f, u = 0.0f, v = 0.0f;
+    MatEval m;
+    m.albedo = m.tsn = m.emissive = pt_mk3(0.0f, 0.0f, 0.0f);
+    m.roughness = m.metallic = m.transmission = m.ior = m.anisotropy = 0.0f;
+    const MatDev* mp = s.mats;
+    uint32_t todo;
+    if (miss) {                                                            // :229-232
+        sky_uv(ps.d, u, v);
+        todo = 1u << SLOT_SKY;
+    } else {
+        // rt_helpers.wgsl:57-67 through the re-packed per-triangle record
+        const TriShade& ts = s.shade[hit.tri];
+        q0 = ld4(&ts.q[0]); q1 = ld4(&ts.q[1]); q2 = ld4(&ts.q[2]);
+        const F4 q3 = ld4(&ts.q[3]);
+        w0 = 1.0f - hit.b1 - hit.b2;
+        u = q0.w * w0 + q2.w * hit.b1 + q3.y * hit.b2;
+        v = q1.w * w0 + q3.x * hit.b1 + q3.z * hit.b2;
+        mp = s.mats + f2u(q3.w);
+        m.albedo = pt_mk3(mp->albedo[0], mp->albedo[1], mp->albedo[2]);
+        m.tsn = pt_mk3(mp->tsn[0], mp->tsn[1], mp->tsn[2]);
+        m.emissive = pt_mk3(mp->emissive[0], mp->emissive[1], mp->emissive[2]);
+        m.roughness = mp->roughness; m.metallic = mp->metallic; m.transmission = mp->transmission; m.ior = mp->ior; m.anisotropy = mp->anisotropy;
+        todo = mp->tex_mask;
+    }
+    pt_v3 sky = pt_mk3(0.0f, 0.0f, 0.0f);
+    while (todo != 0) {
+        const uint32_t slot = pt_ctz(todo);
+        todo &= todo - 1u;
+        const pt_v4 c = sample_tex(s, slot == SLOT_SKY ? s.env_tex : mp->tex[slot], u, v);
+        switch (slot) {
+            case SLOT_ALBEDO: m.albedo = pt_mk3(c.x, c.y, c.z); break;
+            case SLOT_NORMAL: m.tsn = pt_mk3(c.x * 2.0f - 1.0f, c.y * 2.0f - 1.0f, c.z * 2.0f - 1.0f); break;
+            case SLOT_ROUGHNESS: m.roughness = c.x; break;
+            case SLOT_METALLIC: m.metallic = c.x; break;
+            case SLOT_EMISSIVE: m.emissive = pt_mk3(c.x, c.y, c.z); break;
+            case SLOT_TRANSMISSION: m.transmission = c.x; break;
+            case SLOT_IOR: m.ior = c.x; break;
+            default: sky = pt_mk3(c.x, c.y, c.z); break;
+        }
+    }
+    if (miss) {
+        out.radiance = pt_add(ps.acc, pt_mul(sky, ps.mask));
         return out;
     }
-    // rt_helpers.wgsl:57-67 through the re-packed per-triangle record
-    const TriShade& ts = s.shade[hit.tri];
-    F4 q0 = ld4(&ts.q[0]), q1 = ld4(&ts.q[1]), q2 = ld4(&ts.q[2]), q3 = ld4(&ts.q[3]);
-    float w0 = 1.0f - hit.b1 - hit.b2;
-    float u = q0.w * w0 + q2.w * hit.b1 + q3.y * hit.b2;
-    float v = q1.w * w0 + q3.x * hit.b1 + q3.z * hit.b2;
-    uint32_t mat_id = f2u(q3.w);
-    MatEval m = eval_material(s, mat_id, u, v);
     bool hit_light = pt_dot(m.emissive, pt_mk3(1.0f, 1.0f, 1.0f)) > 0.0f;   // rt_helpers.wgsl:70
 
     uint32_t rng = ps.rng;

@@ -5,6 +5,9 @@ namespace ptc {
 
 constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
+#ifndef PTC_SHADE_MIN_BLOCKS
+#define PTC_SHADE_MIN_BLOCKS 8            // <= 64 registers: 32 resident warps per SM to cover the gather latency
+#endif
 
 // ---- raygen: rand_init + primary ray (pathtracer.wgsl:27, pathtracer/pathtracer.wgsl:240-250) ----
 __global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameCounters* fc, uint32_t npix) {
@@ -27,9 +30,13 @@ __device__ __forceinline__ uint32_t warp_fetch(uint32_t* cursor) {
     return __shfl_sync(0xffffffffu, base, 0);
 }
 
-__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
-                                                          U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
-                                                          uint32_t* cursor, unsigned long long* total_rays) {
+// Reference form of the closest-hit kernel: one ray per lane, 32-ray batches, every lane runs the plain
+// per-ray loop of pt_device.cuh.  Kept for A/B timing (PTC_TRACE_IMPL=simple) and as the readable statement
+// of what k_trace computes; its SIMT efficiency on incoherent rays is ~30 % (ncu, profiles/r01a): a warp
+// pays node test + triangle loop on every iteration and runs until its slowest ray is done.
+__global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+                                                                 U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
+                                                                 uint32_t* cursor, unsigned long long* total_rays) {
     const uint32_t n = *count_ptr;
     if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
     const uint32_t lane = threadIdx.x & 31;
@@ -41,6 +48,164 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene s, const F4* _
             F4 o = ld4(ray_o + i), d = ld4(ray_d + i);
             HitRec h = trace_closest_bvh2(s, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), nullptr);
             reinterpret_cast<uint4*>(hits)[i] = make_uint4(__float_as_uint(h.t), __float_as_uint(h.b1), __float_as_uint(h.b2), h.tri);
+        }
+    }
+}
+
+// Production closest-hit kernel.  Same result as k_trace_simple ray for ray (the hit is the minimum of
+// (t, global triangle id) over all accepted triangles, which does not depend on visiting order), but the warp's
+// work is re-shaped so that both phases run dense:
+//   * node phase: every lane that owns a ray does ONE node step per iteration (both children of a BVH2 node, slab test
+//     of pt_device.cuh).  A lane that reaches a leaf does not test it: it appends the leaf's triangles to a per-warp
+//     list in shared memory as (lane, triangle) pairs and pops its stack, so it is back on an inner node next iteration.
+//   * triangle phase: when >= 32 pairs are pending the warp tests them 32 at a time, lane k taking pair k — the ray
+//     comes from shared memory, so a test is not tied to the lane that owns the ray.  Results are combined with a
+//     64-bit atomicMin on ((t bits) << 32 | triangle id) in shared memory: smaller t wins, equal t goes to the
+//     smaller id — exactly the tie rule of leaf_closest.  The winner then records its barycentrics.
+//   * a lane whose stack is empty and whose pairs are all resolved writes its hit and takes the next ray from the
+//     device cursor (one aggregated atomicAdd per refill), so lanes do not idle until the slowest ray of a batch ends.
+// The pruning distance each lane carries is refreshed after every triangle phase; between two phases it is stale
+// (larger), which costs a few extra node visits and never a wrong result.
+constexpr int kTraceWarps = kTraceThreads / 32;
+constexpr uint32_t kTriCap = 32 + 32 * 4;         // < 32 carried over + at most 4 per lane per iteration
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+#ifndef PTC_WAIT_FLUSH
+#define PTC_WAIT_FLUSH 8                           // finished lanes that force a full flush
+#endif
+
+struct TraceWarp {
+    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];
+    unsigned long long best[32];                  // (t bits << 32) | global triangle id
+    float b1[32], b2[32];
+    uint32_t pend[32];                            // unresolved pairs per lane
+    uint32_t pair[kTriCap];                       // (lane << 27) | leaf-order triangle index
+};
+
+__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+                                                          U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
+                                                          uint32_t* cursor, unsigned long long* total_rays) {
+    __shared__ TraceWarp sh[kTraceWarps];
+    TraceWarp& ws = sh[threadIdx.x >> 5];
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t n = *count_ptr;
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
+    const unsigned long long kMissKey = ((unsigned long long)__float_as_uint(PT_RAY_TMAX) << 32) | 0xFFFFFFFFull;
+
+    int stack[PTC_STACK_SIZE];
+    int node = PTC_SENTINEL, sp = 0;
+    uint32_t ray = kNoRay;
+    RaySlab r = {};
+    float tbest = PT_RAY_TMAX;
+    uint32_t npair = 0;                            // warp-uniform
+    bool exhausted = false;                        // warp-uniform: the cursor has passed n
+    ws.pend[lane] = 0;
+    __syncwarp();
+
+    for (;;) {
+        // ---- refill idle lanes from the device cursor ----
+        const bool want = ray == kNoRay;
+        const uint32_t wm = __ballot_sync(FULL, want);
+        if (wm != 0 && !exhausted) {
+            const uint32_t k = __popc(wm);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, k);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + k >= n) exhausted = true;
+            const uint32_t i = base + __popc(wm & lt);
+            if (want && i < n) {
+                ray = i;
+                const F4 o = ld4(ray_o + i), d = ld4(ray_d + i);
+                ws.ox[lane] = o.x; ws.oy[lane] = o.y; ws.oz[lane] = o.z;
+                ws.dx[lane] = d.x; ws.dy[lane] = d.y; ws.dz[lane] = d.z;
+                ws.best[lane] = kMissKey; ws.b1[lane] = 0.0f; ws.b2[lane] = 0.0f;
+                const pt_v3 ov = pt_mk3(o.x, o.y, o.z), dv = pt_mk3(d.x, d.y, d.z);
+                r = make_ray_slab(ov, dv);
+                tbest = PT_RAY_TMAX;
+                stack[0] = PTC_SENTINEL; sp = 1;
+                node = (s.num_nodes != 0 && ray_is_finite(ov, dv)) ? 0 : PTC_SENTINEL;
+            }
+        }
+        __syncwarp();
+        if (__ballot_sync(FULL, ray != kNoRay) == 0) break;
+
+        // ---- node phase ----
+        bool force;
+        for (;;) {
+            if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {                   // inner node
+                const F4* np = s.nodes + (size_t)node * 4;
+                const F4 q0 = ld4(np), q1 = ld4(np + 1), q2 = ld4(np + 2), q3 = ld4(np + 3);
+                bool h0, h1; float tn0, tn1;
+                node_test(r, q0, q1, q2, tbest, h0, h1, tn0, tn1);
+                const int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
+                const bool swap = tn1 < tn0;
+                const int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+                if (h0 && h1) { stack[sp++] = farc; node = nearc; }
+                else if (h0 || h1) node = h0 ? c0 : c1;
+                else node = stack[--sp];
+            }
+            // leaves: queue their triangles, continue with the next stack entry
+            const bool leaf = node < 0;
+            const uint32_t lm = __ballot_sync(FULL, leaf);
+            if (lm != 0) {
+                const uint32_t enc = ~(uint32_t)node;
+                const uint32_t c1m = leaf ? (enc & 7u) : 0u;                  // count - 1, in 0..3
+                const uint32_t m0 = __ballot_sync(FULL, (c1m & 1u) != 0), m1 = __ballot_sync(FULL, (c1m & 2u) != 0);
+                if (leaf) {
+                    const uint32_t pos = npair + __popc(lm & lt) + __popc(m0 & lt) + 2u * __popc(m1 & lt);
+                    const uint32_t first = enc >> 3, tag = lane << 27;
+                    for (uint32_t m = 0; m <= c1m; ++m) ws.pair[pos + m] = tag | (first + m);
+                    ws.pend[lane] += c1m + 1u;
+                    node = stack[--sp];
+                }
+                npair += __popc(lm) + __popc(m0) + 2u * __popc(m1);
+            }
+            const uint32_t busy = __ballot_sync(FULL, node != PTC_SENTINEL);
+            const uint32_t waiting = __ballot_sync(FULL, ray != kNoRay && node == PTC_SENTINEL);
+            force = busy == 0 || __popc(waiting) >= PTC_WAIT_FLUSH;
+            if (force || npair >= 32u) break;
+        }
+        __syncwarp();
+
+        // ---- triangle phase: full batches, plus the remainder when forced ----
+        const uint32_t nproc = force ? npair : (npair & ~31u);
+        for (uint32_t k0 = 0; k0 < nproc; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            bool hit = false; float t = 0.0f, b1 = 0.0f, b2 = 0.0f; uint32_t src = 0; unsigned long long key = 0;
+            if (k < nproc) {
+                const uint32_t e = ws.pair[k];
+                src = e >> 27;
+                const F4* tp = s.tris + (size_t)(e & 0x07FFFFFFu) * 3;
+                const F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+                const pt_v3 o = pt_mk3(ws.ox[src], ws.oy[src], ws.oz[src]), d = pt_mk3(ws.dx[src], ws.dy[src], ws.dz[src]);
+                hit = pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
+                                 PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2) != 0;
+                if (hit) {
+                    key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)f2u(a.w);   // t > 0: bit order == value order
+                    atomicMin(&ws.best[src], key);
+                }
+            }
+            __syncwarp();
+            if (hit && ws.best[src] == key) { ws.b1[src] = b1; ws.b2[src] = b2; }   // keys are unique per ray: one writer
+            __syncwarp();
+        }
+        // carry the remainder to the front of the list and recount what each lane still waits for
+        const uint32_t rem = npair - nproc;
+        const uint32_t keep = lane < rem ? ws.pair[nproc + lane] : 0u;
+        ws.pend[lane] = 0;
+        __syncwarp();
+        if (lane < rem) { ws.pair[lane] = keep; atomicAdd(&ws.pend[keep >> 27], 1u); }
+        npair = rem;
+        __syncwarp();
+
+        // ---- refresh pruning distances, retire finished rays ----
+        if (ray != kNoRay) {
+            const unsigned long long key = ws.best[lane];
+            tbest = __uint_as_float((uint32_t)(key >> 32));
+            if (node == PTC_SENTINEL && ws.pend[lane] == 0) {
+                reinterpret_cast<uint4*>(hits)[ray] = make_uint4((uint32_t)(key >> 32), __float_as_uint(ws.b1[lane]), __float_as_uint(ws.b2[lane]), (uint32_t)key);
+                ray = kNoRay;
+            }
         }
     }
 }
@@ -61,15 +226,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_any(DevScene s, const F
 }
 
 // ---- shade: one bounce, ballot compaction into the next queue, fused accumulation ---------------
-__global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene s, PathCfg cfg, Queue qin, Queue qout, const U4* __restrict__ hits,
+// Work is split statically (warp w takes 32-ray batches w, w + #warps, ...): the cost per ray is nearly uniform, so a
+// device cursor would only add one dependent global atomic per batch.
+__global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(DevScene s, PathCfg cfg, Queue qin, Queue qout, const U4* __restrict__ hits,
                                                           FrameCounters* fc, uint32_t segment, Planes planes) {
     const uint32_t n = fc->count[segment];
-    uint32_t* cursor = &fc->shade_cursor[segment];
     uint32_t* next_count = &fc->count[segment + 1];
     const uint32_t lane = threadIdx.x & 31;
-    for (;;) {
-        uint32_t base = warp_fetch(cursor);
-        if (base >= n) break;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32u; base < n; base += nwarps * 32u) {
         uint32_t i = base + lane;
         bool alive = false;
         BounceOut bo;
@@ -115,9 +280,10 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DevScene s, PathCfg cfg
 void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t npix) {
     k_raygen<<<(npix + 255) / 256, 256, 0, st>>>(un, q, fc, npix);
 }
-void launch_trace(cudaStream_t st, int grid, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
+void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays) {
-    k_trace<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
+    if (impl == 0) k_trace<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
+    else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
                   FrameCounters* fc, uint32_t segment, Planes planes) {
@@ -126,10 +292,11 @@ void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& c
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 
-void launch_trace_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor) {
+void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor) {
     // cursor[0] = work cursor (zeroed by caller), cursor[1] = count
     k_set_u32<<<1, 1, 0, st>>>(cursor + 1, n);
-    k_trace<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
+    if (impl == 0) k_trace<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
+    else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
 }
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor) {
     k_trace_any<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, occluded, n, cursor);
@@ -162,6 +329,26 @@ void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float*
     k_math<<<(n + 255) / 256, 256, 0, st>>>(fn, a, b, out, n);
 }
 
+// ---- sample_tex / sky on caller-supplied coordinates (unit-test entry) ------------------------------------------------
+__global__ void k_sample(DevScene s, uint32_t tex, int sky, const float* __restrict__ in, float* __restrict__ out, uint32_t n, uint32_t tex_mod) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (tex_mod) tex = (tex + i) % tex_mod;               // a different texture per lane, as in k_shade
+    if (sky) { pt_v3 c = sky_radiance(s, pt_mk3(in[i * 3], in[i * 3 + 1], in[i * 3 + 2])); out[i * 4] = c.x; out[i * 4 + 1] = c.y; out[i * 4 + 2] = c.z; out[i * 4 + 3] = 1.0f; }
+    else { pt_v4 c = sample_tex(s, tex, in[i * 2], in[i * 2 + 1]); out[i * 4] = c.x; out[i * 4 + 1] = c.y; out[i * 4 + 2] = c.z; out[i * 4 + 3] = c.w; }
+}
+void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, const float* in, float* out, uint32_t n, uint32_t tex_mod) {
+    k_sample<<<(n + 127) / 128, 128, 0, st>>>(s, tex, sky, in, out, n, tex_mod);
+}
+
+// ---- probe of the texture unit's u8 -> f32 conversion (cudaReadModeNormalizedFloat) ----------------------------------
+__global__ void k_unorm_probe(unsigned long long obj, float* out) {
+    uint32_t i = threadIdx.x;
+    float4 v = tex2D<float4>((cudaTextureObject_t)obj, (float)i + 0.5f, 0.5f);
+    out[i] = v.x; out[256 + i] = v.w;
+}
+void launch_unorm_probe(cudaStream_t st, unsigned long long obj, float* out) { k_unorm_probe<<<1, 256, 0, st>>>(obj, out); }
+
 static int persistent_grid(const void* kernel, int threads, int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -170,7 +357,7 @@ static int persistent_grid(const void* kernel, int threads, int device) {
     if (sms < 1) sms = 1;
     return sms * per_sm;          // a multiple of the SM count (148 on B200): every SM holds its full share of resident CTAs
 }
-int trace_grid_size(int device) { return persistent_grid((const void*)k_trace, kTraceThreads, device); }
+int trace_grid_size(int device, int impl) { return persistent_grid(impl == 0 ? (const void*)k_trace : (const void*)k_trace_simple, kTraceThreads, device); }
 int shade_grid_size(int device) { return persistent_grid((const void*)k_shade, kShadeThreads, device); }
 
 }  // namespace ptc

@@ -5,9 +5,10 @@
 // One frame = raygen -> (trace -> shade) x (MAX_BOUNCES + 1).  Paths live in SoA queues indexed by
 // queue slot; `shade` compacts survivors into the next queue with a warp ballot and accumulates
 // finished paths straight into the COLOR plane (every pixel finishes exactly once per frame, so no
-// separate accumulate pass and no atomics on the image are needed).  trace and shade are persistent:
-// a fixed grid of warps pulls 32-ray batches from a device-side cursor, so ray counts never travel
-// to the host and a frame is one uninterrupted stream of launches.
+// separate accumulate pass and no atomics on the image are needed).  trace and shade are persistent
+// (a fixed grid sized to the SM count; trace pulls rays from a device-side cursor), and the per-segment
+// ray counts live in device memory, so they never travel to the host and a frame is one uninterrupted
+// stream of launches.
 #pragma once
 #include "pt_device.cuh"
 
@@ -38,17 +39,19 @@ struct Planes {
 };
 
 void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t npix);
-void launch_trace(cudaStream_t st, int grid, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
+void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays);
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
                   FrameCounters* fc, uint32_t segment, Planes planes);
 // standalone traversal of caller rays (tests/tools)
-void launch_trace_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
+void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor);
 
+void launch_unorm_probe(cudaStream_t st, unsigned long long tex_obj, float* out512);   // x and w channels of a 256x1 RGBA8 ramp
+void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, const float* in, float* out, uint32_t n, uint32_t tex_mod);
 void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n);
 
-int trace_grid_size(int device);
+int trace_grid_size(int device, int impl);   // impl 0 = k_trace (warp-cooperative), 1 = k_trace_simple
 int shade_grid_size(int device);
 
 }  // namespace ptc

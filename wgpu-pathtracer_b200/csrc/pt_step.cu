@@ -6,6 +6,7 @@
 #include "pt_kernels.cuh"
 #include "pt_error.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -40,7 +41,8 @@ struct ptc_step {
     // scene (device)
     F4* d_nodes = nullptr; F4* d_tris = nullptr; TriShade* d_shade = nullptr;
     MatDev* d_mats = nullptr; TexDev* d_texs = nullptr; ptc_triangle* d_lights = nullptr;
-    std::vector<cudaArray_t> arrays; std::vector<cudaTextureObject_t> tex_objs;
+    std::vector<cudaArray_t> pages; std::vector<cudaTextureObject_t> page_objs;   // texture atlas pages
+    uint32_t num_textures = 0; uint64_t atlas_bytes = 0;
     DevScene scene{};
     uint32_t num_lights = 0;
     // host tables for HIT_ID conversion
@@ -55,6 +57,7 @@ struct ptc_step {
     Planes planes{}; F4* owned_color = nullptr; F4* d_snapshot = nullptr; size_t snapshot_bytes = 0;
     uint32_t npix = 0;
     int trace_grid = 0, shade_grid = 0;
+    int trace_impl = 0;                            // 0 = k_trace, 1 = k_trace_simple (PTC_TRACE_IMPL=simple, A/B timing only)
     uint64_t frames = 0, launches = 0;
     // optional per-stage timing (CUDA events on the render stream)
     bool profiling = false;
@@ -85,6 +88,48 @@ static void prof_collect(ptc_step* s) {
 }
 
 static const uint32_t kFcRing = 64;
+
+// Reads a 256x1 RGBA8 ramp through a cudaReadModeNormalizedFloat texture object: out[0..255] = .x, out[256..511] = .w.
+static int unorm8_probe(float out[512]) {
+    uchar4 ramp[256];
+    for (int i = 0; i < 256; ++i) ramp[i] = make_uchar4((unsigned char)i, 0, 0, (unsigned char)(255 - i));
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; float* d_out = nullptr;
+    int rc = PTC_OK;
+    do {
+        if (cudaMallocArray(&arr, &cd, 256, 1) != cudaSuccess || cudaMalloc(&d_out, 512 * sizeof(float)) != cudaSuccess) { rc = PTC_ERR_OOM; break; }
+        if (cudaMemcpy2DToArray(arr, 0, 0, ramp, 256 * 4, 256 * 4, 1, cudaMemcpyHostToDevice) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
+        cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+        cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
+        if (cudaCreateTextureObject(&obj, &rd, &td, nullptr) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
+        launch_unorm_probe(nullptr, (unsigned long long)obj, d_out);
+        if (cudaMemcpy(out, d_out, 512 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
+    } while (0);
+    if (rc != PTC_OK) { set_error(std::string("unorm8 probe: ") + cudaGetErrorString(cudaGetLastError())); }
+    if (obj) cudaDestroyTextureObject(obj);
+    if (arr) cudaFreeArray(arr);
+    cudaFree(d_out);
+    return rc;
+}
+
+// 1 iff the texture unit converts every u8 value to exactly rn(v / 255.0f) — the value texture.rs:241 (`to_rgba32f`)
+// produces and the oracle uses.  Evaluated once per process on the device being created; decides the device
+// encoding of 8-bit textures (PTC_DEVTEX_UNORM8 vs read-bytes-and-divide).  PTC_UNORM8=div forces the latter.
+static int unorm8_hw_exact() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    const char* e = getenv("PTC_UNORM8");
+    if (e && std::strcmp(e, "div") == 0) { cached = 0; return 0; }
+    float out[512];
+    if (unorm8_probe(out) != PTC_OK) { cached = 0; return 0; }
+    int ok = 1;
+    for (int i = 0; i < 256; ++i)
+        if (out[i] != pt_div((float)i, 255.0f) || out[256 + i] != pt_div((float)(255 - i), 255.0f)) { ok = 0; break; }
+    cached = ok;
+    return ok;
+}
 
 static void free_frame_buffers(ptc_step* s) {
     for (int i = 0; i < 2; ++i) {
@@ -141,27 +186,80 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
         CK(cudaMemcpy(s->d_shade, ps.shade.data(), ps.shade.size() * sizeof(TriShade), cudaMemcpyHostToDevice));
     }
 
-    // textures: bindless table of texture objects over cudaArrays (texture.rs:232-336)
+    // textures (texture.rs:232-336): shelf-packed into atlas pages, one cudaArray + texture object per page
     std::vector<TexDev> texs(v->num_textures);
-    s->arrays.assign(v->num_textures, nullptr); s->tex_objs.assign(v->num_textures, 0);
-    for (uint64_t i = 0; i < v->num_textures; ++i) {
-        const ptc_texture_desc& t = v->textures[i];
-        TexDev& d = texs[i]; std::memset(&d, 0, sizeof(d));
-        d.w = t.width; d.h = t.height; d.fmt = t.format;
-        cudaChannelFormatDesc cd = t.format == PTC_TEXEL_RGBA8 ? cudaCreateChannelDesc<uchar4>() : cudaCreateChannelDesc<float4>();
-        size_t texel_bytes = t.format == PTC_TEXEL_RGBA8 ? 4 : 16;
-        CK(cudaMallocArray(&s->arrays[i], &cd, t.width, t.height));
-        CK(cudaMemcpy2DToArray(s->arrays[i], 0, 0, t.texels, (size_t)t.width * texel_bytes, (size_t)t.width * texel_bytes, t.height, cudaMemcpyHostToDevice));
-        cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd));
-        rd.resType = cudaResourceTypeArray; rd.res.array.array = s->arrays[i];
-        cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
-        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;   // Repeat is applied in integer texel space (pt_bilinear_axis)
-        td.filterMode = cudaFilterModePoint;                             // fp32 bilinear weights are applied in the kernel
-        td.readMode = cudaReadModeElementType;
-        td.normalizedCoords = 0;
-        CK(cudaCreateTextureObject(&s->tex_objs[i], &rd, &td, nullptr));
-        d.obj = (unsigned long long)s->tex_objs[i];
+    {
+        const int hw_unorm = unorm8_hw_exact();
+        int max_w = 0, max_h = 0;
+        CK(cudaDeviceGetAttribute(&max_w, cudaDevAttrMaxTexture2DWidth, s->device));
+        CK(cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DHeight, s->device));
+        const uint32_t lim_w = (uint32_t)std::min(max_w, 32768), lim_h = (uint32_t)std::min(max_h, 65536);
+        // 8-bit textures stay 8-bit (read through the texture unit's exact unorm conversion); without that guarantee
+        // they are expanded to f32 here with the host's rn(v / 255)
+        std::vector<std::vector<float>> expanded(v->num_textures);
+        struct Item { uint32_t idx, w, h; };
+        std::vector<Item> group[2];
+        for (uint64_t i = 0; i < v->num_textures; ++i) {
+            const ptc_texture_desc& t = v->textures[i];
+            if (t.width > lim_w || t.height > lim_h) { set_error("texture " + std::to_string(i) + " exceeds the device's 2D texture limits"); return PTC_ERR_INVALID; }
+            TexDev& d = texs[i]; std::memset(&d, 0, sizeof(d));
+            d.w = t.width; d.h = t.height; d.fmt = t.format;
+            int g = t.format == PTC_TEXEL_RGBA8 ? 0 : 1;
+            if (g == 0 && !hw_unorm) {
+                const uint8_t* p = (const uint8_t*)t.texels; size_t n = (size_t)t.width * t.height * 4;
+                expanded[i].resize(n);
+                for (size_t k = 0; k < n; ++k) expanded[i][k] = pt_div((float)p[k], 255.0f);
+                g = 1;
+            }
+            group[g].push_back(Item{(uint32_t)i, t.width, t.height});
+        }
+        for (int g = 0; g < 2; ++g) {
+            std::vector<Item>& items = group[g];
+            if (items.empty()) continue;
+            std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.h > b.h; });
+            uint64_t area = 0; uint32_t widest = 0;
+            for (const Item& it : items) { area += (uint64_t)it.w * it.h; widest = std::max(widest, it.w); }
+            uint32_t page_w = 4096;                       // roughly square pages: width = max(widest texture, ~sqrt(total area))
+            while ((uint64_t)page_w * page_w < area && page_w < lim_w) page_w *= 2;
+            page_w = std::min(std::max(page_w, widest), lim_w);
+            const size_t texel_bytes = g == 0 ? 4 : 16;
+            size_t k = 0;
+            while (k < items.size()) {
+                // one page: shelves of decreasing height, left to right
+                if (s->pages.size() >= PTC_MAX_TEX_PAGES) { set_error("textures exceed the atlas capacity (PTC_MAX_TEX_PAGES pages)"); return PTC_ERR_INVALID; }
+                const uint32_t page = (uint32_t)s->pages.size();
+                uint32_t x = 0, y = 0, shelf_h = 0, used_w = 0; size_t first = k;
+                for (; k < items.size(); ++k) {
+                    Item& it = items[k];
+                    if (x + it.w > page_w) { x = 0; y += shelf_h; shelf_h = 0; }
+                    if (y + it.h > lim_h) break;
+                    TexDev& d = texs[it.idx]; d.page = page; d.ax = x; d.ay = y;
+                    x += it.w; shelf_h = std::max(shelf_h, it.h); used_w = std::max(used_w, x);
+                }
+                if (k == first) { set_error("atlas packing made no progress"); return PTC_ERR_INVALID; }
+                const uint32_t used_h = y + shelf_h;
+                cudaChannelFormatDesc cd = g == 0 ? cudaCreateChannelDesc<uchar4>() : cudaCreateChannelDesc<float4>();
+                cudaArray_t arr = nullptr;
+                CK(cudaMallocArray(&arr, &cd, used_w, used_h));
+                s->pages.push_back(arr); s->page_objs.push_back(0);
+                for (size_t j = first; j < k; ++j) {
+                    const Item& it = items[j]; const TexDev& d = texs[it.idx];
+                    const void* src = expanded[it.idx].empty() ? v->textures[it.idx].texels : (const void*)expanded[it.idx].data();
+                    CK(cudaMemcpy2DToArray(arr, (size_t)d.ax * texel_bytes, d.ay, src, (size_t)it.w * texel_bytes, (size_t)it.w * texel_bytes, it.h, cudaMemcpyHostToDevice));
+                }
+                cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd));
+                rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+                cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+                td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;   // Repeat is applied in integer texel space (pt_bilinear_axis)
+                td.filterMode = cudaFilterModePoint;                             // fp32 bilinear weights are applied in the kernel
+                td.readMode = g == 0 ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+                td.normalizedCoords = 0;
+                CK(cudaCreateTextureObject(&s->page_objs[page], &rd, &td, nullptr));
+                s->atlas_bytes += (uint64_t)used_w * used_h * texel_bytes;
+            }
+        }
     }
+    s->num_textures = (uint32_t)texs.size();
     if (!texs.empty()) {
         CK(cudaMalloc(&s->d_texs, texs.size() * sizeof(TexDev)));
         CK(cudaMemcpy(s->d_texs, texs.data(), texs.size() * sizeof(TexDev), cudaMemcpyHostToDevice));
@@ -175,6 +273,8 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
     DevScene& ds = s->scene;
     ds.nodes = s->d_nodes; ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
     ds.num_nodes = (uint32_t)dev.nodes.size(); ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
+    ds.num_pages = (uint32_t)s->page_objs.size();
+    for (size_t p = 0; p < s->page_objs.size(); ++p) ds.page_obj[p] = (unsigned long long)s->page_objs[p];
     return PTC_OK;
 }
 
@@ -184,8 +284,8 @@ static void destroy_step(ptc_step* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     free_frame_buffers(s);
-    for (auto o : s->tex_objs) if (o) cudaDestroyTextureObject(o);
-    for (auto a : s->arrays) if (a) cudaFreeArray(a);
+    for (auto o : s->page_objs) if (o) cudaDestroyTextureObject(o);
+    for (auto a : s->pages) if (a) cudaFreeArray(a);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_shade); cudaFree(s->d_mats); cudaFree(s->d_texs); cudaFree(s->d_lights);
     cudaFree(s->d_fc); cudaFree(s->d_total_rays);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
@@ -226,7 +326,8 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
         if ((rc = alloc_frame_buffers(s, config->width, config->height)) != PTC_OK) break;
         if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
         cudaMemsetAsync(s->d_total_rays, 0, 8, s->stream);
-        s->trace_grid = trace_grid_size(cuda_device);
+        { const char* e = getenv("PTC_TRACE_IMPL"); s->trace_impl = (e && std::strcmp(e, "simple") == 0) ? 1 : 0; }
+        s->trace_grid = trace_grid_size(cuda_device, s->trace_impl);
         s->shade_grid = shade_grid_size(cuda_device);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
     } while (0);
@@ -258,7 +359,7 @@ PTC_API int ptc_render(ptc_step* s) {
     s->launches++;
     for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
         prof_mark(s, 1);
-        launch_trace(s->stream, s->trace_grid, s->scene, s->q[seg & 1], s->d_hits, fc, seg, s->d_total_rays);
+        launch_trace(s->stream, s->trace_grid, s->trace_impl, s->scene, s->q[seg & 1], s->d_hits, fc, seg, s->d_total_rays);
         prof_mark(s, 2);
         launch_shade(s->stream, s->shade_grid, s->scene, pc, s->q[seg & 1], s->q[(seg + 1) & 1], s->d_hits, fc, seg, s->planes);
         s->launches += 2;
@@ -448,7 +549,7 @@ PTC_API int ptc_trace_rays(ptc_step* s, const float* rays, uint64_t n, uint32_t*
         do {
             if (cudaMalloc(&d_h, n * 16) != cudaSuccess || cudaMalloc(&d_cur, 8) != cudaSuccess) { set_error("trace_rays: allocation failed"); rc = PTC_ERR_OOM; break; }
             cudaMemsetAsync(d_cur, 0, 8, s->stream);
-            launch_trace_n(s->stream, s->trace_grid, s->scene, d_o, d_d, d_h, (uint32_t)n, d_cur);
+            launch_trace_n(s->stream, s->trace_grid, s->trace_impl, s->scene, d_o, d_d, d_h, (uint32_t)n, d_cur);
             s->launches += 2;
             if (cudaMemcpyAsync(hits, d_h, n * 16, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) {
                 set_error(std::string("trace_rays: ") + cudaGetErrorString(cudaGetLastError())); rc = PTC_ERR_CUDA; break;
@@ -505,6 +606,34 @@ PTC_API int ptc_debug_math(int cuda_device, int fn, const float* a, const float*
     }
     cudaFree(da); cudaFree(db); cudaFree(dout);
     return rc;
+}
+
+PTC_API int ptc_debug_sample(ptc_step* s, int texture_index, const float* in, uint64_t n, float* rgba, int per_lane) {
+    if (!s || !in || !rgba || n == 0 || n > 0x7fffffffull) { set_error("bad argument"); return PTC_ERR_INVALID; }
+    const int sky = texture_index < 0;
+    if (!sky && (uint64_t)texture_index >= s->num_textures) { set_error("texture index out of range"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const size_t in_bytes = n * (sky ? 3 : 2) * sizeof(float);
+    float *d_in = nullptr, *d_out = nullptr;
+    int rc = PTC_OK;
+    if (cudaMalloc(&d_in, in_bytes) != cudaSuccess || cudaMalloc(&d_out, n * 16) != cudaSuccess) { set_error("debug_sample: allocation failed"); rc = PTC_ERR_OOM; }
+    if (rc == PTC_OK) {
+        cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, s->stream);
+        launch_sample(s->stream, s->scene, sky ? 0u : (uint32_t)texture_index, sky, d_in, d_out, (uint32_t)n, (!sky && per_lane) ? s->num_textures : 0u);
+        if (cudaMemcpyAsync(rgba, d_out, n * 16, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess) {
+            set_error(std::string("debug_sample: ") + cudaGetErrorString(cudaGetLastError())); rc = PTC_ERR_CUDA;
+        }
+    }
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+PTC_API int ptc_debug_unorm8(int cuda_device, float* out512) {
+    if (!out512) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (ptc_device_count() <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
+    CK(cudaSetDevice(cuda_device));
+    int rc = unorm8_probe(out512);
+    return rc != PTC_OK ? rc : (unorm8_hw_exact() ? 1 : 0);
 }
 
 PTC_API const char* ptc_last_error(void) { return g_last_error.c_str(); }

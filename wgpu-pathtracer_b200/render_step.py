@@ -122,6 +122,21 @@ class RTStep:
         check(lib().ptc_trace_rays_any(self._h, rays.ctypes.data_as(C.c_void_p), len(rays), occ.ctypes.data_as(C.c_void_p)))
         return occ
 
+    def sample_texture(self, index, uv, per_lane=False):
+        """the kernels' bilinear lookup of texture `index` at (n, 2) uv pairs -> (n, 4) rgba (unit-test entry);
+        per_lane: lookup i uses texture (index + i) % num_textures"""
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros((len(uv), 4), dtype=np.float32)
+        check(lib().ptc_debug_sample(self._h, int(index), uv.ctypes.data_as(C.c_void_p), len(uv), out.ctypes.data_as(C.c_void_p), int(per_lane)))
+        return out
+
+    def sky(self, dirs):
+        """the kernels' sky_color for (n, 3) directions -> (n, 3) rgb (unit-test entry)"""
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((len(dirs), 4), dtype=np.float32)
+        check(lib().ptc_debug_sample(self._h, -1, dirs.ctypes.data_as(C.c_void_p), len(dirs), out.ctypes.data_as(C.c_void_p), 0))
+        return out[:, :3].copy()
+
     def destroy(self):
         if self._h:
             lib().ptc_destroy(self._h)
