@@ -52,159 +52,100 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, cons
     }
 }
 
-// Production closest-hit kernel.  Same result as k_trace_simple ray for ray (the hit is the minimum of
-// (t, global triangle id) over all accepted triangles, which does not depend on visiting order), but the warp's
-// work is re-shaped so that both phases run dense:
-//   * node phase: every lane that owns a ray does ONE node step per iteration (both children of a BVH2 node, slab test
-//     of pt_device.cuh).  A lane that reaches a leaf does not test it: it appends the leaf's triangles to a per-warp
-//     list in shared memory as (lane, triangle) pairs and pops its stack, so it is back on an inner node next iteration.
-//   * triangle phase: when >= 32 pairs are pending the warp tests them 32 at a time, lane k taking pair k — the ray
-//     comes from shared memory, so a test is not tied to the lane that owns the ray.  Results are combined with a
-//     64-bit atomicMin on ((t bits) << 32 | triangle id) in shared memory: smaller t wins, equal t goes to the
-//     smaller id — exactly the tie rule of leaf_closest.  The winner then records its barycentrics.
-//   * a lane whose stack is empty and whose pairs are all resolved writes its hit and takes the next ray from the
-//     device cursor (one aggregated atomicAdd per refill), so lanes do not idle until the slowest ray of a batch ends.
-// The pruning distance each lane carries is refreshed after every triangle phase; between two phases it is stale
-// (larger), which costs a few extra node visits and never a wrong result.
-constexpr int kTraceWarps = kTraceThreads / 32;
-constexpr uint32_t kTriCap = 32 + 32 * 4;         // < 32 carried over + at most 4 per lane per iteration
-constexpr uint32_t kNoRay = 0xFFFFFFFFu;
-#ifndef PTC_WAIT_FLUSH
-#define PTC_WAIT_FLUSH 8                           // finished lanes that force a full flush
+// Production closest-hit kernel: same per-ray arithmetic and visiting order as k_trace_simple (node_test,
+// pt_ray_tri, near child first, ties to the smaller triangle id), re-scheduled at warp level:
+//   * every lane is a persistent ray slot.  A lane is in one of three states: at an inner node, at a leaf with
+//     triangles left to test, or idle (its ray finished / it has none).
+//   * each iteration the warp VOTES on what to run, and runs only that: a triangle phase (every lane at a leaf tests
+//     ONE triangle) when at least PTC_TRI_VOTE lanes wait at a leaf or nobody can take a node step; otherwise a node
+//     phase (every lane at an inner node tests both children).  k_trace_simple instead pays node test + a loop over
+//     up to 4 triangles on every iteration, the triangle part with ~13 % of the lanes active.
+//   * when PTC_REFILL_VOTE lanes are idle (or all are) they write their hits and take new rays from the device cursor
+//     with one aggregated atomicAdd, so a warp does not drain down to its slowest ray.
+// A lane waiting at a leaf does not traverse speculatively, so the nodes and triangles visited per ray are exactly
+// those of the plain loop (and of the oracle's counters).
+#ifndef PTC_TRI_VOTE
+#define PTC_TRI_VOTE 10
 #endif
+#ifndef PTC_REFILL_VOTE
+#define PTC_REFILL_VOTE 16
+#endif
+#ifndef PTC_TRACE_MIN_BLOCKS
+#define PTC_TRACE_MIN_BLOCKS 9
+#endif
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
-struct TraceWarp {
-    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];
-    unsigned long long best[32];                  // (t bits << 32) | global triangle id
-    float b1[32], b2[32];
-    uint32_t pend[32];                            // unresolved pairs per lane
-    uint32_t pair[kTriCap];                       // (lane << 27) | leaf-order triangle index
-};
-
-__global__ void __launch_bounds__(kTraceThreads) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+__global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
                                                           U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
                                                           uint32_t* cursor, unsigned long long* total_rays) {
-    __shared__ TraceWarp sh[kTraceWarps];
-    TraceWarp& ws = sh[threadIdx.x >> 5];
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     const uint32_t n = *count_ptr;
     if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
-    const unsigned long long kMissKey = ((unsigned long long)__float_as_uint(PT_RAY_TMAX) << 32) | 0xFFFFFFFFull;
 
     int stack[PTC_STACK_SIZE];
     int node = PTC_SENTINEL, sp = 0;
-    uint32_t ray = kNoRay;
+    uint32_t ray = kNoRay, tri_i = 0, tri_end = 0;
+    pt_v3 o = pt_mk3(0.0f, 0.0f, 0.0f), d = o;
     RaySlab r = {};
-    float tbest = PT_RAY_TMAX;
-    uint32_t npair = 0;                            // warp-uniform
+    HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
     bool exhausted = false;                        // warp-uniform: the cursor has passed n
-    ws.pend[lane] = 0;
-    __syncwarp();
 
     for (;;) {
-        // ---- refill idle lanes from the device cursor ----
-        const bool want = ray == kNoRay;
-        const uint32_t wm = __ballot_sync(FULL, want);
-        if (wm != 0 && !exhausted) {
-            const uint32_t k = __popc(wm);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(cursor, k);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + k >= n) exhausted = true;
-            const uint32_t i = base + __popc(wm & lt);
-            if (want && i < n) {
-                ray = i;
-                const F4 o = ld4(ray_o + i), d = ld4(ray_d + i);
-                ws.ox[lane] = o.x; ws.oy[lane] = o.y; ws.oz[lane] = o.z;
-                ws.dx[lane] = d.x; ws.dy[lane] = d.y; ws.dz[lane] = d.z;
-                ws.best[lane] = kMissKey; ws.b1[lane] = 0.0f; ws.b2[lane] = 0.0f;
-                const pt_v3 ov = pt_mk3(o.x, o.y, o.z), dv = pt_mk3(d.x, d.y, d.z);
-                r = make_ray_slab(ov, dv);
-                tbest = PT_RAY_TMAX;
-                stack[0] = PTC_SENTINEL; sp = 1;
-                node = (s.num_nodes != 0 && ray_is_finite(ov, dv)) ? 0 : PTC_SENTINEL;
+        const uint32_t idle = __ballot_sync(FULL, node == PTC_SENTINEL);
+        if (idle == FULL || (!exhausted && __popc(idle) >= PTC_REFILL_VOTE)) {
+            // ---- retire finished rays, refill idle lanes ----
+            if (node == PTC_SENTINEL && ray != kNoRay) {
+                reinterpret_cast<uint4*>(hits)[ray] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+                ray = kNoRay;
             }
+            if (!exhausted) {
+                const uint32_t k = __popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, k);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + k >= n) exhausted = true;
+                const uint32_t i = base + __popc(idle & lt);
+                if (node == PTC_SENTINEL && i < n) {
+                    ray = i;
+                    const F4 ro = ld4(ray_o + i), rd = ld4(ray_d + i);
+                    o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z);
+                    r = make_ray_slab(o, d);
+                    best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
+                    stack[0] = PTC_SENTINEL; sp = 1;
+                    tri_i = tri_end = 0;
+                    if (s.num_nodes != 0 && ray_is_finite(o, d)) node = 0;
+                }
+            }
+            if (__ballot_sync(FULL, ray != kNoRay) == 0) break;
+            continue;
         }
-        __syncwarp();
-        if (__ballot_sync(FULL, ray != kNoRay) == 0) break;
-
-        // ---- node phase ----
-        bool force;
-        for (;;) {
-            if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {                   // inner node
+        const uint32_t at_leaf = __ballot_sync(FULL, node < 0);
+        if (__popc(at_leaf) >= PTC_TRI_VOTE || (at_leaf | idle) == FULL) {
+            // ---- triangle phase: one triangle per waiting lane ----
+            if (node < 0) {
+                if (tri_i == tri_end) { const uint32_t enc = ~(uint32_t)node; tri_i = enc >> 3; tri_end = tri_i + (enc & 7u) + 1u; }
+                const F4* tp = s.tris + (size_t)tri_i * 3;
+                const F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+                float t, b1, b2;
+                if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                    const uint32_t id = f2u(a.w);
+                    if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+                }
+                if (++tri_i == tri_end) node = stack[--sp];
+            }
+        } else {
+            // ---- node phase: both children of one node per lane ----
+            if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
                 const F4* np = s.nodes + (size_t)node * 4;
-                const F4 q0 = ld4(np), q1 = ld4(np + 1), q2 = ld4(np + 2), q3 = ld4(np + 3);
+                F4 q0, q1, q2, q3; ld8(np, q0, q1); ld8(np + 2, q2, q3);
                 bool h0, h1; float tn0, tn1;
-                node_test(r, q0, q1, q2, tbest, h0, h1, tn0, tn1);
+                node_test(r, q0, q1, q2, best.t, h0, h1, tn0, tn1);
                 const int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
                 const bool swap = tn1 < tn0;
-                const int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                if (h0 && h1) { stack[sp++] = farc; node = nearc; }
+                if (h0 && h1) { stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }
                 else if (h0 || h1) node = h0 ? c0 : c1;
                 else node = stack[--sp];
-            }
-            // leaves: queue their triangles, continue with the next stack entry
-            const bool leaf = node < 0;
-            const uint32_t lm = __ballot_sync(FULL, leaf);
-            if (lm != 0) {
-                const uint32_t enc = ~(uint32_t)node;
-                const uint32_t c1m = leaf ? (enc & 7u) : 0u;                  // count - 1, in 0..3
-                const uint32_t m0 = __ballot_sync(FULL, (c1m & 1u) != 0), m1 = __ballot_sync(FULL, (c1m & 2u) != 0);
-                if (leaf) {
-                    const uint32_t pos = npair + __popc(lm & lt) + __popc(m0 & lt) + 2u * __popc(m1 & lt);
-                    const uint32_t first = enc >> 3, tag = lane << 27;
-                    for (uint32_t m = 0; m <= c1m; ++m) ws.pair[pos + m] = tag | (first + m);
-                    ws.pend[lane] += c1m + 1u;
-                    node = stack[--sp];
-                }
-                npair += __popc(lm) + __popc(m0) + 2u * __popc(m1);
-            }
-            const uint32_t busy = __ballot_sync(FULL, node != PTC_SENTINEL);
-            const uint32_t waiting = __ballot_sync(FULL, ray != kNoRay && node == PTC_SENTINEL);
-            force = busy == 0 || __popc(waiting) >= PTC_WAIT_FLUSH;
-            if (force || npair >= 32u) break;
-        }
-        __syncwarp();
-
-        // ---- triangle phase: full batches, plus the remainder when forced ----
-        const uint32_t nproc = force ? npair : (npair & ~31u);
-        for (uint32_t k0 = 0; k0 < nproc; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            bool hit = false; float t = 0.0f, b1 = 0.0f, b2 = 0.0f; uint32_t src = 0; unsigned long long key = 0;
-            if (k < nproc) {
-                const uint32_t e = ws.pair[k];
-                src = e >> 27;
-                const F4* tp = s.tris + (size_t)(e & 0x07FFFFFFu) * 3;
-                const F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-                const pt_v3 o = pt_mk3(ws.ox[src], ws.oy[src], ws.oz[src]), d = pt_mk3(ws.dx[src], ws.dy[src], ws.dz[src]);
-                hit = pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
-                                 PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2) != 0;
-                if (hit) {
-                    key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)f2u(a.w);   // t > 0: bit order == value order
-                    atomicMin(&ws.best[src], key);
-                }
-            }
-            __syncwarp();
-            if (hit && ws.best[src] == key) { ws.b1[src] = b1; ws.b2[src] = b2; }   // keys are unique per ray: one writer
-            __syncwarp();
-        }
-        // carry the remainder to the front of the list and recount what each lane still waits for
-        const uint32_t rem = npair - nproc;
-        const uint32_t keep = lane < rem ? ws.pair[nproc + lane] : 0u;
-        ws.pend[lane] = 0;
-        __syncwarp();
-        if (lane < rem) { ws.pair[lane] = keep; atomicAdd(&ws.pend[keep >> 27], 1u); }
-        npair = rem;
-        __syncwarp();
-
-        // ---- refresh pruning distances, retire finished rays ----
-        if (ray != kNoRay) {
-            const unsigned long long key = ws.best[lane];
-            tbest = __uint_as_float((uint32_t)(key >> 32));
-            if (node == PTC_SENTINEL && ws.pend[lane] == 0) {
-                reinterpret_cast<uint4*>(hits)[ray] = make_uint4((uint32_t)(key >> 32), __float_as_uint(ws.b1[lane]), __float_as_uint(ws.b2[lane]), (uint32_t)key);
-                ray = kNoRay;
             }
         }
     }
