@@ -37,6 +37,8 @@ WORKLOADS = {
     "sponza_1080p": dict(scene="sponza", width=1920, height=1080, max_bounces=4, config_index=2),
     "cornell_512": dict(scene="cornell", width=512, height=512, max_bounces=8, config_index=0),
     "dragon_1080p": dict(scene="dragon", width=1920, height=1080, max_bounces=4, config_index=1),
+    "classroom_1080p": dict(scene="classroom", width=1920, height=1080, max_bounces=4, config_index=3),
+    "san_miguel_4k": dict(scene="san_miguel", width=3840, height=2160, max_bounces=4, config_index=4),
 }
 
 

@@ -307,3 +307,53 @@ def test_sponza_1080p_properties(ptc, standins, oracle):
     tot = a.read(T.PLANE_COLOR) + b.read(T.PLANE_COLOR)
     assert (tot[..., 3] == frames).all()
     np.testing.assert_allclose(tot[..., :3] / frames, col[..., :3], rtol=1e-5, atol=1e-6)
+
+
+def band_parity(ptc, standins, oracle, scene, cam, W, H, frames, rows, **cfg_kw):
+    """Full-resolution render on the GPU; the oracle renders only rows [rows[0], rows[1]) of the same frames."""
+    T = ptc.types
+    cfg = ptc.make_config(W, H, **cfg_kw)
+    camera = standins.make_camera(cam, W, H)
+    step = ptc.RTStep.create(scene, cfg)
+    us = [camera.uniforms(frame=f) for f in range(1, frames + 1)]
+    for u in us:
+        step.update(u); step.render()
+    step.poll(True)
+    col = step.read(T.PLANE_COLOR)
+    assert (col[..., 3] == frames).all()
+    orc = oracle.OracleScene(scene, cfg)
+    ref = np.zeros((H, W, 4), np.float32)
+    for u in us:
+        r = orc.render_frame(u, ref, rows=rows)
+    band = slice(*rows)
+    assert np.array_equal(step.read(T.PLANE_HIT_ID)[band], r["hit_id"][band]), "primary hit ids differ"
+    finite = np.isfinite(ref[band]).all(axis=-1) & np.isfinite(col[band]).all(axis=-1)
+    assert np.array_equal(np.isfinite(ref[band]), np.isfinite(col[band]))
+    assert_radiance(col[band][finite], ref[band][finite])
+    assert np.array_equal(col[band], ref[band], equal_nan=True), "colour band is not bit-identical"
+    for plane, key in ((T.PLANE_DEPTH, "depth"), (T.PLANE_NORMAL, "normal"), (T.PLANE_ALBEDO, "albedo")):
+        assert np.array_equal(step.read(plane)[band], r[key][band], equal_nan=True), key
+    stats = step.stats()
+    step.destroy()
+    return stats
+
+
+def test_dragon_1080p_c2(ptc, standins, oracle):
+    """configs[1]: one 871 k-triangle glass mesh, 1920x1080 (2 of the 256 spp), band of 24 rows against the oracle."""
+    scene, cam = standins.dragon()
+    s = band_parity(ptc, standins, oracle, scene, cam, 1920, 1080, 2, (528, 552))
+    assert s["rays_traced"] >= 1920 * 1080 * 2
+
+
+@pytest.mark.parametrize("nee", [0.0, 0.5])
+def test_classroom_1080p_c4(ptc, standins, oracle, nee):
+    """configs[3]: ~0.6 M triangles, 79 constant materials, emitters; reference mode and the light-sampling branch."""
+    scene, cam = standins.classroom()
+    band_parity(ptc, standins, oracle, scene, cam, 1920, 1080, 2, (600, 616), send_to_light_probability=nee)
+
+
+def test_san_miguel_4k_c5(ptc, standins, oracle):
+    """configs[4]: 10.7 M triangles, 287 materials, 323 textures, 3840x2160; band of 8 rows against the oracle."""
+    scene, cam = standins.san_miguel()
+    assert scene.num_triangles > 10_000_000
+    band_parity(ptc, standins, oracle, scene, cam, 3840, 2160, 1, (1200, 1208))

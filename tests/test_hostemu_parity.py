@@ -62,6 +62,20 @@ def test_sponza_standin_band(ptc, standins, oracle, hostemu):
     assert (ro["hit_id"][..., 0] != 0xFFFFFFFF).mean() > 0.9
 
 
+@pytest.mark.parametrize("name,kw,cfg", [
+    ("dragon", {"n": 120}, {}),
+    ("classroom", {"detail": 0.04}, {}),
+    ("classroom", {"detail": 0.04}, {"send_to_light_probability": 0.5}),      # emitters present: exercises the light list
+    ("san_miguel", {"n_plants": 12, "leaves_per_plant": 400, "tex_size": 32}, {}),
+])
+def test_reduced_baseline_standins(ptc, standins, oracle, hostemu, name, kw, cfg):
+    """Small cuts of the C2 / C4 / C5 stand-ins (same generators, fewer triangles): every plane bit-identical."""
+    scene, cam = standins.BUILDERS[name](**kw)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 160, 90, 2, **cfg)
+    assert_identical(ro, re)
+    assert (ro["hit_id"][..., 0] != 0xFFFFFFFF).mean() > 0.5
+
+
 def test_trace_rays_product_bvh_vs_brute(ptc, standins, oracle, hostemu):
     from conftest import random_rays
     scene, _ = standins.random_soup(30000, seed=11, textured=False, tri_size=0.12)

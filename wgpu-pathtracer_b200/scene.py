@@ -157,6 +157,27 @@ class Scene:
         self.meshes = np.concatenate([self.meshes, mesh])
         return len(self.meshes) - 1
 
+    def add_meshes(self, parts):
+        """Append many meshes at once: parts = iterable of (positions, normals, uvs, indices, material_index).
+        Same records as repeated add_mesh, one concatenation (stand-ins with thousands of meshes)."""
+        V, I, M = [self.vertices], [self.indices], [self.meshes]
+        nv0, ni0 = len(self.vertices), len(self.indices)
+        for positions, normals, uvs, indices, material_index in parts:
+            positions = np.asarray(positions, dtype=np.float32).reshape(-1, 3)
+            v = np.zeros(len(positions), dtype=T.VERTEX_DT)
+            v["position"] = positions
+            if normals is not None:
+                v["normal"] = np.asarray(normals, dtype=np.float32).reshape(-1, 3)
+            if uvs is not None:
+                v["uv"] = np.asarray(uvs, dtype=np.float32).reshape(-1, 2)
+            idx = np.asarray(indices, dtype=np.uint32).reshape(-1)
+            mesh = np.zeros(1, dtype=T.MESH_DT)
+            mesh["vertex_offset"], mesh["vertex_count"] = nv0, len(v)
+            mesh["index_offset"], mesh["index_count"], mesh["material_index"] = ni0, len(idx), material_index
+            V.append(v); I.append(idx + np.uint32(nv0)); M.append(mesh)
+            nv0 += len(v); ni0 += len(idx)
+        self.vertices, self.indices, self.meshes = np.concatenate(V), np.concatenate(I), np.concatenate(M)
+
     @property
     def num_triangles(self):
         return len(self.indices) // 3

@@ -455,7 +455,178 @@ def random_soup(n_tris, seed=1, env=None, textured=True, extent=4.0, tri_size=0.
     return sc, {"position": (-extent * 1.6, 0.3, 0.2), "fov": 60.0, "target": (0.0, 0.0, 0.0)}
 
 
-BUILDERS = {"cornell": cornell, "dragon": dragon, "sponza": sponza, "furnace": furnace, "empty": empty}
+# --------------------------------------------------------------------------------------------------------
+# C4 classroom / C5 san_miguel
+# --------------------------------------------------------------------------------------------------------
+def _classroom_mtl(n_mats=79):
+    """79 constant-colour materials as res/classroom/classroom.mtl: no textures, no Tf, three emitters (Ke 5 / 7 / 15)."""
+    rng = np.random.RandomState(0xC1A55)
+    out = []
+    for i in range(n_mats):
+        kd = 0.15 + 0.75 * rng.rand(3)
+        out.append(f"newmtl cl_{i:02d}")
+        out += ["Ns %.6f" % (20 + 400 * rng.rand()), "Ka 1.000000 1.000000 1.000000", "Kd %.6f %.6f %.6f" % tuple(kd),
+                "Ks %.6f %.6f %.6f" % ((0.5 * rng.rand(),) * 3), "Ni 1.450000", "d 1.000000", "illum 2"]
+        if i in (10, 11, 12):
+            out.append("Ke %d %d %d" % (((5, 7, 15)[i - 10],) * 3))
+        else:
+            out.append("Ke 0.000000 0.000000 0.000000")
+        if i % 9 == 4:
+            out += ["Pr %.6f" % (0.05 + 0.5 * rng.rand()), "Pm %.6f" % (0.2 + 0.6 * rng.rand())]
+        out.append("")
+    return "\n".join(out) + "\n"
+
+
+def classroom(env=None, detail=1.32):
+    """C4: a classroom of ~0.6 M triangles (detail=1): shell, 30 desks + chairs, shelves of books, blinds, a globe, ceiling
+    light panels (the emitters), 79 constant-colour materials, no transmission."""
+    sc = Scene(env or make_envmap())
+    mats = _materials_from_mtl(sc, _classroom_mtl())
+    mid = [mats[f"cl_{i:02d}"] for i in range(79)]
+    k = lambda n: max(1, int(round(n * np.sqrt(detail))))
+    X, Y, Z = 12.0, 3.2, 9.0
+    parts = []
+    add = lambda geo, m: parts.append((*geo, mid[m]))
+    add(grid((0, 0, 0), (0, 0, Z), (X, 0, 0), k(150), k(200), uv_scale=(6, 8)), 0)                        # floor
+    add(grid((0, Y, 0), (X, 0, 0), (0, 0, Z), k(100), k(75), uv_scale=(6, 8)), 1)                         # ceiling
+    add(grid((0, 0, 0), (X, 0, 0), (0, Y, 0), k(120), k(32)), 2)                                          # walls
+    add(grid((0, 0, Z), (0, Y, 0), (X, 0, 0), k(32), k(120)), 2)
+    add(grid((0, 0, 0), (0, Y, 0), (0, 0, Z), k(32), k(90)), 3)
+    add(grid((X, 0, 0), (0, 0, Z), (0, Y, 0), k(90), k(32)), 3)
+    for i in range(6):                                                                                     # light panels (emitters 10..12)
+        x, z = 2.0 + (i % 3) * 4.0, 2.5 + (i // 3) * 4.0
+        add(grid((x - 0.6, Y - 0.02, z - 0.3), (1.2, 0, 0), (0, 0, 0.6), 4, 2), 10 + i % 3)
+    leg = lambda cx, cz, h: revolve(lambda t: 0.02 + 0.004 * np.sin(t * 30), 0.0, h, k(12), k(10), center=(cx, cz))
+    m = 13
+    for r in range(5):                                                                                     # desks and chairs
+        for c in range(6):
+            x, z = 1.6 + c * 1.7, 1.5 + r * 1.45
+            add(grid((x - 0.6, 0.74, z - 0.3), (0, 0, 0.6), (1.2, 0, 0), k(14), k(28),
+                     displace=lambda S, Tt: 0.004 * np.sin(S * 40) * np.sin(Tt * 40)), m % 60 + 13)
+            add(grid((x - 0.6, 0.71, z - 0.3), (1.2, 0, 0), (0, 0, 0.6), k(28), k(14)), m % 60 + 13)
+            for dx, dz in ((-0.55, -0.25), (0.55, -0.25), (-0.55, 0.25), (0.55, 0.25)):
+                add(leg(x + dx, z + dz, 0.71), (m + 1) % 60 + 13)
+            cz = z + 0.55
+            add(grid((x - 0.22, 0.45, cz - 0.2), (0, 0, 0.4), (0.44, 0, 0), k(26), k(26),
+                     displace=lambda S, Tt: -0.03 * np.sin(S * np.pi) * np.sin(Tt * np.pi)), (m + 2) % 60 + 13)
+            add(grid((x - 0.22, 0.5, cz + 0.2), (0.44, 0, 0), (0, 0.45, 0), k(26), k(26),
+                     displace=lambda S, Tt: 0.04 * np.sin(S * np.pi)), (m + 3) % 60 + 13)
+            for dx, dz in ((-0.2, -0.18), (0.2, -0.18), (-0.2, 0.18), (0.2, 0.18)):
+                add(leg(x + dx, cz + dz, 0.45), (m + 4) % 60 + 13)
+            m += 5
+    rng = np.random.RandomState(0xB00C)
+    for sh in range(3):                                                                                    # shelves of books along the +x wall
+        for row in range(4):
+            z = 0.6
+            while z < Z - 0.8:
+                w, h, dpt = 0.02 + 0.05 * rng.rand(), 0.18 + 0.1 * rng.rand(), 0.15 + 0.06 * rng.rand()
+                y0 = 0.3 + row * 0.45
+                add(box((X - 0.05 - dpt - sh * 0.0, y0, z), (X - 0.05, y0 + h, z + w)), int(rng.randint(13, 79)))
+                z += w + 0.004
+    for i in range(4):                                                                                     # window blinds on the z = 0 wall
+        add(grid((1.2 + i * 2.6, 1.0, 0.03), (2.0, 0, 0), (0, 1.8, 0), k(100), k(60),
+                 displace=lambda S, Tt: 0.015 * np.sin(Tt * 150.0)), 5 + i % 4)
+    def gdisp(th, ph):
+        return 0.01 * np.sin(9 * th) * np.sin(7 * ph) + 0.004 * np.sin(41 * th) * np.sin(37 * ph)
+    add(sphere_displaced(k(200), k(200), 0.25, (X - 1.2, 1.1, Z - 1.0), gdisp), 9)                        # globe
+    add(grid((3.0, 0.9, Z - 0.03), (0, 1.4, 0), (6.0, 0, 0), k(80), k(160), displace=lambda S, Tt: -0.003 * (np.sin(S * 60) * np.sin(Tt * 90) > 0.6)), 4)  # board
+    sc.add_meshes(parts)
+    cam = {"position": (0.6, 1.5, 0.7), "fov": 60.0, "target": (8.0, 1.0, 6.0)}
+    return sc, cam
+
+
+def _san_miguel_mtl(n_mats=287, n_kd=200, n_bump=100, n_pr=23):
+    """287 materials / 323 texture files as res/san_miguel: map_Kd on the first 200, map_bump on 100, map_Pr on 23;
+    five carry Tf (glass)."""
+    rng = np.random.RandomState(0x5A17)
+    out = []
+    for i in range(n_mats):
+        out.append(f"newmtl sm_{i:03d}")
+        out += ["Ns %.6f" % (10 + 90 * rng.rand()), "Ni 1.500000", "d 1.000000", "illum 2",
+                "Kd %.6f %.6f %.6f" % tuple(0.2 + 0.7 * rng.rand(3)), "Ks 0.000000 0.000000 0.000000", "Ke 0.000000 0.000000 0.000000"]
+        if i < n_kd:
+            out.append(f"map_Kd kd_{i:03d}.png")
+        if 50 <= i < 50 + n_bump:
+            out.append(f"map_bump bump_{i:03d}.png")
+        if 120 <= i < 120 + n_pr:
+            out.append(f"map_Pr pr_{i:03d}.png")
+        if i in (240, 250, 260, 270, 280):
+            out += ["Tf 1.000000 1.000000 1.000000", "Pr 0.020000"]
+        out.append("")
+    return "\n".join(out) + "\n"
+
+
+def san_miguel(env=None, n_plants=2000, leaves_per_plant=2500, tex_size=256):
+    """C5: courtyard shell + n_plants procedural plants of leaves_per_plant leaf quads (2 triangles each; 10 M triangles
+    at the defaults), 287 materials, 323 textures, materials assigned by hash => divergent shading."""
+    sc = Scene(env or make_envmap())
+    rng = np.random.RandomState(0x5A17)
+
+    def decode(path):
+        name = path.rsplit("/", 1)[-1]
+        kseed = int(name.split("_")[1].split(".")[0])
+        if name.startswith("kd"):
+            r = np.random.RandomState(kseed)
+            return make_albedo_texture(tex_size, tex_size, 1000 + kseed, tuple(0.3 + 0.7 * r.rand(3)))
+        if name.startswith("bump"):
+            return make_bump_texture(tex_size, tex_size, 2000 + kseed)
+        t = make_bump_texture(tex_size // 2, tex_size // 2, 3000 + kseed)
+        return t
+
+    mats = _materials_from_mtl(sc, _san_miguel_mtl(), decode=decode)
+    mid = np.array([mats[f"sm_{i:03d}"] for i in range(287)], dtype=np.uint32)
+    Lx, Lz, Hy = 40.0, 30.0, 12.0
+    parts = []
+    sub = 400 if n_plants >= 500 else 120
+    parts.append((*grid((-Lx / 2, 0, -Lz / 2), (0, 0, Lz), (Lx, 0, 0), sub, sub, uv_scale=(10, 10),
+                        displace=lambda S, Tt: 0.03 * np.sin(S * 60) * np.sin(Tt * 45)), mid[0]))             # ground
+    wsub = sub // 2
+    parts.append((*grid((-Lx / 2, 0, -Lz / 2), (Lx, 0, 0), (0, Hy, 0), wsub, wsub // 2, uv_scale=(8, 3)), mid[1]))
+    parts.append((*grid((-Lx / 2, 0, Lz / 2), (0, Hy, 0), (Lx, 0, 0), wsub // 2, wsub, uv_scale=(3, 8)), mid[2]))
+    parts.append((*grid((-Lx / 2, 0, -Lz / 2), (0, Hy, 0), (0, 0, Lz), wsub // 2, wsub, uv_scale=(3, 8)), mid[3]))
+    parts.append((*grid((Lx / 2, 0, -Lz / 2), (0, 0, Lz), (0, Hy, 0), wsub, wsub // 2, uv_scale=(8, 3)), mid[4]))
+    # arcade columns around the courtyard
+    ncol = 0
+    for x in np.linspace(-Lx / 2 + 3, Lx / 2 - 3, 14):
+        for z in (-Lz / 2 + 3.5, Lz / 2 - 3.5):
+            parts.append((*revolve(lambda t: 0.28 + 0.05 * np.cos(t * np.pi * 2) ** 6, 0.0, 5.0, 24, 24, center=(x, z), uv_scale=(2, 4)), mid[5 + ncol % 20]))
+            ncol += 1
+    # plants: leaf quads in an ellipsoidal crown above a stem
+    side = int(np.ceil(np.sqrt(n_plants)))
+    for pi in range(n_plants):
+        gx, gz = pi % side, pi // side
+        cx = -Lx / 2 + 5 + (gx + rng.rand()) * (Lx - 10) / side
+        cz = -Lz / 2 + 5 + (gz + rng.rand()) * (Lz - 10) / side
+        hgt = 1.0 + 2.5 * rng.rand()
+        n = leaves_per_plant
+        u = rng.randn(n, 3).astype(F)
+        u /= np.maximum(np.linalg.norm(u, axis=1, keepdims=True), 1e-6)
+        rad = (rng.rand(n, 1).astype(F)) ** F(1 / 3)
+        c = np.array([cx, hgt, cz], F) + u * rad * np.array([0.7, 0.9, 0.7], F)
+        a = rng.randn(n, 3).astype(F); a /= np.maximum(np.linalg.norm(a, axis=1, keepdims=True), 1e-6)
+        b = np.cross(a, rng.randn(n, 3).astype(F)); b /= np.maximum(np.linalg.norm(b, axis=1, keepdims=True), 1e-6)
+        sz = F(0.03) + F(0.05) * rng.rand(n, 1).astype(F)
+        a *= sz; b *= sz * F(0.6)
+        P = np.stack([c - a - b, c + a - b, c + a + b, c - a + b], axis=1).reshape(-1, 3)
+        nrm = np.cross(a, b); nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-12)
+        N = np.repeat(nrm, 4, axis=0)
+        UV = np.tile(np.array([[0, 0], [1, 0], [1, 1], [0, 1]], F), (n, 1))
+        q = (np.arange(n, dtype=np.uint32) * 4)[:, None]
+        idx = (q + np.array([0, 1, 2, 0, 2, 3], np.uint32)[None, :]).reshape(-1)
+        # 3 meshes per plant with hashed materials (divergent shading inside one crown)
+        cuts = [0, n // 3, 2 * n // 3, n]
+        for j in range(3):
+            lo, hi = cuts[j], cuts[j + 1]
+            mat = mid[(pi * 2654435761 + j * 40503) % 287]
+            parts.append((P[lo * 4:hi * 4], N[lo * 4:hi * 4], UV[lo * 4:hi * 4], idx[lo * 6:hi * 6] - np.uint32(lo * 4), mat))
+        parts.append((*revolve(lambda t: 0.06 * (1 - 0.5 * t), 0.0, hgt, 8, 6, center=(cx, cz)), mid[30 + pi % 10]))
+    sc.add_meshes(parts)
+    cam = {"position": (-Lx / 2 + 2.0, 2.2, -Lz / 2 + 2.5), "fov": 60.0, "target": (4.0, 1.8, 3.0)}
+    return sc, cam
+
+
+BUILDERS = {"cornell": cornell, "dragon": dragon, "sponza": sponza, "furnace": furnace, "empty": empty,
+            "classroom": classroom, "san_miguel": san_miguel}
 
 
 def make_camera(cam, width, height):
