@@ -9,8 +9,9 @@ pixel = raygen + 5 x (closest-hit traversal + shade/accumulate) kernels, MAX_BOU
 value    Mrays/s (trace_ray invocations per second, whole job), inputs resident in HBM, device-timed with CUDA events on
          the step's stream, max over ranks.
 e2e      the same through the reference-facing call sequence with HOST buffers: every step uploads its 112-byte Uniforms
-         (ptc_update), renders (ptc_render) and reads the accumulated rgba32f image back into pinned host memory
-         (ptc_read_async, overlapped on a copy stream; drained before the clock stops).
+         (ptc_update), renders (ptc_render), tonemaps to the 8-bit display image (ptc_blit, the reference's BlitStep) and
+         reads that image back into pinned host memory (ptc_read_async, overlapped on a copy stream; drained before the
+         clock stops).
 roofline the closest-hit traversal kernel: algorithmic bytes/ray (64 B x BVH2 inner nodes + 48 B x triangles tested, both
          counted by the oracle on the identical rays, + 64 B ray/hit record) x rays / its CUDA-event time, against the
          measured HBM copy peak in MEASURED_PEAKS.json.
@@ -59,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -198,7 +199,7 @@ def main():
     out = torch.zeros(H, W, 4, device=f"cuda:{local}", dtype=torch.float32)
     step.set_output(out.data_ptr())                       # the caller injects the accumulation target (raytracer.rs:86)
     ext = torch.cuda.ExternalStream(step.stream, device=local)
-    pinned = torch.empty(H, W, 4, dtype=torch.float32).pin_memory()
+    pinned = torch.empty(H, W, 4, dtype=torch.uint8).pin_memory()   # the displayed image: tonemapped sRGB RGBA8 (BlitStep's output)
 
     def frame_of(i):                                      # frame sharding: the union over ranks is frames 1..N*K (+warm-up)
         return 1 + rank + i * world
@@ -257,7 +258,8 @@ def main():
     for i in range(K):
         u = camera.uniforms(frame=frame_of(Wm + K + i))    # host-side Uniforms built per step, 112 B H2D as kernel arguments
         step.update(u); step.render()
-        step.read_async(T.PLANE_COLOR, pinned.data_ptr())  # D2H of the accumulated image, overlapped on the copy stream
+        step.blit()                                        # BlitStep: tonemap + sRGB encode of the accumulated image (1 kernel)
+        step.read_async(T.PLANE_DISPLAY, pinned.data_ptr())  # D2H of the frame a user sees, overlapped on the copy stream
     if dist is not None:
         with torch.cuda.stream(ext):
             dist.reduce(out, dst=0)
@@ -280,17 +282,23 @@ def main():
         return
 
     # ---- CPU baseline + algorithmic bytes per ray (oracle counters on the identical rays) ------------------------
+    # N = 1: the oracle is timed on a bounded sample (cpu_baseline).  N > 1: one untimed oracle frame only supplies the
+    # BVH2 node/triangle counters the roofline figure is defined on.
     base = None
     if not args.no_cpu_baseline:
-        base = cpu_baseline(pkg, w, scene, camera, args.cpu_seconds, T.ACCUM_MEAN, first_frame=frame_of(Wm))
-    nodes_per_ray = base["nodes_per_ray"] if base else float("nan")
-    tris_per_ray = base["tris_per_ray"] if base else float("nan")
-    bytes_per_ray = 64.0 * nodes_per_ray + 48.0 * tris_per_ray + 64.0
+        base = cpu_baseline(pkg, w, scene, camera, args.cpu_seconds if world == 1 else 0.0, T.ACCUM_MEAN, first_frame=frame_of(Wm))
+    nodes_per_ray = base["nodes_per_ray"] if base else None
+    tris_per_ray = base["tris_per_ray"] if base else None
+    bytes_per_ray = 64.0 * nodes_per_ray + 48.0 * tris_per_ray + 64.0 if base else None
     peak, peak_src = load_peaks()
     trace_ms, trace_n = prof["trace"]["ms"], prof["trace"]["launches"]
     rank_rays = rays / world                                # per-rank share (identical work per rank up to RNG streams)
-    achieved = bytes_per_ray * rank_rays / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else float("nan")
+    achieved = bytes_per_ray * rank_rays / (trace_ms * 1e-3) / 1e9 if (base and trace_ms > 0) else None
     bvh = step.bvh_info()
+    traffic = None                                          # dram bytes per k_trace launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "trace_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -299,19 +307,20 @@ def main():
                    "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: each frame streams ~%.0f MB of path-state queues; the %.1f MB BVH is L2-resident by design" % (
                        W * H * 144 / 1e6, (bvh["node_bytes"] + bvh["triangle_bytes"]) / 1e6)},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 16,
-                "note": "per step: ptc_update(host Uniforms) + ptc_render + ptc_read_async(COLOR -> pinned host); wall clock incl. final copy drain"},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 4,
+                "note": "per step: ptc_update(host Uniforms, 112 B) + ptc_render + ptc_blit (tonemap to the 8-bit display image, as the reference's "
+                        "BlitStep) + ptc_read_async(DISPLAY -> pinned host, overlapped on a copy stream); wall clock incl. final copy drain"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_trace (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak if achieved is not None else None, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                      "rays_per_launch": rank_rays / max(trace_n, 1), "avg_launch_ms": trace_ms / max(trace_n, 1), "launches": int(trace_n),
                      "kernel_share_of_step": trace_ms / ms if ms > 0 else None,
                      "stage_ms": {k: v["ms"] for k, v in prof.items()}},
-        "cpu_baseline": ({k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} if base else None),
+        "cpu_baseline": ({k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} if (base and world == 1) else None),
     }
-    print(json.dumps(line))
+    print(json.dumps(line, allow_nan=False))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -70,6 +70,20 @@ PTC_API int ptc_set_output(ptc_step* step, void* device_rgba32f);
 /* zero the accumulation plane (what recreating the texture does) */
 PTC_API int ptc_reset_accumulation(ptc_step* step);
 
+/* ---- display path: the two passes that follow the path tracer in Raytracer::update (raytracer.rs:215-241) ---- */
+
+/* replaces BlitStep::render (src/render_steps/blit.rs:176-205, shaders/blit/blit.wgsl:35-40, shaders/common/color.wgsl:4-27):
+ * Khronos PBR-neutral tonemap of an rgba32f image + the surface's sRGB encode (wgpu_util.rs:235-238) into the 8-bit
+ * DISPLAY plane.  src = device pointer to width*height float4, NULL = the COLOR plane.  Enqueued on the step's stream. */
+PTC_API int ptc_blit(ptc_step* step, const void* src_device_rgba32f);
+
+/* replaces RayprojectStep::render (src/render_steps/rayproject.rs:205-249, shaders/rayproject/rayproject.wgsl:45-74):
+ * forward-splats every pixel of the last real frame (src, NULL = COLOR) by its first-hit distance (DEPTH plane, rendered
+ * with `prev`) to where it lands under camera `cur`, into the REPROJECTED plane.  Targets nothing lands on keep their
+ * previous content (the reference never clears blit_storage_texture); where several sources land on one target the
+ * reference lets the stores race — here the highest source pixel index wins. */
+PTC_API int ptc_rayproject(ptc_step* step, const ptc_uniforms* prev, const ptc_uniforms* cur, const void* src_device_rgba32f);
+
 PTC_API void ptc_destroy(ptc_step* step);
 
 /* ---- results -------------------------------------------------------------- */

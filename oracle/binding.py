@@ -47,6 +47,8 @@ def lib():
     L.orc_sample_texture.restype, L.orc_sample_texture.argtypes = None, [vp, u32, vp, u64, vp]
     L.orc_sky.restype, L.orc_sky.argtypes = None, [vp, vp, u64, vp]
     L.orc_bvh_info.restype, L.orc_bvh_info.argtypes = None, [vp, P(u64)]
+    L.orc_rayproject.restype, L.orc_rayproject.argtypes = None, [P(T.Uniforms), P(T.Uniforms), vp, vp]
+    L.orc_blit.restype, L.orc_blit.argtypes = None, [vp, u64, vp, vp]
     _lib = L
     return L
 
@@ -143,6 +145,24 @@ def camera_uniforms(width, height, fov, pos, theta_x=0.0, theta_y=0.0, extra_upd
     p = (C.c_float * 3)(*[float(v) for v in pos])
     lib().orc_camera(width, height, fov, p, theta_x, theta_y, extra_updates, C.byref(u))
     return u
+
+
+def rayproject(cur, prev, depth):
+    """rayproject.wgsl: target pixel index of every source pixel (0xFFFFFFFF = store dropped)."""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    out = np.zeros(depth.size, dtype=np.uint32)
+    lib().orc_rayproject(C.byref(cur), C.byref(prev), depth.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def blit(rgba):
+    """blit.wgsl + sRGB surface: (..., 4) float32 -> (..., 4) uint8, plus the tonemapped linear rgb."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    n = rgba.size // 4
+    out = np.zeros(rgba.shape, dtype=np.uint8)
+    tm = np.zeros(rgba.shape[:-1] + (3,), dtype=np.float32)
+    lib().orc_blit(rgba.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), tm.ctypes.data_as(C.c_void_p))
+    return out, tm
 
 
 def math_fn(fn, a, b=None):

@@ -692,6 +692,60 @@ int orc_trace_rays_any(const orc_scene* o, const float* rays, uint64_t n, uint8_
     return 0;
 }
 
+// ---- display path: rayproject.wgsl:45-74 and blit.wgsl:35-40 / color.wgsl:4-27 --------------------------------------
+// Restated from the WGSL line by line.  dst_of_src[i] = target pixel index of source pixel i, or 0xFFFFFFFF when the
+// textureStore is out of bounds (dropped).  Collisions (several sources, one target) are a data race in the reference;
+// callers resolve them (the product lets the highest source index win).
+__attribute__((visibility("default")))
+void orc_rayproject(const ptc_uniforms* cur, const ptc_uniforms* prev, const float* depth, uint32_t* dst_of_src) {
+    const ptc_camera& c = cur->camera; const ptc_camera& q = prev->camera;
+    auto v3 = [](const float* a) { return pt_mk3(a[0], a[1], a[2]); };
+    for (uint32_t y = 0; y < q.height; ++y) for (uint32_t x = 0; x < q.width; ++x) {
+        uint32_t i = y * q.width + x;
+        pt_v3 prev_ray_origin_at_xy = pt_add(pt_add(v3(q.first_pixel_pos), pt_scale(v3(q.pixel_space_x), (float)x)), pt_scale(v3(q.pixel_space_y), (float)y));
+        pt_v3 prev_ray_dir_at_xy = pt_normalize(pt_sub(prev_ray_origin_at_xy, v3(q.position)));
+        float first_t = depth[i];
+        pt_v3 new_center_to_old_pix = pt_sub(pt_add(prev_ray_origin_at_xy, pt_scale(prev_ray_dir_at_xy, first_t)), v3(c.position));
+        float den = pt_dot(new_center_to_old_pix, pt_sub(v3(c.lookat), v3(c.position)));
+        pt_v3 on_vp = pt_mk3(pt_div(new_center_to_old_pix.x, den), pt_div(new_center_to_old_pix.y, den), pt_div(new_center_to_old_pix.z, den));
+        float px = pt_div(pt_dot(pt_normalize(v3(c.pixel_space_x)), on_vp), pt_length(v3(c.pixel_space_x))) + (float)c.width * 0.5f + 0.5f;
+        float py = pt_div(pt_dot(pt_normalize(v3(c.pixel_space_y)), on_vp), pt_length(v3(c.pixel_space_y))) + (float)c.height * 0.5f + 0.5f;
+        dst_of_src[i] = 0xFFFFFFFFu;
+        if (std::isnan(px) || std::isnan(py)) continue;                      // u32(NaN): undefined in WGSL, dropped here
+        float rx = std::nearbyintf(px), ry = std::nearbyintf(py);            // round(): half to even
+        uint32_t ux = rx <= 0.0f ? 0u : (rx >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)rx);   // u32(): saturating
+        uint32_t uy = ry <= 0.0f ? 0u : (ry >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)ry);
+        if (ux >= c.width || uy >= c.height) continue;                       // textureStore out of bounds: no-op
+        dst_of_src[i] = uy * c.width + ux;
+    }
+}
+
+// to_khronos_pbr_neutral (color.wgsl:4-27) followed by the *Srgb surface's encode; rgba in, 4 x u8 out per pixel
+__attribute__((visibility("default")))
+void orc_blit(const float* rgba, uint64_t n, uint8_t* out, float* tonemapped) {
+    const float F90 = 0.04f;
+    for (uint64_t i = 0; i < n; ++i) {
+        float r = rgba[i * 4], g = rgba[i * 4 + 1], b = rgba[i * 4 + 2], a = rgba[i * 4 + 3];
+        float k_s = 0.8f - F90, k_d = 0.15f;
+        float x = pt_min(pt_min(r, g), b);
+        float f = (x - pt_div(x * x, 4.0f * F90)) * (x <= 2.0f * F90 ? 1.0f : 0.0f) + F90 * (x > 2.0f * F90 ? 1.0f : 0.0f);
+        float p = pt_max(pt_max(r - f, g - f), b - f);
+        float p_n = 1.0f - pt_div((1.0f - k_s) * (1.0f - k_s), p + 1.0f - 2.0f * k_s);
+        float gg = pt_div(1.0f, k_d * (p - p_n) + 1.0f);
+        float lo = p <= k_s ? 1.0f : 0.0f, hi = p > k_s ? 1.0f : 0.0f;
+        float c[3] = {r, g, b};
+        for (int k = 0; k < 3; ++k) {
+            float v = (c[k] - f) * lo + ((c[k] - f) * pt_div(p_n, p) * gg + p_n * (1.0f - gg)) * hi;
+            if (tonemapped) tonemapped[i * 3 + k] = v;
+            uint32_t q;
+            if (!(v > 0.0f)) q = 0; else if (v >= 1.0f) q = 255;
+            else { double e = v <= 0.0031308f ? 12.92 * v : 1.055 * std::pow((double)v, 1.0 / 2.4) - 0.055; q = (uint32_t)(e * 255.0 + 0.5); }
+            out[i * 4 + k] = (uint8_t)q;
+        }
+        out[i * 4 + 3] = !(a > 0.0f) ? 0 : (a >= 1.0f ? 255 : (uint8_t)(a * 255.0f + 0.5f));
+    }
+}
+
 // ---- unit-level entry points for known-answer tests -------------------------
 __attribute__((visibility("default")))
 uint32_t orc_jenkins_hash(uint32_t x) { return jenkins_hash(x); }

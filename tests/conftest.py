@@ -53,7 +53,21 @@ class HostEmu:
         L.emu_trace_rays.restype, L.emu_trace_rays.argtypes = i32, [vp, vp, u64, vp, vp]
         L.emu_trace_rays_any.restype, L.emu_trace_rays_any.argtypes = i32, [vp, vp, u64, vp]
         L.emu_bvh_info.restype, L.emu_bvh_info.argtypes = None, [vp, C.POINTER(u64)]
+        L.emu_rayproject.restype, L.emu_rayproject.argtypes = None, [C.POINTER(T.Uniforms), C.POINTER(T.Uniforms), vp, vp]
+        L.emu_blit.restype, L.emu_blit.argtypes = None, [vp, u64, vp]
         self.L = L
+
+    def rayproject(self, cur, prev, depth):
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        out = np.zeros(depth.size, dtype=np.uint32)
+        self.L.emu_rayproject(C.byref(cur), C.byref(prev), depth.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def blit(self, rgba):
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        out = np.zeros(rgba.shape, dtype=np.uint8)
+        self.L.emu_blit(rgba.ctypes.data_as(C.c_void_p), rgba.size // 4, out.ctypes.data_as(C.c_void_p))
+        return out
 
     def scene(self, scene, config):
         return HostEmuScene(self.L, scene, config)

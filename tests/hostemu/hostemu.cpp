@@ -136,4 +136,23 @@ int emu_trace_rays_any(const emu_scene* e, const float* rays, uint64_t n, uint8_
     return 0;
 }
 
+// display path (device functions of pt_device.cuh on the host)
+__attribute__((visibility("default")))
+void emu_rayproject(const ptc_uniforms* cur, const ptc_uniforms* prev, const float* depth, uint32_t* dst_of_src) {
+    const uint32_t W = prev->camera.width, H = prev->camera.height;
+    for (uint32_t y = 0; y < H; ++y) for (uint32_t x = 0; x < W; ++x) {
+        uint32_t dx, dy, i = y * W + x;
+        dst_of_src[i] = reproject_pixel(cur->camera, prev->camera, x, y, depth[i], dx, dy) ? dy * cur->camera.width + dx : 0xFFFFFFFFu;
+    }
+}
+
+__attribute__((visibility("default")))
+void emu_blit(const float* rgba, uint64_t n, uint8_t* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        pt_v3 t = tonemap_khronos_pbr_neutral(pt_mk3(rgba[i * 4], rgba[i * 4 + 1], rgba[i * 4 + 2]));
+        out[i * 4] = (uint8_t)encode_srgb8(t.x); out[i * 4 + 1] = (uint8_t)encode_srgb8(t.y); out[i * 4 + 2] = (uint8_t)encode_srgb8(t.z);
+        out[i * 4 + 3] = (uint8_t)encode_unorm8(rgba[i * 4 + 3]);
+    }
+}
+
 }  // extern "C"

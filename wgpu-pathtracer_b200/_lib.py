@@ -40,6 +40,8 @@ def lib():
         "ptc_resize": (i32, [vp, u32, u32]),
         "ptc_set_output": (i32, [vp, vp]),
         "ptc_reset_accumulation": (i32, [vp]),
+        "ptc_blit": (i32, [vp, vp]),
+        "ptc_rayproject": (i32, [vp, P(T.Uniforms), P(T.Uniforms), vp]),
         "ptc_destroy": (None, [vp]),
         "ptc_read": (i32, [vp, i32, vp, sz]),
         "ptc_read_async": (i32, [vp, i32, vp]),

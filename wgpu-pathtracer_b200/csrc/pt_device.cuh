@@ -544,4 +544,62 @@ PT_HD void accumulate_pixel(F4* px, pt_v3 c, uint32_t accum_mode, uint32_t is_gr
     *px = o;
 }
 
+// ---- display path: the two passes the reference runs right after the path tracer -------------------------------------
+
+// rayproject.wgsl:45-74 — where source pixel (x, y) of the last real frame lands under the current camera, given its
+// first-hit distance.  Returns false when the store would be dropped (outside the target, or a non-finite position:
+// WGSL leaves u32(NaN) undefined, this project drops it).  Negative coordinates saturate to 0 as WGSL's u32() does.
+PT_HD bool reproject_pixel(const ptc_camera& cam, const ptc_camera& prev, uint32_t x, uint32_t y, float first_t, uint32_t& dx, uint32_t& dy) {
+    const pt_v3 pfp = pt_mk3(prev.first_pixel_pos[0], prev.first_pixel_pos[1], prev.first_pixel_pos[2]);
+    const pt_v3 ppx = pt_mk3(prev.pixel_space_x[0], prev.pixel_space_x[1], prev.pixel_space_x[2]);
+    const pt_v3 ppy = pt_mk3(prev.pixel_space_y[0], prev.pixel_space_y[1], prev.pixel_space_y[2]);
+    const pt_v3 ppos = pt_mk3(prev.position[0], prev.position[1], prev.position[2]);
+    const pt_v3 cpos = pt_mk3(cam.position[0], cam.position[1], cam.position[2]);
+    const pt_v3 clook = pt_mk3(cam.lookat[0], cam.lookat[1], cam.lookat[2]);
+    const pt_v3 cpx = pt_mk3(cam.pixel_space_x[0], cam.pixel_space_x[1], cam.pixel_space_x[2]);
+    const pt_v3 cpy = pt_mk3(cam.pixel_space_y[0], cam.pixel_space_y[1], cam.pixel_space_y[2]);
+    const pt_v3 o = pt_add(pt_add(pfp, pt_scale(ppx, (float)x)), pt_scale(ppy, (float)y));
+    const pt_v3 d = pt_normalize(pt_sub(o, ppos));
+    const pt_v3 p = pt_sub(pt_add(o, pt_scale(d, first_t)), cpos);
+    const float depth = pt_dot(p, pt_sub(clook, cpos));
+    const pt_v3 on_plane = pt_mk3(pt_div(p.x, depth), pt_div(p.y, depth), pt_div(p.z, depth));
+    const float rx = pt_div(pt_dot(pt_normalize(cpx), on_plane), pt_length(cpx)) + (float)cam.width * 0.5f + 0.5f;
+    const float ry = pt_div(pt_dot(pt_normalize(cpy), on_plane), pt_length(cpy)) + (float)cam.height * 0.5f + 0.5f;
+    if (!(rx == rx) || !(ry == ry)) return false;
+    const float qx = rintf(rx), qy = rintf(ry);               // WGSL round(): ties to even
+    if (qx >= (float)cam.width || qy >= (float)cam.height) return false;
+    dx = qx <= 0.0f ? 0u : (uint32_t)qx;
+    dy = qy <= 0.0f ? 0u : (uint32_t)qy;
+    return true;
+}
+
+// color.wgsl:4-27 to_khronos_pbr_neutral, F90 = 0.04 (shader_definitions.rs:7); both arms are evaluated and blended
+// with 0/1 weights as the shader does (so a black pixel yields NaN exactly like the reference's).
+PT_HD pt_v3 tonemap_khronos_pbr_neutral(pt_v3 c) {
+    const float F90 = 0.04f, k_s = 0.8f - F90, k_d = 0.15f;
+    const float x = pt_min(pt_min(c.x, c.y), c.z);
+    const float f = (x - pt_div(x * x, 4.0f * F90)) * (x <= 2.0f * F90 ? 1.0f : 0.0f) + F90 * (x > 2.0f * F90 ? 1.0f : 0.0f);
+    const float p = pt_max(pt_max(c.x - f, c.y - f), c.z - f);
+    const float p_n = 1.0f - pt_div((1.0f - k_s) * (1.0f - k_s), p + 1.0f - 2.0f * k_s);
+    const float g = pt_div(1.0f, k_d * (p - p_n) + 1.0f);
+    const float lo = p <= k_s ? 1.0f : 0.0f, hi = p > k_s ? 1.0f : 0.0f;
+    const float r = pt_div(p_n, p), off = p_n * (1.0f - g);
+    return pt_mk3((c.x - f) * lo + ((c.x - f) * r * g + off) * hi,
+                  (c.y - f) * lo + ((c.y - f) * r * g + off) * hi,
+                  (c.z - f) * lo + ((c.z - f) * r * g + off) * hi);
+}
+// what writing a linear value to the reference's *Srgb surface format does (wgpu_util.rs:235-238): clamp, sRGB OETF,
+// round to 8 bits; NaN -> 0.
+PT_HD uint32_t encode_srgb8(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v >= 1.0f) return 255u;
+    const float e = v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+    return (uint32_t)(e * 255.0f + 0.5f);
+}
+PT_HD uint32_t encode_unorm8(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v >= 1.0f) return 255u;
+    return (uint32_t)(v * 255.0f + 0.5f);
+}
+
 }  // namespace ptc

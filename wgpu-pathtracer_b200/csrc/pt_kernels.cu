@@ -270,6 +270,40 @@ void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float*
     k_math<<<(n + 255) / 256, 256, 0, st>>>(fn, a, b, out, n);
 }
 
+// ---- display path (the reference's pp queue: rayproject.wgsl + blit.wgsl) --------------------------------------------
+// rayproject is a forward splat with a data race in the reference (several source pixels may store to one target;
+// whichever store lands last wins).  Here the race is resolved deterministically — the highest source index wins —
+// in two passes: sources claim their target with atomicMax, targets then gather from their owner.
+__global__ void k_reproject_claim(ptc_camera cam, ptc_camera prev, const float* __restrict__ depth, uint32_t* __restrict__ owner) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prev.width * prev.height) return;
+    const uint32_t x = i % prev.width, y = i / prev.width;
+    uint32_t dx, dy;
+    if (reproject_pixel(cam, prev, x, y, depth[i], dx, dy)) atomicMax(&owner[dy * cam.width + dx], i + 1u);
+}
+__global__ void k_reproject_gather(uint32_t* __restrict__ owner, const F4* __restrict__ src, F4* __restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t o = owner[i];
+    if (o != 0u) { dst[i] = src[o - 1u]; owner[i] = 0u; }       // untouched targets keep their previous content, as out_tex does
+}
+// blit.wgsl:35-40 + the surface's sRGB encode: one RGBA8 texel per pixel
+__global__ void k_blit(const F4* __restrict__ src, uchar4* __restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F4 c = ld4(src + i);
+    const pt_v3 t = tonemap_khronos_pbr_neutral(pt_mk3(c.x, c.y, c.z));
+    dst[i] = make_uchar4((unsigned char)encode_srgb8(t.x), (unsigned char)encode_srgb8(t.y), (unsigned char)encode_srgb8(t.z), (unsigned char)encode_unorm8(c.w));
+}
+void launch_reproject(cudaStream_t st, const ptc_camera& cam, const ptc_camera& prev, const float* depth, uint32_t* owner, const F4* src, F4* dst) {
+    const uint32_t ns = prev.width * prev.height, nd = cam.width * cam.height;
+    k_reproject_claim<<<(ns + 255) / 256, 256, 0, st>>>(cam, prev, depth, owner);
+    k_reproject_gather<<<(nd + 255) / 256, 256, 0, st>>>(owner, src, dst, nd);
+}
+void launch_blit(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n) {
+    k_blit<<<(n + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<uchar4*>(dst_rgba8), n);
+}
+
 // ---- sample_tex / sky on caller-supplied coordinates (unit-test entry) ------------------------------------------------
 __global__ void k_sample(DevScene s, uint32_t tex, int sky, const float* __restrict__ in, float* __restrict__ out, uint32_t n, uint32_t tex_mod) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,6 +47,9 @@ void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& c
 void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor);
 
+// display path: rayproject.wgsl (forward reprojection of the last real frame) and blit.wgsl (tonemap to the 8-bit surface)
+void launch_reproject(cudaStream_t st, const ptc_camera& cam, const ptc_camera& prev, const float* depth, uint32_t* owner, const F4* src, F4* dst);
+void launch_blit(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n);
 void launch_unorm_probe(cudaStream_t st, unsigned long long tex_obj, float* out512);   // x and w channels of a 256x1 RGBA8 ramp
 void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, const float* in, float* out, uint32_t n, uint32_t tex_mod);
 void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n);

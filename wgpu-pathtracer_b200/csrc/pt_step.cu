@@ -55,6 +55,8 @@ struct ptc_step {
     uint32_t fc_next = 0;
     unsigned long long* d_total_rays = nullptr;
     Planes planes{}; F4* owned_color = nullptr; F4* d_snapshot = nullptr; size_t snapshot_bytes = 0;
+    // display path (allocated on first use): tonemapped RGBA8 image, reprojected rgba32f image, splat ownership
+    void* d_display = nullptr; F4* d_reprojected = nullptr; uint32_t* d_owner = nullptr;
     uint32_t npix = 0;
     int trace_grid = 0, shade_grid = 0;
     int trace_impl = 0;                            // 0 = k_trace, 1 = k_trace_simple (PTC_TRACE_IMPL=simple, A/B timing only)
@@ -140,6 +142,7 @@ static void free_frame_buffers(ptc_step* s) {
     cudaFree(s->owned_color); s->owned_color = nullptr;
     cudaFree(s->planes.depth); cudaFree(s->planes.normal); cudaFree(s->planes.albedo); cudaFree(s->planes.hit_tri);
     cudaFree(s->d_snapshot); s->d_snapshot = nullptr; s->snapshot_bytes = 0;
+    cudaFree(s->d_display); s->d_display = nullptr; cudaFree(s->d_reprojected); s->d_reprojected = nullptr; cudaFree(s->d_owner); s->d_owner = nullptr;
     s->planes = Planes{};
 }
 
@@ -409,6 +412,32 @@ PTC_API int ptc_reset_accumulation(ptc_step* s) {
     return PTC_OK;
 }
 
+PTC_API int ptc_blit(ptc_step* s, const void* src_device_rgba32f) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    if (!s->d_display) CK(cudaMalloc(&s->d_display, (size_t)s->npix * 4));
+    launch_blit(s->stream, src_device_rgba32f ? (const F4*)src_device_rgba32f : s->planes.color, s->d_display, s->npix);
+    s->launches += 1;
+    CK(cudaGetLastError());
+    return PTC_OK;
+}
+
+PTC_API int ptc_rayproject(ptc_step* s, const ptc_uniforms* prev, const ptc_uniforms* cur, const void* src_device_rgba32f) {
+    if (!s || !prev || !cur) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (prev->camera.width != s->cfg.width || prev->camera.height != s->cfg.height || cur->camera.width != s->cfg.width || cur->camera.height != s->cfg.height) {
+        set_error("rayproject: camera size differs from step size"); return PTC_ERR_INVALID;
+    }
+    CK(cudaSetDevice(s->device));
+    if (!s->d_reprojected) {
+        CK(cudaMalloc(&s->d_reprojected, (size_t)s->npix * 16)); CK(cudaMalloc(&s->d_owner, (size_t)s->npix * 4));
+        CK(cudaMemsetAsync(s->d_reprojected, 0, (size_t)s->npix * 16, s->stream)); CK(cudaMemsetAsync(s->d_owner, 0, (size_t)s->npix * 4, s->stream));
+    }
+    launch_reproject(s->stream, cur->camera, prev->camera, s->planes.depth, s->d_owner, src_device_rgba32f ? (const F4*)src_device_rgba32f : s->planes.color, s->d_reprojected);
+    s->launches += 2;
+    CK(cudaGetLastError());
+    return PTC_OK;
+}
+
 PTC_API void ptc_destroy(ptc_step* s) { destroy_step(s); }
 
 static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
@@ -418,6 +447,8 @@ static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
         case PTC_PLANE_NORMAL: *p = s->planes.normal; *px_bytes = 16; return true;
         case PTC_PLANE_ALBEDO: *p = s->planes.albedo; *px_bytes = 16; return true;
         case PTC_PLANE_HIT_ID: *p = s->planes.hit_tri; *px_bytes = 4; return true;
+        case PTC_PLANE_DISPLAY: *p = s->d_display; *px_bytes = 4; return s->d_display != nullptr;
+        case PTC_PLANE_REPROJECTED: *p = s->d_reprojected; *px_bytes = 16; return s->d_reprojected != nullptr;
     }
     return false;
 }
@@ -425,7 +456,7 @@ static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
 PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
     if (!s || !dst) { set_error("null argument"); return PTC_ERR_INVALID; }
     void* src; size_t pb;
-    if (!plane_ptr(s, plane, &src, &pb)) { set_error("unknown plane"); return PTC_ERR_INVALID; }
+    if (!plane_ptr(s, plane, &src, &pb)) { set_error("unknown plane, or a display-path plane that has not been produced yet"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     const uint32_t W = s->cfg.width, H = s->cfg.height;
     if (plane == PTC_PLANE_HIT_ID) {
@@ -454,7 +485,7 @@ PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
 PTC_API int ptc_read_async(ptc_step* s, int plane, void* dst_pinned) {
     if (!s || !dst_pinned) { set_error("null argument"); return PTC_ERR_INVALID; }
     void* src; size_t pb;
-    if (plane == PTC_PLANE_HIT_ID || !plane_ptr(s, plane, &src, &pb)) { set_error("plane not readable asynchronously"); return PTC_ERR_INVALID; }
+    if (plane == PTC_PLANE_HIT_ID || !plane_ptr(s, plane, &src, &pb)) { set_error("plane not readable asynchronously (or not produced yet)"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     size_t bytes = (size_t)s->npix * pb;
     if (s->snapshot_bytes < bytes) {

@@ -64,10 +64,19 @@ class RTStep:
         w, h = self.config.width, self.config.height
         shape, dt = {T.PLANE_COLOR: ((h, w, 4), np.float32), T.PLANE_DEPTH: ((h, w), np.float32),
                      T.PLANE_NORMAL: ((h, w, 4), np.float32), T.PLANE_ALBEDO: ((h, w, 4), np.float32),
-                     T.PLANE_HIT_ID: ((h, w, 2), np.uint32)}[plane]
+                     T.PLANE_HIT_ID: ((h, w, 2), np.uint32), T.PLANE_DISPLAY: ((h, w, 4), np.uint8),
+                     T.PLANE_REPROJECTED: ((h, w, 4), np.float32)}[plane]
         out = np.empty(shape, dtype=dt)
         check(lib().ptc_read(self._h, plane, out.ctypes.data_as(C.c_void_p), 0))
         return out
+
+    def blit(self, src_device_ptr=None):
+        """BlitStep::render: tonemap + sRGB-encode the COLOR plane (or `src`) into the 8-bit DISPLAY plane."""
+        check(lib().ptc_blit(self._h, C.c_void_p(src_device_ptr) if src_device_ptr else None))
+
+    def rayproject(self, prev_uniforms, cur_uniforms, src_device_ptr=None):
+        """RayprojectStep::render: reproject the last real frame from `prev` to `cur` into the REPROJECTED plane."""
+        check(lib().ptc_rayproject(self._h, C.byref(prev_uniforms), C.byref(cur_uniforms), C.c_void_p(src_device_ptr) if src_device_ptr else None))
 
     def read_async(self, plane, pinned_ptr):
         check(lib().ptc_read_async(self._h, plane, C.c_void_p(pinned_ptr)))
