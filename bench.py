@@ -76,6 +76,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)          # nvidia-smi must be gone before anything else is timed
+        except Exception:
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         for ts, line in self.rows:
             if not (t0 - 0.05 <= ts <= t1 + 0.15):
@@ -249,32 +253,35 @@ def main():
     value = rays / (ms * 1e-3) / 1e6
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------------------------
-    step.reset_accumulation(); step.poll(True)
-    rays0 = step.stats()["rays_traced"]
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_e0 = time.perf_counter()
-    e0.record(ext)
-    for i in range(K):
-        u = camera.uniforms(frame=frame_of(Wm + K + i))    # host-side Uniforms built per step, 112 B H2D as kernel arguments
-        step.update(u); step.render()
-        step.blit()                                        # BlitStep: tonemap + sRGB encode of the accumulated image (1 kernel)
-        step.read_async(T.PLANE_DISPLAY, pinned.data_ptr())  # D2H of the frame a user sees, overlapped on the copy stream
-    if dist is not None:
-        with torch.cuda.stream(ext):
-            dist.reduce(out, dst=0)
-    e1.record(ext)
-    e1.synchronize()
-    step.read_wait()
-    barrier()
-    e2e_s = time.perf_counter() - t_e0                      # includes the drain of the last host copy
-    e2e_rays = float(step.stats()["rays_traced"] - rays0)
-    es = torch.tensor([e2e_s, e2e_rays], device=f"cuda:{local}", dtype=torch.float64)
-    if dist is not None:
-        mx = es.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = es.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_rays = float(mx[0]), float(sm[1])
-    e2e_value = e2e_rays / e2e_s / 1e6
+    # K steps, repeated E2E_REPS times; the reported value is the MEDIAN repetition (all are listed in e2e.runs):
+    # a single wall-clock pass is exposed to host-side noise (other tenants' PCIe traffic, nvidia-smi holding driver locks).
+    E2E_REPS = 3
+    runs = []
+    for rep in range(E2E_REPS):
+        step.reset_accumulation(); step.poll(True)
+        rays0 = step.stats()["rays_traced"]
+        barrier()
+        t_e0 = time.perf_counter()
+        for i in range(K):
+            u = camera.uniforms(frame=frame_of(Wm + K * (rep + 1) + i))   # host-side Uniforms built per step, 112 B H2D as kernel arguments
+            step.update(u); step.render()
+            step.blit()                                        # BlitStep: tonemap + sRGB encode of the accumulated image (1 kernel)
+            step.read_async(T.PLANE_DISPLAY, pinned.data_ptr())  # D2H of the frame a user sees, overlapped on the copy stream
+        if dist is not None:
+            with torch.cuda.stream(ext):
+                dist.reduce(out, dst=0)
+        step.poll(True)
+        step.read_wait()
+        barrier()
+        e2e_s = time.perf_counter() - t_e0                      # includes the drain of the last host copy
+        e2e_rays = float(step.stats()["rays_traced"] - rays0)
+        es = torch.tensor([e2e_s, e2e_rays], device=f"cuda:{local}", dtype=torch.float64)
+        if dist is not None:
+            mx = es.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = es.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            e2e_s, e2e_rays = float(mx[0]), float(sm[1])
+        runs.append(e2e_rays / e2e_s / 1e6)
+    e2e_value = float(np.median(runs))
 
     if rank != 0:
         if dist is not None:

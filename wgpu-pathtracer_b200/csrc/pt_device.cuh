@@ -440,30 +440,44 @@ PT_HD void scatter_regular(uint32_t& rng, pt_v3 ro, pt_v3 rd, float t, pt_v3 n, 
 // (sample_material, rt_helpers.wgsl:17-42; 1x1 textures were folded to constants at upload), a path that escaped
 // needs the environment lookup (sky.wgsl:1-12).  Each lane walks its own list, so in a warp the lanes sample
 // different slots of different materials in the same pass instead of each `if (slot)` serialising the warp.
-PT_HD BounceOut shade_bounce(const DevScene& s, const PathCfg& cfg, const PathState& ps, const HitRec& hit, uint32_t bounce) {
-    BounceOut out;
-    out.alive = false;
+//
+// shade_surface is everything that does not need the path's throughput / accumulated colour (mask, acc): the kernel
+// loads those two queue entries only afterwards, so they are not live across the BSDF code (k_shade is register-bound:
+// at 64 registers every spilled value is local-memory traffic, measured at ~45 % of the kernel's L2 sectors before this split).
+enum SurfaceKind { SURF_MISS = 0, SURF_LIGHT = 1, SURF_LAST = 2, SURF_CONTINUE = 3 };
+struct SurfaceOut {
+    uint32_t kind;
+    pt_v3 light;                  // sky radiance (SURF_MISS) or the hit's emissive colour
+    pt_v3 atten;                  // throughput factor of this bounce
+    pt_v3 next_o, next_d;         // scattered ray (SURF_CONTINUE)
+    uint32_t rng;
+    float first_t; pt_v3 first_normal, first_albedo;   // first-hit aux (bounce 0)
+};
+
+PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_o, pt_v3 ray_d, uint32_t rng_in, const HitRec& hit, uint32_t bounce) {
+    SurfaceOut out;
     out.first_t = 0.0f; out.first_normal = pt_mk3(0.0f, 0.0f, 0.0f); out.first_albedo = pt_mk3(0.0f, 0.0f, 0.0f);
-    out.next = ps;
+    out.atten = pt_mk3(0.0f, 0.0f, 0.0f); out.next_o = ray_o; out.next_d = ray_d; out.rng = rng_in;
     const bool miss = hit.tri == 0xFFFFFFFFu;
-    F4 q0 = {0, 0, 0, 0}, q1 = q0, q2 = q0;
-    float w0 = 0.0f, u = 0.0f, v = 0.0f;
+    pt_v3 n = pt_mk3(0.0f, 0.0f, 0.0f);
+    float u = 0.0f, v = 0.0f;
     MatEval m;
     m.albedo = m.tsn = m.emissive = pt_mk3(0.0f, 0.0f, 0.0f);
     m.roughness = m.metallic = m.transmission = m.ior = m.anisotropy = 0.0f;
     const MatDev* mp = s.mats;
     uint32_t todo;
     if (miss) {                                                            // :229-232
-        sky_uv(ps.d, u, v);
+        sky_uv(ray_d, u, v);
         todo = 1u << SLOT_SKY;
     } else {
         // rt_helpers.wgsl:57-67 through the re-packed per-triangle record
         const TriShade& ts = s.shade[hit.tri];
-        q0 = ld4(&ts.q[0]); q1 = ld4(&ts.q[1]); q2 = ld4(&ts.q[2]);
-        const F4 q3 = ld4(&ts.q[3]);
-        w0 = 1.0f - hit.b1 - hit.b2;
+        const F4 q0 = ld4(&ts.q[0]), q1 = ld4(&ts.q[1]), q2 = ld4(&ts.q[2]), q3 = ld4(&ts.q[3]);
+        const float w0 = 1.0f - hit.b1 - hit.b2;
         u = q0.w * w0 + q2.w * hit.b1 + q3.y * hit.b2;
         v = q1.w * w0 + q3.x * hit.b1 + q3.z * hit.b2;
+        // interpolated normal now (3 live values instead of the three vertex normals across the texture loop), :85
+        n = pt_normalize(pt_add(pt_add(pt_scale(pt_mk3(q0.x, q0.y, q0.z), w0), pt_scale(pt_mk3(q1.x, q1.y, q1.z), hit.b1)), pt_scale(pt_mk3(q2.x, q2.y, q2.z), hit.b2)));
         mp = s.mats + f2u(q3.w);
         m.albedo = pt_mk3(mp->albedo[0], mp->albedo[1], mp->albedo[2]);
         m.tsn = pt_mk3(mp->tsn[0], mp->tsn[1], mp->tsn[2]);
@@ -487,45 +501,63 @@ PT_HD BounceOut shade_bounce(const DevScene& s, const PathCfg& cfg, const PathSt
             default: sky = pt_mk3(c.x, c.y, c.z); break;
         }
     }
-    if (miss) {
-        out.radiance = pt_add(ps.acc, pt_mul(sky, ps.mask));
-        return out;
-    }
+    if (miss) { out.kind = SURF_MISS; out.light = sky; return out; }
     bool hit_light = pt_dot(m.emissive, pt_mk3(1.0f, 1.0f, 1.0f)) > 0.0f;   // rt_helpers.wgsl:70
 
-    uint32_t rng = ps.rng;
-    pt_v3 n0 = pt_mk3(q0.x, q0.y, q0.z), n1 = pt_mk3(q1.x, q1.y, q1.z), n2 = pt_mk3(q2.x, q2.y, q2.z);
-    pt_v3 n = pt_normalize(pt_add(pt_add(pt_scale(n0, w0), pt_scale(n1, hit.b1)), pt_scale(n2, hit.b2)));   // :85
+    uint32_t rng = rng_in;
     pt_v3 so, sd, atten, sn;
     bool regular = rng_next_f32(rng) < 1.0f - cfg.send_to_light_probability;   // :170
     if (!regular) {
         // light_scatter, :48-73 (the probe trace of triangle_pdf only feeds the never-read `importance`)
+        const F4 qn = ld4(&s.shade[hit.tri].q[0]);                          // vertex 0's normal (re-read: rare branch)
+        const pt_v3 n0 = pt_mk3(qn.x, qn.y, qn.z);
         const ptc_triangle& L = s.lights[rng_next_u32(rng) % s.num_lights];
         float r1 = rng_next_f32(rng), r2 = rng_next_f32(rng);               // helpers.wgsl:7-18
         float s1 = pt_sqrt(r1);
         pt_v3 q = pt_mk3(L.v0[0] * (1.0f - s1) + L.v1[0] * s1 * (1.0f - r2) + L.v2[0] * s1 * r2,
                          L.v0[1] * (1.0f - s1) + L.v1[1] * s1 * (1.0f - r2) + L.v2[1] * s1 * r2,
                          L.v0[2] * (1.0f - s1) + L.v1[2] * s1 * (1.0f - r2) + L.v2[2] * s1 * r2);
-        pt_v3 p = pt_fma3(ps.d, hit.t, ps.o);
+        pt_v3 p = pt_fma3(ray_d, hit.t, ray_o);
         pt_v3 dir = pt_normalize(pt_sub(q, p));
         if (pt_dot(dir, n0) > 0.0f) { so = p; sd = dir; atten = m.albedo; sn = n0; }
         else regular = true;                                                // :183-189
     }
-    if (regular) scatter_regular(rng, ps.o, ps.d, hit.t, n, m, so, sd, atten, sn);
+    if (regular) scatter_regular(rng, ray_o, ray_d, hit.t, n, m, so, sd, atten, sn);
 
-    pt_v3 acc = pt_add(ps.acc, pt_mul(m.emissive, ps.mask));               // :200
-    pt_v3 mask = pt_mul(ps.mask, atten);                                    // :202
-    if (hit_light) { out.radiance = acc; return out; }                      // :204-206
+    out.light = m.emissive; out.atten = atten; out.rng = rng;
+    if (hit_light) { out.kind = SURF_LIGHT; return out; }                   // :204-206
     if (bounce == 0) {                                                      // :208-223
         out.first_t = hit.t;
-        pt_v3 tangent = pt_normalize(pt_cross(sn, pt_neg(ps.d)));
+        pt_v3 tangent = pt_normalize(pt_cross(sn, pt_neg(ray_d)));
         pt_v3 bitangent = pt_normalize(pt_cross(sn, tangent));
         out.first_normal = pt_normalize(pt_add(pt_add(pt_scale(tangent, m.tsn.x), pt_scale(bitangent, m.tsn.y)), pt_scale(sn, m.tsn.z)));
         out.first_albedo = m.albedo;
     }
-    if (bounce >= cfg.max_bounces) { out.radiance = acc; return out; }      // loop bound `i <= MAX_BOUNCES`, :159
-    out.alive = true;
-    out.next.o = so; out.next.d = sd; out.next.mask = mask; out.next.acc = acc; out.next.rng = rng;
+    if (bounce >= cfg.max_bounces) { out.kind = SURF_LAST; return out; }    // loop bound `i <= MAX_BOUNCES`, :159
+    out.kind = SURF_CONTINUE; out.next_o = so; out.next_d = sd;
+    return out;
+}
+
+// The part of the loop body that touches the path's running values (pathtracer/pathtracer.wgsl:200-206, 229-232):
+// returns true when the path continues (mask / acc updated), else `radiance` is ray_color's result.
+PT_HD bool combine_path(const SurfaceOut& so, pt_v3& mask, pt_v3& acc, pt_v3& radiance) {
+    if (so.kind == SURF_MISS) { radiance = pt_add(acc, pt_mul(so.light, mask)); return false; }
+    acc = pt_add(acc, pt_mul(so.light, mask));                             // :200
+    mask = pt_mul(mask, so.atten);                                          // :202
+    if (so.kind != SURF_CONTINUE) { radiance = acc; return false; }
+    return true;
+}
+
+// whole loop body in one call (host build of the tests)
+PT_HD BounceOut shade_bounce(const DevScene& s, const PathCfg& cfg, const PathState& ps, const HitRec& hit, uint32_t bounce) {
+    const SurfaceOut so = shade_surface(s, cfg, ps.o, ps.d, ps.rng, hit, bounce);
+    BounceOut out;
+    out.next = ps;
+    out.radiance = pt_mk3(0.0f, 0.0f, 0.0f);
+    out.first_t = so.first_t; out.first_normal = so.first_normal; out.first_albedo = so.first_albedo;
+    pt_v3 mask = ps.mask, acc = ps.acc;
+    out.alive = combine_path(so, mask, acc, out.radiance);
+    if (out.alive) { out.next.o = so.next_o; out.next.d = so.next_d; out.next.mask = mask; out.next.acc = acc; out.next.rng = so.rng; }
     return out;
 }
 

@@ -19,8 +19,7 @@ __global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameC
     gen_primary(un.camera, x, y, rng, ro, rd);
     reinterpret_cast<float4*>(q.ray_o)[i] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(i));
     reinterpret_cast<float4*>(q.ray_d)[i] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(rng));
-    reinterpret_cast<float4*>(q.mask)[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-    reinterpret_cast<float4*>(q.acc)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // color_mask = 1 and accumulated_color = 0 at segment 0 are constants of k_shade<true>: not stored
 }
 
 // ---- trace: persistent warps, warp-level work fetch -------------------------------------------
@@ -169,6 +168,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_any(DevScene s, const F
 // ---- shade: one bounce, ballot compaction into the next queue, fused accumulation ---------------
 // Work is split statically (warp w takes 32-ray batches w, w + #warps, ...): the cost per ray is nearly uniform, so a
 // device cursor would only add one dependent global atomic per batch.
+// FIRST (segment 0): throughput and accumulated colour are the constants (1,1,1) / (0,0,0) of ray_color's entry
+// (pathtracer/pathtracer.wgsl:155-156), so raygen does not write those queue entries and this kernel does not read them;
+// it also carries the first-hit aux outputs, which later segments do not.
+template <bool FIRST>
 __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(DevScene s, PathCfg cfg, Queue qin, Queue qout, const U4* __restrict__ hits,
                                                           FrameCounters* fc, uint32_t segment, Planes planes) {
     const uint32_t n = fc->count[segment];
@@ -176,42 +179,47 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32u; base < n; base += nwarps * 32u) {
-        uint32_t i = base + lane;
+        const uint32_t i = base + lane;
         bool alive = false;
-        BounceOut bo;
-        uint32_t pixel = 0;
+        uint32_t pixel = 0, rng = 0;
+        pt_v3 no = pt_mk3(0.0f, 0.0f, 0.0f), nd = no, mask = pt_mk3(1.0f, 1.0f, 1.0f), acc = no;
         if (i < n) {
-            F4 o = ld4(qin.ray_o + i), d = ld4(qin.ray_d + i), m = ld4(qin.mask + i), a = ld4(qin.acc + i);
-            uint4 hr = __ldg(reinterpret_cast<const uint4*>(hits) + i);
-            PathState ps;
-            ps.o = pt_mk3(o.x, o.y, o.z); ps.d = pt_mk3(d.x, d.y, d.z);
-            ps.mask = pt_mk3(m.x, m.y, m.z); ps.acc = pt_mk3(a.x, a.y, a.z);
-            ps.rng = __float_as_uint(d.w);
-            pixel = __float_as_uint(o.w);
-            HitRec h; h.t = __uint_as_float(hr.x); h.b1 = __uint_as_float(hr.y); h.b2 = __uint_as_float(hr.z); h.tri = hr.w;
-            bo = shade_bounce(s, cfg, ps, h, segment);
-            alive = bo.alive;
-            if (segment == 0) {                                   // pathtracer/pathtracer.wgsl:270-273
-                planes.depth[pixel] = bo.first_t;
-                reinterpret_cast<float4*>(planes.normal)[pixel] = make_float4(bo.first_normal.x, bo.first_normal.y, bo.first_normal.z, 1.0f);
-                reinterpret_cast<float4*>(planes.albedo)[pixel] = make_float4(bo.first_albedo.x, bo.first_albedo.y, bo.first_albedo.z, 1.0f);
-                planes.hit_tri[pixel] = h.tri;
+            SurfaceOut so;
+            {
+                const F4 o = ld4(qin.ray_o + i), d = ld4(qin.ray_d + i);
+                const uint4 hr = __ldg(reinterpret_cast<const uint4*>(hits) + i);
+                pixel = __float_as_uint(o.w);
+                HitRec h; h.t = __uint_as_float(hr.x); h.b1 = __uint_as_float(hr.y); h.b2 = __uint_as_float(hr.z); h.tri = hr.w;
+                so = shade_surface(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
+                if (FIRST) {                                          // pathtracer/pathtracer.wgsl:270-273
+                    planes.depth[pixel] = so.first_t;
+                    reinterpret_cast<float4*>(planes.normal)[pixel] = make_float4(so.first_normal.x, so.first_normal.y, so.first_normal.z, 1.0f);
+                    reinterpret_cast<float4*>(planes.albedo)[pixel] = make_float4(so.first_albedo.x, so.first_albedo.y, so.first_albedo.z, 1.0f);
+                    planes.hit_tri[pixel] = h.tri;
+                }
             }
-            if (!alive) accumulate_pixel(planes.color + pixel, bo.radiance, cfg.accum_mode, cfg.is_grabbed);   // pathtracer.wgsl:32-42
+            if (!FIRST) {
+                asm volatile("" ::: "memory");                        // keep these two loads AFTER the BSDF code (register pressure)
+                const F4 m = ld4(qin.mask + i), a = ld4(qin.acc + i);
+                mask = pt_mk3(m.x, m.y, m.z); acc = pt_mk3(a.x, a.y, a.z);
+            }
+            pt_v3 radiance;
+            alive = combine_path(so, mask, acc, radiance);
+            no = so.next_o; nd = so.next_d; rng = so.rng;
+            if (!alive) accumulate_pixel(planes.color + pixel, radiance, cfg.accum_mode, cfg.is_grabbed);   // pathtracer.wgsl:32-42
         }
         // warp-aggregated slot allocation in the next queue
-        uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
         if (ballot) {
             uint32_t slot0 = 0;
             if (lane == 0) slot0 = atomicAdd(next_count, (uint32_t)__popc(ballot));
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (alive) {
-                uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
-                const PathState& p = bo.next;
-                reinterpret_cast<float4*>(qout.ray_o)[slot] = make_float4(p.o.x, p.o.y, p.o.z, __uint_as_float(pixel));
-                reinterpret_cast<float4*>(qout.ray_d)[slot] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.rng));
-                reinterpret_cast<float4*>(qout.mask)[slot] = make_float4(p.mask.x, p.mask.y, p.mask.z, 0.0f);
-                reinterpret_cast<float4*>(qout.acc)[slot] = make_float4(p.acc.x, p.acc.y, p.acc.z, 0.0f);
+                const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                reinterpret_cast<float4*>(qout.ray_o)[slot] = make_float4(no.x, no.y, no.z, __uint_as_float(pixel));
+                reinterpret_cast<float4*>(qout.ray_d)[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng));
+                reinterpret_cast<float4*>(qout.mask)[slot] = make_float4(mask.x, mask.y, mask.z, 0.0f);
+                reinterpret_cast<float4*>(qout.acc)[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
             }
         }
     }
@@ -228,7 +236,8 @@ void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue 
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
                   FrameCounters* fc, uint32_t segment, Planes planes) {
-    k_shade<<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes);
+    if (segment == 0) k_shade<true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes);
+    else k_shade<false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes);
 }
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
@@ -333,6 +342,6 @@ static int persistent_grid(const void* kernel, int threads, int device) {
     return sms * per_sm;          // a multiple of the SM count (148 on B200): every SM holds its full share of resident CTAs
 }
 int trace_grid_size(int device, int impl) { return persistent_grid(impl == 0 ? (const void*)k_trace : (const void*)k_trace_simple, kTraceThreads, device); }
-int shade_grid_size(int device) { return persistent_grid((const void*)k_shade, kShadeThreads, device); }
+int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false>, kShadeThreads, device); }
 
 }  // namespace ptc
