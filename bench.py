@@ -224,7 +224,6 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    step.set_profiling(True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
@@ -239,8 +238,6 @@ def main():
     barrier()
     tw1 = time.time()
     ms = e0.elapsed_time(e1)
-    prof = step.profile()
-    step.set_profiling(False)
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     rays1 = step.stats()
     rays = rays1["rays_traced"] - rays0["rays_traced"]
@@ -251,6 +248,18 @@ def main():
         sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, rays, launches = float(mx[0]), float(sm[1]), float(sm[2])
     value = rays / (ms * 1e-3) / 1e6
+
+    # ---- per-stage device times: a separate, shorter pass with stage timing on.  Profiling keeps every launch on one
+    # stream (no primary-ray prefetch), so each kernel's CUDA-event duration is exclusive — that is what the roofline uses.
+    P = min(K, 32)
+    step.set_profiling(True)
+    r0 = step.stats()["rays_traced"]
+    for i in range(P):
+        step.update(uniforms[Wm + i]); step.render()
+    step.poll(True)
+    prof = step.profile()
+    prof_rays = step.stats()["rays_traced"] - r0
+    step.set_profiling(False)
 
     # ---- end to end through the reference-facing calls with host buffers ---------------------------------------
     # K steps, repeated E2E_REPS times; the reported value is the MEDIAN repetition (all are listed in e2e.runs):
@@ -299,7 +308,8 @@ def main():
     bytes_per_ray = 64.0 * nodes_per_ray + 48.0 * tris_per_ray + 64.0 if base else None
     peak, peak_src = load_peaks()
     trace_ms, trace_n = prof["trace"]["ms"], prof["trace"]["launches"]
-    rank_rays = rays / world                                # per-rank share (identical work per rank up to RNG streams)
+    rank_rays = prof_rays                                   # this rank's rays in the profiled pass
+    stage_total = sum(v["ms"] for v in prof.values())
     achieved = bytes_per_ray * rank_rays / (trace_ms * 1e-3) / 1e9 if (base and trace_ms > 0) else None
     bvh = step.bvh_info()
     traffic = None                                          # dram bytes per k_trace launch from the committed ncu --set full capture
@@ -323,8 +333,9 @@ def main():
                      "frac": achieved / peak if achieved is not None else None, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                      "rays_per_launch": rank_rays / max(trace_n, 1), "avg_launch_ms": trace_ms / max(trace_n, 1), "launches": int(trace_n),
-                     "kernel_share_of_step": trace_ms / ms if ms > 0 else None,
-                     "stage_ms": {k: v["ms"] for k, v in prof.items()}},
+                     "kernel_share_of_step": trace_ms / stage_total if stage_total > 0 else None,
+                     "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_pass_steps": P,
+                     "note": "stage times from a separate single-stream pass (no primary-ray prefetch) so that durations are exclusive"},
         "cpu_baseline": ({k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} if (base and world == 1) else None),
     }
     print(json.dumps(line, allow_nan=False))

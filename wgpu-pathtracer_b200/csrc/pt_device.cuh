@@ -32,6 +32,16 @@ PT_HD F4 ld4(const F4* p) { float4 v = __ldg(reinterpret_cast<const float4*>(p))
 PT_HD F4 ld4(const F4* p) { return *p; }
 #endif
 
+// Path-queue traffic (SoA ray / throughput records, ~300 MB per 1080p frame) is written once and read once, a whole
+// queue later: streaming (evict-first) accesses keep it from displacing the BVH, shading records and textures in L2.
+#if defined(__CUDA_ARCH__) && !defined(PTC_NO_STREAM_HINTS)
+PT_HD F4 ld4_stream(const F4* p) { float4 v = __ldcs(reinterpret_cast<const float4*>(p)); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+PT_HD void st4_stream(F4* p, float x, float y, float z, float w) { __stcs(reinterpret_cast<float4*>(p), make_float4(x, y, z, w)); }
+#else
+PT_HD F4 ld4_stream(const F4* p) { return ld4(p); }
+PT_HD void st4_stream(F4* p, float x, float y, float z, float w) { p->x = x; p->y = y; p->z = z; p->w = w; }
+#endif
+
 // Two consecutive F4 (32 bytes, 32-byte aligned) in ONE load: sm_100 has 256-bit global loads (LDG.E.256).  A BVH
 // node is then 2 memory instructions instead of 4 — for divergent lanes every load instruction costs one L1 tag
 // lookup per lane, and k_trace is bound by exactly that (l1tex throughput 60-75 % of peak at ~50 % issue utilisation).

@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameC
     uint32_t x = i % un.camera.width, y = i / un.camera.width;
     uint32_t rng; pt_v3 ro, rd;
     gen_primary(un.camera, x, y, rng, ro, rd);
-    reinterpret_cast<float4*>(q.ray_o)[i] = make_float4(ro.x, ro.y, ro.z, __uint_as_float(i));
-    reinterpret_cast<float4*>(q.ray_d)[i] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(rng));
+    st4_stream(q.ray_o + i, ro.x, ro.y, ro.z, __uint_as_float(i));
+    st4_stream(q.ray_d + i, rd.x, rd.y, rd.z, __uint_as_float(rng));
     // color_mask = 1 and accumulated_color = 0 at segment 0 are constants of k_shade<true>: not stored
 }
 
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
         if (i < n) {
             SurfaceOut so;
             {
-                const F4 o = ld4(qin.ray_o + i), d = ld4(qin.ray_d + i);
-                const uint4 hr = __ldg(reinterpret_cast<const uint4*>(hits) + i);
+                const F4 o = ld4_stream(qin.ray_o + i), d = ld4_stream(qin.ray_d + i);
+                const uint4 hr = __ldcs(reinterpret_cast<const uint4*>(hits) + i);
                 pixel = __float_as_uint(o.w);
                 HitRec h; h.t = __uint_as_float(hr.x); h.b1 = __uint_as_float(hr.y); h.b2 = __uint_as_float(hr.z); h.tri = hr.w;
                 so = shade_surface(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             }
             if (!FIRST) {
                 asm volatile("" ::: "memory");                        // keep these two loads AFTER the BSDF code (register pressure)
-                const F4 m = ld4(qin.mask + i), a = ld4(qin.acc + i);
+                const F4 m = ld4_stream(qin.mask + i), a = ld4_stream(qin.acc + i);
                 mask = pt_mk3(m.x, m.y, m.z); acc = pt_mk3(a.x, a.y, a.z);
             }
             pt_v3 radiance;
@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (alive) {
                 const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
-                reinterpret_cast<float4*>(qout.ray_o)[slot] = make_float4(no.x, no.y, no.z, __uint_as_float(pixel));
-                reinterpret_cast<float4*>(qout.ray_d)[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(rng));
-                reinterpret_cast<float4*>(qout.mask)[slot] = make_float4(mask.x, mask.y, mask.z, 0.0f);
-                reinterpret_cast<float4*>(qout.acc)[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+                st4_stream(qout.ray_o + slot, no.x, no.y, no.z, __uint_as_float(pixel));
+                st4_stream(qout.ray_d + slot, nd.x, nd.y, nd.z, __uint_as_float(rng));
+                st4_stream(qout.mask + slot, mask.x, mask.y, mask.z, 0.0f);
+                st4_stream(qout.acc + slot, acc.x, acc.y, acc.z, 0.0f);
             }
         }
     }
