@@ -48,7 +48,8 @@ emu_scene* emu_create(const ptc_scene_view* v, const ptc_config* cfg) {
         d.w = t.width; d.h = t.height; d.fmt = t.format; d.linear = e->texel_store[i].data();
     }
     DevScene& ds = e->ds;
-    ds.nodes = reinterpret_cast<const F4*>(e->ps.bvh.nodes.data());
+    ds.nodes = reinterpret_cast<const NodeQ*>(e->ps.bvh.nodes.data());
+    for (int a = 0; a < 3; ++a) { ds.grid_base[a] = e->ps.bvh.grid.base[a]; ds.grid_extent[a] = e->ps.bvh.grid.extent[a]; }
     ds.tris = reinterpret_cast<const F4*>(e->ps.bvh.tris.data());
     ds.shade = e->ps.shade.data(); ds.mats = e->ps.mats.data(); ds.texs = e->texs.data(); ds.lights = e->ps.lights.data();
     ds.num_nodes = (uint32_t)e->ps.bvh.nodes.size(); ds.num_tris = e->ps.num_tris;

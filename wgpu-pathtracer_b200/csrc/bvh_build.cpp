@@ -190,18 +190,29 @@ void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthr
 }
 
 void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
-    out.nodes.clear(); out.tris.clear();
+    out.nodes.clear(); out.tris.clear(); out.grid = QuantGrid{};
     if (bvh.nodes.empty()) return;
-    const float inf = std::numeric_limits<float>::infinity();
     uint32_t ntri = (uint32_t)bvh.order.size();
     out.tris.resize(ntri);
     for (uint32_t i = 0; i < ntri; ++i) {
         uint32_t id = bvh.order[i];
         const float* v = tri_pos + (size_t)id * 9;
-        DevTri& t = out.tris[i];
+        DevTri& t = out.tris[i]; std::memset(&t, 0, sizeof(t));
         t.q[0] = v[0]; t.q[1] = v[1]; t.q[2] = v[2]; std::memcpy(&t.q[3], &id, 4);
-        t.q[4] = v[3] - v[0]; t.q[5] = v[4] - v[1]; t.q[6] = v[5] - v[2]; t.q[7] = 0.0f;
-        t.q[8] = v[6] - v[0]; t.q[9] = v[7] - v[1]; t.q[10] = v[8] - v[2]; t.q[11] = 0.0f;
+        t.q[4] = v[3] - v[0]; t.q[5] = v[4] - v[1]; t.q[6] = v[5] - v[2];
+        t.q[8] = v[6] - v[0]; t.q[9] = v[7] - v[1]; t.q[10] = v[8] - v[2];
+    }
+    // quantisation grid: the padded scene box, widened by a few steps so that outward rounding never clamps
+    const BuildNode& root = bvh.nodes[0];
+    double step[3];
+    for (int a = 0; a < 3; ++a) {
+        double ext = (double)root.hi[a] - (double)root.lo[a] + 2.0 * (double)bvh.pad;
+        double S = ext * (1.0 + 16.0 / 32768.0);
+        if (!(S > 1e-20)) S = 1e-20;
+        float Sf = std::nextafter((float)S, std::numeric_limits<float>::infinity());
+        float bf = std::nextafter((float)((double)root.lo[a] - (double)bvh.pad - 0.5 * ((double)Sf - ext)), -std::numeric_limits<float>::infinity());
+        out.grid.base[a] = bf; out.grid.extent[a] = Sf;
+        step[a] = (double)Sf / 32768.0;
     }
     // inner build nodes -> device node ids in depth-first order
     std::vector<int32_t> dev_id(bvh.nodes.size(), -1);
@@ -222,32 +233,35 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
         }
         out.nodes.resize(n_inner);
     }
-    auto child_ref = [&](uint32_t n) -> int32_t {
-        if (!is_leaf(n)) return dev_id[n];
+    auto child_ref = [&](uint32_t n) -> uint32_t {
+        if (!is_leaf(n)) return (uint32_t)dev_id[n];
         const BuildNode& b = bvh.nodes[n];
         uint32_t enc = (b.first << 3) | (b.count - 1);
-        return (int32_t)~enc;
+        return ~enc;
     };
-    auto put_box = [&](DevNode2& d, int c, const BuildNode* b) {
-        float lo[3], hi[3];
-        for (int a = 0; a < 3; ++a) { lo[a] = b ? b->lo[a] - bvh.pad : inf; hi[a] = b ? b->hi[a] + bvh.pad : -inf; }
-        d.q[c * 4 + 0] = lo[0]; d.q[c * 4 + 1] = hi[0]; d.q[c * 4 + 2] = lo[1]; d.q[c * 4 + 3] = hi[1];
-        d.q[8 + c * 2 + 0] = lo[2]; d.q[8 + c * 2 + 1] = hi[2];
+    // planes rounded outwards by one extra step: the kernel's plane distance carries up to ~1/30 step of rounding error
+    auto put_box = [&](DevNode2& d, int c, const BuildNode& b) {
+        for (int a = 0; a < 3; ++a) {
+            double lo = ((double)b.lo[a] - (double)bvh.pad - (double)out.grid.base[a]) / step[a];
+            double hi = ((double)b.hi[a] + (double)bvh.pad - (double)out.grid.base[a]) / step[a];
+            long ql = (long)std::floor(lo) - 1, qh = (long)std::ceil(hi) + 1;
+            ql = std::min(std::max(ql, 0l), 32767l); qh = std::min(std::max(qh, 0l), 32767l);
+            d.w[c * 4 + a] = (0x8000u | (uint32_t)ql) | ((0x8000u | (uint32_t)qh) << 16);
+        }
     };
     if (is_leaf(0)) {
-        DevNode2& d = out.nodes[0]; std::memset(&d, 0, sizeof(d));
-        put_box(d, 0, &bvh.nodes[0]); put_box(d, 1, nullptr);
-        int32_t c0 = child_ref(0), c1 = c0;
-        std::memcpy(&d.q[12], &c0, 4); std::memcpy(&d.q[13], &c1, 4);
+        DevNode2& d = out.nodes[0];
+        put_box(d, 0, bvh.nodes[0]);
+        for (int a = 0; a < 3; ++a) d.w[4 + a] = 0xFFFFu | (0x8000u << 16);   // absent child: inverted box (lo = 32767, hi = 0), never entered
+        d.w[3] = d.w[7] = child_ref(0);
         return;
     }
     for (uint32_t n = 0; n < bvh.nodes.size(); ++n) {
         if (dev_id[n] < 0) continue;
-        DevNode2& d = out.nodes[dev_id[n]]; std::memset(&d, 0, sizeof(d));
+        DevNode2& d = out.nodes[dev_id[n]];
         uint32_t l = bvh.nodes[n].left;
-        put_box(d, 0, &bvh.nodes[l]); put_box(d, 1, &bvh.nodes[l + 1]);
-        int32_t c0 = child_ref(l), c1 = child_ref(l + 1);
-        std::memcpy(&d.q[12], &c0, 4); std::memcpy(&d.q[13], &c1, 4);
+        put_box(d, 0, bvh.nodes[l]); put_box(d, 1, bvh.nodes[l + 1]);
+        d.w[3] = child_ref(l); d.w[7] = child_ref(l + 1);
     }
 }
 

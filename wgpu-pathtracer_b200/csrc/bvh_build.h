@@ -33,24 +33,32 @@ void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthr
 
 // ---- device layouts --------------------------------------------------------
 
-// BVH2 device node, 64 bytes, four 128-bit loads (Aila-Laine style: the node
-// carries BOTH children's boxes so one visit decides both descents):
-//   q0 = c0.lo.x c0.hi.x c0.lo.y c0.hi.y
-//   q1 = c1.lo.x c1.hi.x c1.lo.y c1.hi.y
-//   q2 = c0.lo.z c0.hi.z c1.lo.z c1.hi.z
-//   q3 = child0 child1 (int bits) 0 0
-// child >= 0: inner node index.  child < 0: leaf, ~child = (first_tri << 3) | (count - 1),
-// first_tri indexing the leaf-ordered triangle array.  An absent child has an
-// inverted box (lo = +inf, hi = -inf) and is never entered.
-struct DevNode2 { float q[16]; };
+// BVH2 device node, 32 bytes = ONE 256-bit load (Aila-Laine style: the node carries BOTH children's boxes so one
+// visit decides both descents).  Box planes are quantised to a 15-bit grid over the (padded) scene box, rounded
+// outwards — the traversal kernel is bound by L1 wavefronts (one per lane per load instruction for divergent lanes),
+// so halving the node from two loads to one matters more than the ~1e-4 relative growth of the boxes:
+//   w[0..2] = child 0, axis x/y/z: lo16 | hi16 << 16      w[3] = child 0 reference
+//   w[4..6] = child 1, axis x/y/z                         w[7] = child 1 reference
+// each 16-bit plane is 0x8000 | q (q in [0, 32767]): with 0x3F as the top byte and 0x00 as the bottom byte (one PRMT)
+// it IS the float 1 + q / 32768, so decoding costs one instruction and the plane distance one FMA (pt_device.cuh).
+// plane position = grid.base[axis] + q * grid.extent[axis] / 32768.
+// child >= 0: inner node index.  child < 0: leaf, ~child = (first_tri << 3) | (count - 1), first_tri indexing the
+// leaf-ordered triangle array.  An absent child (single-leaf tree)
+// has an inverted box (lo = 32767, hi = 0) and is never entered.
+struct DevNode2 { uint32_t w[8]; };
 
-// Leaf-ordered triangle for traversal, 48 bytes, three 128-bit loads:
-//   (v0.xyz, global triangle id bits) (e1.xyz, 0) (e2.xyz, 0), e1 = v1 - v0, e2 = v2 - v0 in fp32
-struct DevTri { float q[12]; };
+// Leaf-ordered triangle for traversal, 64-byte stride so that (v0, id, e1) is one aligned 256-bit load:
+//   (v0.xyz, global triangle id bits) (e1.xyz, 0) | (e2.xyz, 0) (unused)
+// e1 = v1 - v0, e2 = v2 - v0 in fp32.
+struct DevTri { float q[16]; };
+
+// quantisation grid of the node boxes (per axis)
+struct QuantGrid { float base[3]; float extent[3]; };
 
 struct DevBvh2 {
     std::vector<DevNode2> nodes;
     std::vector<DevTri> tris;
+    QuantGrid grid{};
 };
 
 void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out);

@@ -42,15 +42,40 @@ PT_HD F4 ld4_stream(const F4* p) { return ld4(p); }
 PT_HD void st4_stream(F4* p, float x, float y, float z, float w) { p->x = x; p->y = y; p->z = z; p->w = w; }
 #endif
 
-// Two consecutive F4 (32 bytes, 32-byte aligned) in ONE load: sm_100 has 256-bit global loads (LDG.E.256).  A BVH
-// node is then 2 memory instructions instead of 4 — for divergent lanes every load instruction costs one L1 tag
-// lookup per lane, and k_trace is bound by exactly that (l1tex throughput 60-75 % of peak at ~50 % issue utilisation).
+// 32 bytes (32-byte aligned) in ONE load: sm_100 has 256-bit global loads (LDG.E.256).  For divergent lanes every
+// load instruction costs one L1 wavefront per lane, and k_trace is bound by exactly that (ncu, profiles/r01e:
+// l1tex__data_pipe_lsu_wavefronts at 60-80 % of peak), so a BVH node is one such load and a triangle two.
 PT_HD void ld8(const F4* p, F4& a, F4& b) {
 #if defined(__CUDA_ARCH__) && !defined(PTC_NO_LDG256)
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 #else
     a = ld4(p); b = ld4(p + 1);
+#endif
+}
+struct alignas(32) NodeQ { uint32_t w[8]; };      // device BVH2 node (layout: bvh_build.h DevNode2)
+PT_HD NodeQ ld_node(const NodeQ* p) {
+    NodeQ n;
+#if defined(__CUDA_ARCH__) && !defined(PTC_NO_LDG256)
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(n.w[0]), "=r"(n.w[1]), "=r"(n.w[2]), "=r"(n.w[3]), "=r"(n.w[4]), "=r"(n.w[5]), "=r"(n.w[6]), "=r"(n.w[7]) : "l"(p));
+#elif defined(__CUDA_ARCH__)
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    n.w[0] = a.x; n.w[1] = a.y; n.w[2] = a.z; n.w[3] = a.w; n.w[4] = b.x; n.w[5] = b.y; n.w[6] = b.z; n.w[7] = b.w;
+#else
+    memcpy(&n, p, sizeof(n));      // host vectors are not 32-byte aligned
+#endif
+    return n;
+}
+// PRMT: byte k of the result is byte (sel >> 4k) & 7 of the 8-byte pool {lo = bytes 0-3, hi = bytes 4-7}
+PT_HD uint32_t pt_prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel)); return r;   // (__byte_perm would first mask sel)
+#else
+    const uint64_t pool = (uint64_t)lo | ((uint64_t)hi << 32);
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+    return r;
 #endif
 }
 
@@ -90,8 +115,8 @@ struct alignas(16) MatDev {
 struct alignas(16) TriShade { F4 q[4]; };
 
 struct DevScene {
-    const F4* nodes;          // BVH2 device nodes (4 x F4 each)
-    const F4* tris;           // leaf-ordered traversal triangles (3 x F4 each)
+    const NodeQ* nodes;       // BVH2 device nodes, 32 bytes each
+    const F4* tris;           // leaf-ordered traversal triangles (4 x F4 each, the last one unused)
     const TriShade* shade;    // global-order shading records
     const MatDev* mats;
     const TexDev* texs;
@@ -99,6 +124,7 @@ struct DevScene {
     uint32_t num_nodes, num_tris, num_lights, env_tex;
     uint32_t num_pages, _pad;
     unsigned long long page_obj[PTC_MAX_TEX_PAGES];   // cudaTextureObject_t per atlas page (device build only)
+    float grid_base[3], grid_extent[3];               // quantisation grid of the node boxes (bvh_build.h QuantGrid)
 };
 
 struct PathCfg {
@@ -140,16 +166,26 @@ struct HitRec { float t, b1, b2; uint32_t tri; };   // tri = global triangle id,
 #define PTC_SENTINEL 0x7fffffff
 
 // ---- slab test ------------------------------------------------------------------------------------------
-// Entry/exit distances are evaluated as fma(bound, 1/d, -o/d): one FMA per plane.  Its absolute error is about
-// |o/d| * 2^-24 (NOT relative to t), which for a ray nearly parallel to an axis exceeds any fixed box padding, so
-// each axis carries its own error bound e = |o/d| * 2^-21 folded into the FMA constant: the plane the ray enters
-// through is moved back by e and the exit plane forward by e.  The test therefore stays conservative with respect to
-// pt_ray_tri (hit identity can never depend on it) at no extra instruction, and a near-parallel ray only loses
-// culling along the one axis it is parallel to.  Direction components below 2^-80 are clamped so 1/d stays finite.
+// A box plane is stored as q in [0, 32767] on the scene grid: position = base + q * extent / 32768.  One PRMT turns the
+// stored 16 bits into the float F = 1 + q / 32768, and the plane's ray distance is ONE FMA:
+//     t = (base + q * extent / 32768 - o) / d = F * A + C,   A = extent / d,   C = (base - o) / d - A.
+// Which of a box's two planes per axis the ray enters through depends only on the sign of d, so the PRMT selector
+// (a per-ray register) picks the entry plane and the exit plane directly: no per-node min/max per axis.
+// Error: |fma(F, A, C) - t| <= 2^-21 (|A| + |(base - o) / d|) (roundings of 1/d, A, C and the FMA itself; F <= 2), an
+// ABSOLUTE bound that is largest for a ray nearly parallel to the axis.  Twice that bound is folded into the constant:
+// the entry plane moves back, the exit plane forward, so the test is conservative with respect to pt_ray_tri (hit
+// identity can never depend on it) at no extra instruction, and a near-parallel ray only loses culling along the one
+// axis it is parallel to.  In space units the bound is ~1e-6 of the scene extent, 1/30 of a grid step; the builder
+// rounds every plane outwards by a whole extra step.  Direction components below 2^-80 are clamped so 1/d is finite.
 struct RaySlab {
-    float idx, idy, idz;          // 1/d
-    float lx, hx, ly, hy, lz, hz; // additive constants for the lo / hi plane of each axis (already negated)
+    float ax, ay, az;             // A per axis
+    float nx, fx, ny, fy, nz, fz; // C for the entry (near) / exit (far) plane of each axis
+    uint32_t sx, sy, sz;          // PRMT selector of the entry plane; the exit plane's is sel ^ PT_SEL_FLIP
 };
+#define PT_SEL_LO 0x7104u          // bytes {0x00, w.b0, w.b1, 0x3F}: the low 16 bits of the word -> float bits
+#define PT_SEL_HI 0x7324u          // bytes {0x00, w.b2, w.b3, 0x3F}: the high 16 bits
+#define PT_SEL_FLIP 0x0220u
+#define PT_SEL_POOL 0x3F000000u
 
 PT_HD float pt_min3(float a, float b, float c) {
 #if defined(__CUDA_ARCH__) && !defined(PTC_NO_MINMAX3)
@@ -166,20 +202,23 @@ PT_HD float pt_max3(float a, float b, float c) {
 #endif
 }
 
-PT_HD RaySlab make_ray_slab(pt_v3 o, pt_v3 d) {
+PT_HD void slab_axis(float o, float d, float base, float extent, float& a, float& cn, float& cf, uint32_t& sel) {
     const float kTiny = 8.271806125530277e-25f;   // 2^-80
-    const float kErr = 4.76837158203125e-7f;      // 2^-21
-    float dx = pt_abs(d.x) > kTiny ? d.x : copysignf(kTiny, d.x);
-    float dy = pt_abs(d.y) > kTiny ? d.y : copysignf(kTiny, d.y);
-    float dz = pt_abs(d.z) > kTiny ? d.z : copysignf(kTiny, d.z);
+    const float kErr = 9.5367431640625e-7f;       // 2^-20
+    const float dd = pt_abs(d) > kTiny ? d : copysignf(kTiny, d);
+    const float inv = pt_div(1.0f, dd);
+    a = extent * inv;
+    const float b = (base - o) * inv;
+    const float c = b - a;
+    const float e = (pt_abs(a) + pt_abs(b)) * kErr;
+    cn = c - e; cf = c + e;
+    sel = dd > 0.0f ? PT_SEL_LO : PT_SEL_HI;
+}
+PT_HD RaySlab make_ray_slab(const DevScene& s, pt_v3 o, pt_v3 d) {
     RaySlab r;
-    r.idx = pt_div(1.0f, dx); r.idy = pt_div(1.0f, dy); r.idz = pt_div(1.0f, dz);
-    float ox = o.x * r.idx, oy = o.y * r.idy, oz = o.z * r.idz;
-    float ex = pt_abs(ox) * kErr, ey = pt_abs(oy) * kErr, ez = pt_abs(oz) * kErr;
-    // positive direction: the lo plane is the entry plane (moved back: -(o/d) - e), the hi plane the exit plane
-    r.lx = dx > 0.0f ? -ox - ex : -ox + ex;  r.hx = dx > 0.0f ? -ox + ex : -ox - ex;
-    r.ly = dy > 0.0f ? -oy - ey : -oy + ey;  r.hy = dy > 0.0f ? -oy + ey : -oy - ey;
-    r.lz = dz > 0.0f ? -oz - ez : -oz + ez;  r.hz = dz > 0.0f ? -oz + ez : -oz - ez;
+    slab_axis(o.x, d.x, s.grid_base[0], s.grid_extent[0], r.ax, r.nx, r.fx, r.sx);
+    slab_axis(o.y, d.y, s.grid_base[1], s.grid_extent[1], r.ay, r.ny, r.fy, r.sy);
+    slab_axis(o.z, d.z, s.grid_base[2], s.grid_extent[2], r.az, r.nz, r.fz, r.sz);
     return r;
 }
 
@@ -193,21 +232,16 @@ PT_HD bool ray_is_finite(pt_v3 o, pt_v3 d) {
 }
 
 // Both children of one BVH2 node against the ray: hit flags and entry distances.
-PT_HD void node_test(const RaySlab& r, const F4& q0, const F4& q1, const F4& q2, float tmax,
-                     bool& h0, bool& h1, float& tn0, float& tn1) {
-    float a0 = pt_fma(q0.x, r.idx, r.lx), b0 = pt_fma(q0.y, r.idx, r.hx);
-    float c0 = pt_fma(q0.z, r.idy, r.ly), d0 = pt_fma(q0.w, r.idy, r.hy);
-    float e0 = pt_fma(q2.x, r.idz, r.lz), f0 = pt_fma(q2.y, r.idz, r.hz);
-    float a1 = pt_fma(q1.x, r.idx, r.lx), b1 = pt_fma(q1.y, r.idx, r.hx);
-    float c1 = pt_fma(q1.z, r.idy, r.ly), d1 = pt_fma(q1.w, r.idy, r.hy);
-    float e1 = pt_fma(q2.z, r.idz, r.lz), f1 = pt_fma(q2.w, r.idz, r.hz);
+PT_HD float slab_plane(uint32_t w, uint32_t sel, float a, float c) { return pt_fma(u2f(pt_prmt(w, PT_SEL_POOL, sel)), a, c); }
+PT_HD void node_test(const RaySlab& r, const NodeQ& n, float tmax, bool& h0, bool& h1, float& tn0, float& tn1) {
+    const uint32_t fx = r.sx ^ PT_SEL_FLIP, fy = r.sy ^ PT_SEL_FLIP, fz = r.sz ^ PT_SEL_FLIP;
     // fmin/fmax drop NaNs, so a degenerate plane simply stops constraining the interval
-    tn0 = pt_max3(fminf(a0, b0), fminf(c0, d0), fmaxf(fminf(e0, f0), 0.0f));
-    float tf0 = pt_min3(fmaxf(a0, b0), fmaxf(c0, d0), fminf(fmaxf(e0, f0), tmax));
-    tn1 = pt_max3(fminf(a1, b1), fminf(c1, d1), fmaxf(fminf(e1, f1), 0.0f));
-    float tf1 = pt_min3(fmaxf(a1, b1), fmaxf(c1, d1), fminf(fmaxf(e1, f1), tmax));
-    h0 = tn0 <= tf0 * 1.0000005f;
-    h1 = tn1 <= tf1 * 1.0000005f;
+    tn0 = pt_max3(slab_plane(n.w[0], r.sx, r.ax, r.nx), slab_plane(n.w[1], r.sy, r.ay, r.ny), fmaxf(slab_plane(n.w[2], r.sz, r.az, r.nz), 0.0f));
+    const float tf0 = pt_min3(slab_plane(n.w[0], fx, r.ax, r.fx), slab_plane(n.w[1], fy, r.ay, r.fy), fminf(slab_plane(n.w[2], fz, r.az, r.fz), tmax));
+    tn1 = pt_max3(slab_plane(n.w[4], r.sx, r.ax, r.nx), slab_plane(n.w[5], r.sy, r.ay, r.ny), fmaxf(slab_plane(n.w[6], r.sz, r.az, r.nz), 0.0f));
+    const float tf1 = pt_min3(slab_plane(n.w[4], fx, r.ax, r.fx), slab_plane(n.w[5], fy, r.ay, r.fy), fminf(slab_plane(n.w[6], fz, r.az, r.fz), tmax));
+    h0 = tn0 <= tf0;
+    h1 = tn1 <= tf1;
 }
 
 // All triangles of one leaf (closest hit; ties in t go to the smaller global triangle id so the result does not
@@ -216,8 +250,8 @@ PT_HD void leaf_closest(const DevScene& s, int node, pt_v3 o, pt_v3 d, HitRec& b
     uint32_t enc = ~(uint32_t)node;
     uint32_t first = enc >> 3, cnt = (enc & 7u) + 1u;
     for (uint32_t i = 0; i < cnt; ++i) {
-        const F4* tp = s.tris + (size_t)(first + i) * 3;
-        F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+        const F4* tp = s.tris + (size_t)(first + i) * 4;
+        F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
         if (counters) counters[1]++;
         float t, b1, b2;
         if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
@@ -235,18 +269,17 @@ PT_HD void leaf_closest(const DevScene& s, int node, pt_v3 o, pt_v3 d, HitRec& b
 PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* counters) {
     HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
     if (s.num_nodes == 0 || !ray_is_finite(o, d)) return best;
-    const RaySlab r = make_ray_slab(o, d);
+    const RaySlab r = make_ray_slab(s, o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
     int node = 0;
     while (node != PTC_SENTINEL) {
         if (node >= 0) {
-            const F4* np = s.nodes + (size_t)node * 4;
-            F4 q0, q1, q2, q3; ld8(np, q0, q1); ld8(np + 2, q2, q3);
+            const NodeQ nq = ld_node(s.nodes + node);
             if (counters) counters[0]++;
             bool h0, h1; float tn0, tn1;
-            node_test(r, q0, q1, q2, best.t, h0, h1, tn0, tn1);
-            int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
+            node_test(r, nq, best.t, h0, h1, tn0, tn1);
+            int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
             if (!h0 && !h1) node = stack[--sp];
             else if (h0 && h1) {
                 if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
@@ -264,17 +297,16 @@ PT_HD HitRec trace_closest_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, uint32_t* c
 // configuration — SEND_TO_LIGHT_PROBABILITY = 0, shader_definitions.rs:19 — this serves optional light-sampling modes).
 PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
     if (s.num_nodes == 0 || !ray_is_finite(o, d)) return false;
-    const RaySlab r = make_ray_slab(o, d);
+    const RaySlab r = make_ray_slab(s, o, d);
     int stack[PTC_STACK_SIZE]; int sp = 0;
     stack[sp++] = PTC_SENTINEL;
     int node = 0;
     while (node != PTC_SENTINEL) {
         if (node >= 0) {
-            const F4* np = s.nodes + (size_t)node * 4;
-            F4 q0, q1, q2, q3; ld8(np, q0, q1); ld8(np + 2, q2, q3);
+            const NodeQ nq = ld_node(s.nodes + node);
             bool h0, h1; float tn0, tn1;
-            node_test(r, q0, q1, q2, tmax, h0, h1, tn0, tn1);
-            int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
+            node_test(r, nq, tmax, h0, h1, tn0, tn1);
+            int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
             if (!h0 && !h1) node = stack[--sp];
             else if (h0 && h1) { stack[sp++] = c1; node = c0; }
             else node = h0 ? c0 : c1;
@@ -282,8 +314,8 @@ PT_HD bool trace_any_bvh2(const DevScene& s, pt_v3 o, pt_v3 d, float tmax) {
             uint32_t enc = ~(uint32_t)node;
             uint32_t first = enc >> 3, cnt = (enc & 7u) + 1u;
             for (uint32_t i = 0; i < cnt; ++i) {
-                const F4* tp = s.tris + (size_t)(first + i) * 3;
-                F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+                const F4* tp = s.tris + (size_t)(first + i) * 4;
+                F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
                 float t, b1, b2;
                 if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z),
                                PT_RAY_TMIN, tmax, &t, &b1, &b2)) return true;

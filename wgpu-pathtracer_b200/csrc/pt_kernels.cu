@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
                     ray = i;
                     const F4 ro = ld4(ray_o + i), rd = ld4(ray_d + i);
                     o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z);
-                    r = make_ray_slab(o, d);
+                    r = make_ray_slab(s, o, d);
                     best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
                     stack[0] = PTC_SENTINEL; sp = 1;
                     tri_i = tri_end = 0;
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
             // ---- triangle phase: one triangle per waiting lane ----
             if (node < 0) {
                 if (tri_i == tri_end) { const uint32_t enc = ~(uint32_t)node; tri_i = enc >> 3; tri_end = tri_i + (enc & 7u) + 1u; }
-                const F4* tp = s.tris + (size_t)tri_i * 3;
-                const F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
+                const F4* tp = s.tris + (size_t)tri_i * 4;
+                F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
                 float t, b1, b2;
                 if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
                     const uint32_t id = f2u(a.w);
@@ -136,11 +136,10 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
         } else {
             // ---- node phase: both children of one node per lane ----
             if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
-                const F4* np = s.nodes + (size_t)node * 4;
-                F4 q0, q1, q2, q3; ld8(np, q0, q1); ld8(np + 2, q2, q3);
+                const NodeQ nq = ld_node(s.nodes + node);
                 bool h0, h1; float tn0, tn1;
-                node_test(r, q0, q1, q2, best.t, h0, h1, tn0, tn1);
-                const int c0 = (int)f2u(q3.x), c1 = (int)f2u(q3.y);
+                node_test(r, nq, best.t, h0, h1, tn0, tn1);
+                const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
                 const bool swap = tn1 < tn0;
                 if (h0 && h1) { stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }
                 else if (h0 || h1) node = h0 ? c0 : c1;

@@ -284,9 +284,10 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
     CK(cudaMemcpy(s->d_lights, ps.lights.data(), ps.lights.size() * sizeof(ptc_triangle), cudaMemcpyHostToDevice));
 
     DevScene& ds = s->scene;
-    ds.nodes = s->d_nodes; ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
+    ds.nodes = reinterpret_cast<const NodeQ*>(s->d_nodes); ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
     ds.num_nodes = (uint32_t)dev.nodes.size(); ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
     ds.num_pages = (uint32_t)s->page_objs.size();
+    for (int a = 0; a < 3; ++a) { ds.grid_base[a] = dev.grid.base[a]; ds.grid_extent[a] = dev.grid.extent[a]; }
     for (size_t p = 0; p < s->page_objs.size(); ++p) ds.page_obj[p] = (unsigned long long)s->page_objs[p];
     return PTC_OK;
 }
