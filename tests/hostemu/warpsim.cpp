@@ -1,0 +1,196 @@
+// warpsim.cpp — DEVELOPMENT AID (test-only, part of libpt_hostemu.so, never of libptcore).
+//
+// A lane-accurate model of k_trace's warp scheduling (pt_kernels.cu): 32 persistent ray slots per warp, phase voting
+// (refill / triangle / node), device cursor refill — running the host build of the same node_test / pt_ray_tri.  It
+// counts warp iterations per phase and the lanes active in each, so scheduling policies (vote thresholds, postponed
+// leaves, ...) can be compared on the CPU before spending GPU time: k_trace is issue-bound, so
+// sum(iterations x instructions per iteration) tracks its run time.
+#include "../../wgpu-pathtracer_b200/csrc/pt_device.cuh"
+#include "../../wgpu-pathtracer_b200/csrc/scene_prep.h"
+
+#include <cstring>
+#include <vector>
+
+using namespace ptc;
+
+struct emu_scene_view { const DevScene* ds; };
+extern "C" const DevScene* emu_dev_scene(const void* e);
+extern "C" void emu_path_cfg(const void* e, const ptc_uniforms* un, PathCfg* pc, ptc_uniforms* out_un);
+
+namespace {
+
+struct Lane {
+    int node = PTC_SENTINEL, sp = 0;
+    int stack[PTC_STACK_SIZE];
+    uint32_t ray = 0xFFFFFFFFu, tri_i = 0, tri_end = 0;
+    int pend = 0;                 // postponed leaf (policy 1), 0 = none (leaf refs are negative)
+    pt_v3 o, d;
+    RaySlab r;
+    HitRec best;
+};
+
+struct SimParams {
+    uint32_t tri_vote, refill_vote, policy, nwarps;
+    uint32_t node_steps;          // node steps per voted node phase (policy 2)
+    uint32_t _pad[3];
+};
+
+struct SimOut {
+    uint64_t it_refill, it_tri, it_node;          // warp iterations per phase
+    uint64_t ln_refill, ln_tri, ln_node;          // lanes doing useful work in those iterations
+    uint64_t node_visits, tri_tests, rays;
+    uint64_t mismatches;                          // hits differing from trace_closest_bvh2 (must be 0)
+};
+
+inline void tri_step(const DevScene& s, Lane& L, int leaf, uint32_t& ti, uint32_t& te) {
+    if (ti == te) { const uint32_t enc = ~(uint32_t)leaf; ti = enc >> 3; te = ti + (enc & 7u) + 1u; }
+    const F4* tp = s.tris + (size_t)ti * 4;
+    F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
+    float t, b1, b2;
+    if (pt_ray_tri(L.o, L.d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+        const uint32_t id = f2u(a.w);
+        if (t < L.best.t || (t == L.best.t && id < L.best.tri)) { L.best.t = t; L.best.b1 = b1; L.best.b2 = b2; L.best.tri = id; }
+    }
+    ++ti;
+}
+
+inline void node_step(const DevScene& s, Lane& L) {
+    const NodeQ nq = ld_node(s.nodes + L.node);
+    bool h0, h1; float tn0, tn1;
+    node_test(L.r, nq, L.best.t, h0, h1, tn0, tn1);
+    const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+    const bool swap = tn1 < tn0;
+    if (h0 && h1) { L.stack[L.sp++] = swap ? c0 : c1; L.node = swap ? c1 : c0; }
+    else if (h0 || h1) L.node = h0 ? c0 : c1;
+    else L.node = L.stack[--L.sp];
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default")))
+int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParams* P, SimOut* out, uint32_t* hits_out) {
+    const DevScene& s = *emu_dev_scene(scene);
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t NW = P->nwarps ? P->nwarps : 1;
+    std::vector<Lane> lanes((size_t)NW * 32);
+    std::vector<uint8_t> exhausted(NW, 0), finished(NW, 0);
+    std::vector<HitRec> res(n);
+    uint64_t cursor = 0;
+    uint32_t live = NW;
+    while (live) {
+        for (uint32_t w = 0; w < NW; ++w) {
+            if (finished[w]) continue;
+            Lane* L = &lanes[(size_t)w * 32];
+            uint32_t idle = 0, at_leaf = 0, at_node = 0, pend = 0;
+            for (int l = 0; l < 32; ++l) {
+                if (L[l].node == PTC_SENTINEL && L[l].pend == 0) idle |= 1u << l;
+                else if (L[l].node < 0) at_leaf |= 1u << l;
+                else if (L[l].node != PTC_SENTINEL) at_node |= 1u << l;
+                if (L[l].pend != 0) pend |= 1u << l;
+            }
+            const uint32_t nidle = (uint32_t)__builtin_popcount(idle);
+            if (idle == 0xFFFFFFFFu || (!exhausted[w] && nidle >= P->refill_vote)) {
+                out->it_refill++;
+                for (int l = 0; l < 32; ++l) if ((idle >> l & 1) && L[l].ray != 0xFFFFFFFFu) { res[L[l].ray] = L[l].best; L[l].ray = 0xFFFFFFFFu; }
+                if (!exhausted[w]) {
+                    uint64_t base = cursor; cursor += nidle;
+                    if (base + nidle >= n) exhausted[w] = 1;
+                    uint32_t k = 0;
+                    for (int l = 0; l < 32; ++l) if (idle >> l & 1) {
+                        uint64_t i = base + k++;
+                        if (i >= n) continue;
+                        Lane& X = L[l];
+                        X.ray = (uint32_t)i;
+                        X.o = pt_mk3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]); X.d = pt_mk3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]);
+                        X.r = make_ray_slab(s, X.o, X.d);
+                        X.best.t = PT_RAY_TMAX; X.best.b1 = X.best.b2 = 0.0f; X.best.tri = 0xFFFFFFFFu;
+                        X.stack[0] = PTC_SENTINEL; X.sp = 1; X.tri_i = X.tri_end = 0; X.pend = 0;
+                        if (s.num_nodes != 0 && ray_is_finite(X.o, X.d)) X.node = 0;
+                        out->ln_refill++; out->rays++;
+                    }
+                }
+                bool any = false;
+                for (int l = 0; l < 32; ++l) any |= L[l].ray != 0xFFFFFFFFu;
+                if (!any) { finished[w] = 1; --live; }
+                continue;
+            }
+            if (P->policy == 0 || P->policy == 2) {
+                const uint32_t nleaf = (uint32_t)__builtin_popcount(at_leaf);
+                if (nleaf >= P->tri_vote || (at_leaf | idle) == 0xFFFFFFFFu) {
+                    out->it_tri++;
+                    for (int l = 0; l < 32; ++l) if (at_leaf >> l & 1) {
+                        Lane& X = L[l];
+                        tri_step(s, X, X.node, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
+                        if (X.tri_i == X.tri_end) X.node = X.stack[--X.sp];
+                    }
+                } else {
+                    const uint32_t steps = P->policy == 2 ? (P->node_steps ? P->node_steps : 1) : 1;
+                    for (uint32_t k = 0; k < steps; ++k) {
+                        uint32_t act = 0;
+                        for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) { node_step(s, L[l]); out->node_visits++; act++; }
+                        if (!act) break;
+                        out->it_node++; out->ln_node += act;
+                    }
+                }
+            } else {
+                // policy 1: postponed leaves.  A lane reaching a leaf parks it in `pend` and keeps traversing; it only
+                // waits (node < 0) when it reaches a second leaf.  The triangle phase works on pend first.
+                uint32_t want_tri = 0;
+                for (int l = 0; l < 32; ++l) if (L[l].pend != 0) want_tri++;
+                uint32_t blocked = 0;      // lanes that cannot take a node step
+                for (int l = 0; l < 32; ++l) if (!((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL)) blocked++;
+                if (want_tri >= P->tri_vote || blocked == 32) {
+                    out->it_tri++;
+                    for (int l = 0; l < 32; ++l) if (L[l].pend != 0) {
+                        Lane& X = L[l];
+                        tri_step(s, X, X.pend, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
+                        if (X.tri_i == X.tri_end) {
+                            X.pend = 0;
+                            if (X.node < 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }     // the waiting leaf moves up, traversal resumes
+                        }
+                    }
+                } else {
+                    uint32_t act = 0;
+                    for (int l = 0; l < 32; ++l) {
+                        Lane& X = L[l];
+                        if ((uint32_t)X.node < (uint32_t)PTC_SENTINEL) {
+                            node_step(s, X); out->node_visits++; act++;
+                            if (X.node < 0 && X.pend == 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }
+                        }
+                    }
+                    out->it_node++; out->ln_node += act;
+                }
+            }
+        }
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        if (hits_out) { std::memcpy(&hits_out[i * 4], &res[i].t, 4); std::memcpy(&hits_out[i * 4 + 1], &res[i].b1, 4); std::memcpy(&hits_out[i * 4 + 2], &res[i].b2, 4); hits_out[i * 4 + 3] = res[i].tri; }
+        HitRec h = trace_closest_bvh2(s, pt_mk3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]), pt_mk3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]), nullptr);
+        if (h.tri != res[i].tri || std::memcmp(&h.t, &res[i].t, 4) != 0) out->mismatches++;
+    }
+    return 0;
+}
+
+// rays of every path alive at `segment` (pixel order), as (ox, oy, oz, 0, dx, dy, dz, 0); returns the count
+extern "C" __attribute__((visibility("default")))
+uint64_t emu_collect_rays(const void* scene, const ptc_uniforms* un_in, uint32_t segment, float* out, uint64_t max_rays) {
+    const DevScene& s = *emu_dev_scene(scene);
+    PathCfg pc; ptc_uniforms un;
+    emu_path_cfg(scene, un_in, &pc, &un);
+    uint64_t n = 0;
+    for (uint32_t y = 0; y < pc.height; ++y) for (uint32_t x = 0; x < pc.width; ++x) {
+        PathState ps; ps.mask = pt_mk3(1.0f, 1.0f, 1.0f); ps.acc = pt_mk3(0.0f, 0.0f, 0.0f);
+        gen_primary(un.camera, x, y, ps.rng, ps.o, ps.d);
+        for (uint32_t seg = 0;; ++seg) {
+            if (seg == segment) {
+                if (n < max_rays) { float* r = out + n * 8; r[0] = ps.o.x; r[1] = ps.o.y; r[2] = ps.o.z; r[3] = 0; r[4] = ps.d.x; r[5] = ps.d.y; r[6] = ps.d.z; r[7] = 0; }
+                ++n; break;
+            }
+            HitRec h = trace_closest_bvh2(s, ps.o, ps.d, nullptr);
+            BounceOut bo = shade_bounce(s, pc, ps, h, seg);
+            if (!bo.alive) break;
+            ps = bo.next;
+        }
+    }
+    return n;
+}
