@@ -57,6 +57,17 @@ emu_scene* emu_create(const ptc_scene_view* v, const ptc_config* cfg) {
     return e;
 }
 
+// accessors for warpsim.cpp (development aid in the same test-only library)
+__attribute__((visibility("default")))
+const DevScene* emu_dev_scene(const void* e) { return &static_cast<const emu_scene*>(e)->ds; }
+__attribute__((visibility("default")))
+void emu_path_cfg(const void* ev, const ptc_uniforms* un_in, PathCfg* pc, ptc_uniforms* out_un) {
+    const emu_scene* e = static_cast<const emu_scene*>(ev);
+    *out_un = *un_in; out_un->num_lights = e->ds.num_lights;
+    pc->width = e->cfg.width; pc->height = e->cfg.height; pc->max_bounces = e->cfg.max_bounces;
+    pc->send_to_light_probability = e->cfg.send_to_light_probability; pc->accum_mode = e->cfg.accum_mode; pc->is_grabbed = un_in->is_grabbed;
+}
+
 __attribute__((visibility("default")))
 void emu_destroy(emu_scene* e) { delete e; }
 

@@ -32,7 +32,9 @@ struct Lane {
 struct SimParams {
     uint32_t tri_vote, refill_vote, policy, nwarps;
     uint32_t node_steps;          // node steps per voted node phase (policy 2)
-    uint32_t _pad[3];
+    uint32_t node_inner;          // > 0: stay in the node phase while at least this many lanes can take a node step
+    uint32_t tri_inner;           // > 0: stay in the triangle phase while at least this many lanes have a triangle to test
+    uint32_t _pad;
 };
 
 struct SimOut {
@@ -40,6 +42,7 @@ struct SimOut {
     uint64_t ln_refill, ln_tri, ln_node;          // lanes doing useful work in those iterations
     uint64_t node_visits, tri_tests, rays;
     uint64_t mismatches;                          // hits differing from trace_closest_bvh2 (must be 0)
+    uint64_t it_outer, it_inner_vote;             // outer-loop decisions (full vote) and inner-loop votes
 };
 
 inline void tri_step(const DevScene& s, Lane& L, int leaf, uint32_t& ti, uint32_t& te) {
@@ -89,6 +92,7 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                 if (L[l].pend != 0) pend |= 1u << l;
             }
             const uint32_t nidle = (uint32_t)__builtin_popcount(idle);
+            out->it_outer++;
             if (idle == 0xFFFFFFFFu || (!exhausted[w] && nidle >= P->refill_vote)) {
                 out->it_refill++;
                 for (int l = 0; l < 32; ++l) if ((idle >> l & 1) && L[l].ray != 0xFFFFFFFFu) { res[L[l].ray] = L[l].best; L[l].ray = 0xFFFFFFFFu; }
@@ -117,11 +121,18 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
             if (P->policy == 0 || P->policy == 2) {
                 const uint32_t nleaf = (uint32_t)__builtin_popcount(at_leaf);
                 if (nleaf >= P->tri_vote || (at_leaf | idle) == 0xFFFFFFFFu) {
-                    out->it_tri++;
-                    for (int l = 0; l < 32; ++l) if (at_leaf >> l & 1) {
-                        Lane& X = L[l];
-                        tri_step(s, X, X.node, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
-                        if (X.tri_i == X.tri_end) X.node = X.stack[--X.sp];
+                    for (;;) {
+                        out->it_tri++;
+                        uint32_t still = 0;
+                        for (int l = 0; l < 32; ++l) if (L[l].node < 0) {
+                            Lane& X = L[l];
+                            tri_step(s, X, X.node, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
+                            if (X.tri_i == X.tri_end) X.node = X.stack[--X.sp];
+                            if (X.node < 0) still++;
+                        }
+                        if (!P->tri_inner) break;
+                        out->it_inner_vote++;
+                        if (still < P->tri_inner) break;
                     }
                 } else {
                     const uint32_t steps = P->policy == 2 ? (P->node_steps ? P->node_steps : 1) : 1;
@@ -130,6 +141,12 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                         for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) { node_step(s, L[l]); out->node_visits++; act++; }
                         if (!act) break;
                         out->it_node++; out->ln_node += act;
+                        if (P->node_inner) {
+                            uint32_t still = 0;
+                            for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) still++;
+                            out->it_inner_vote++;
+                            if (still >= P->node_inner) --k;      // stay
+                        }
                     }
                 }
             } else {
@@ -140,25 +157,38 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                 uint32_t blocked = 0;      // lanes that cannot take a node step
                 for (int l = 0; l < 32; ++l) if (!((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL)) blocked++;
                 if (want_tri >= P->tri_vote || blocked == 32) {
-                    out->it_tri++;
-                    for (int l = 0; l < 32; ++l) if (L[l].pend != 0) {
-                        Lane& X = L[l];
-                        tri_step(s, X, X.pend, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
-                        if (X.tri_i == X.tri_end) {
-                            X.pend = 0;
-                            if (X.node < 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }     // the waiting leaf moves up, traversal resumes
+                    for (;;) {
+                        out->it_tri++;
+                        uint32_t still = 0;
+                        for (int l = 0; l < 32; ++l) if (L[l].pend != 0) {
+                            Lane& X = L[l];
+                            tri_step(s, X, X.pend, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
+                            if (X.tri_i == X.tri_end) {
+                                X.pend = 0;
+                                if (X.node < 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }     // the waiting leaf moves up, traversal resumes
+                            }
+                            if (X.pend != 0) still++;
                         }
+                        if (!P->tri_inner) break;
+                        out->it_inner_vote++;
+                        if (still < P->tri_inner) break;
                     }
                 } else {
-                    uint32_t act = 0;
-                    for (int l = 0; l < 32; ++l) {
-                        Lane& X = L[l];
-                        if ((uint32_t)X.node < (uint32_t)PTC_SENTINEL) {
-                            node_step(s, X); out->node_visits++; act++;
-                            if (X.node < 0 && X.pend == 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }
+                    for (;;) {
+                        uint32_t act = 0, still = 0;
+                        for (int l = 0; l < 32; ++l) {
+                            Lane& X = L[l];
+                            if ((uint32_t)X.node < (uint32_t)PTC_SENTINEL) {
+                                node_step(s, X); out->node_visits++; act++;
+                                if (X.node < 0 && X.pend == 0) { X.pend = X.node; X.node = X.stack[--X.sp]; }
+                            }
+                            if ((uint32_t)X.node < (uint32_t)PTC_SENTINEL) still++;
                         }
+                        out->it_node++; out->ln_node += act;
+                        if (!P->node_inner) break;
+                        out->it_inner_vote++;
+                        if (still < P->node_inner) break;
                     }
-                    out->it_node++; out->ln_node += act;
                 }
             }
         }

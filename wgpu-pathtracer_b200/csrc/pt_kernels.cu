@@ -14,10 +14,32 @@ __global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameC
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) fc->count[0] = npix;
     if (i >= npix) return;
-    uint32_t x = i % un.camera.width, y = i / un.camera.width;
+    // Queue slot i -> pixel: 8x4 pixel tiles, one tile per warp, so the 32 primary rays of a warp (and the paths that
+    // descend from them, which k_shade compacts in queue order) share BVH nodes and texture lines; a scanline run of 32
+    // pixels diverges sooner.  Pixels outside the tile-aligned part (right strip, then bottom strip) follow in row
+    // order.  The reference's thread -> pixel map (pathtracer.wgsl:22-24) is not observable: every pixel's result
+    // depends only on (x, y, frame).
+    const uint32_t W = un.camera.width, H = un.camera.height, W8 = W & ~7u, H4 = H & ~3u;
+    uint32_t x, y;
+#ifdef PTC_RAYGEN_LINEAR
+    if (false) {
+#else
+    if (i < W8 * H4) {
+#endif
+        const uint32_t tile = i >> 5, in = i & 31u, tpr = W8 >> 3;
+        x = (tile % tpr) * 8u + (in & 7u); y = (tile / tpr) * 4u + (in >> 3);
+#ifdef PTC_RAYGEN_LINEAR
+    } else if (true) { x = i % W; y = i / W;
+#endif
+    } else {
+        uint32_t j = i - W8 * H4;
+        const uint32_t rw = W - W8;
+        if (j < rw * H4) { x = W8 + j % rw; y = j / rw; }
+        else { j -= rw * H4; x = j % W; y = H4 + j / W; }
+    }
     uint32_t rng; pt_v3 ro, rd;
     gen_primary(un.camera, x, y, rng, ro, rd);
-    st4_stream(q.ray_o + i, ro.x, ro.y, ro.z, __uint_as_float(i));
+    st4_stream(q.ray_o + i, ro.x, ro.y, ro.z, __uint_as_float(y * W + x));
     st4_stream(q.ray_d + i, rd.x, rd.y, rd.z, __uint_as_float(rng));
     // color_mask = 1 and accumulated_color = 0 at segment 0 are constants of k_shade<true>: not stored
 }
@@ -61,10 +83,20 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, cons
 //     up to 4 triangles on every iteration, the triangle part with ~13 % of the lanes active.
 //   * when PTC_REFILL_VOTE lanes are idle (or all are) they write their hits and take new rays from the device cursor
 //     with one aggregated atomicAdd, so a warp does not drain down to its slowest ray.
+//   * a phase, once voted, REPEATS while enough lanes can still use it (PTC_NODE_INNER lanes at an inner node,
+//     PTC_TRI_INNER lanes at a leaf): the repeat test is one ballot, the full vote three plus the branches — the
+//     kernel is issue-bound, and in the lane-accurate model (tools/warpsim.py) the full vote was a third of all
+//     warp instructions when taken every step.
 // A lane waiting at a leaf does not traverse speculatively, so the nodes and triangles visited per ray are exactly
 // those of the plain loop (and of the oracle's counters).
 #ifndef PTC_TRI_VOTE
-#define PTC_TRI_VOTE 10
+#define PTC_TRI_VOTE 8
+#endif
+#ifndef PTC_NODE_INNER
+#define PTC_NODE_INNER 12          // 0: vote after every step
+#endif
+#ifndef PTC_TRI_INNER
+#define PTC_TRI_INNER 8
 #endif
 #ifndef PTC_REFILL_VOTE
 #define PTC_REFILL_VOTE 16
@@ -122,28 +154,36 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
         const uint32_t at_leaf = __ballot_sync(FULL, node < 0);
         if (__popc(at_leaf) >= PTC_TRI_VOTE || (at_leaf | idle) == FULL) {
             // ---- triangle phase: one triangle per waiting lane ----
-            if (node < 0) {
-                if (tri_i == tri_end) { const uint32_t enc = ~(uint32_t)node; tri_i = enc >> 3; tri_end = tri_i + (enc & 7u) + 1u; }
-                const F4* tp = s.tris + (size_t)tri_i * 4;
-                F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
-                float t, b1, b2;
-                if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
-                    const uint32_t id = f2u(a.w);
-                    if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+#pragma unroll 1
+            for (;;) {
+                if (node < 0) {
+                    if (tri_i == tri_end) { const uint32_t enc = ~(uint32_t)node; tri_i = enc >> 3; tri_end = tri_i + (enc & 7u) + 1u; }
+                    const F4* tp = s.tris + (size_t)tri_i * 4;
+                    F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
+                    float t, b1, b2;
+                    if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                        const uint32_t id = f2u(a.w);
+                        if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+                    }
+                    if (++tri_i == tri_end) node = stack[--sp];
                 }
-                if (++tri_i == tri_end) node = stack[--sp];
+                if (PTC_TRI_INNER == 0 || __popc(__ballot_sync(FULL, node < 0)) < PTC_TRI_INNER) break;
             }
         } else {
             // ---- node phase: both children of one node per lane ----
-            if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
-                const NodeQ nq = ld_node(s.nodes + node);
-                bool h0, h1; float tn0, tn1;
-                node_test(r, nq, best.t, h0, h1, tn0, tn1);
-                const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
-                const bool swap = tn1 < tn0;
-                if (h0 && h1) { stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }
-                else if (h0 || h1) node = h0 ? c0 : c1;
-                else node = stack[--sp];
+#pragma unroll 1
+            for (;;) {
+                if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
+                    const NodeQ nq = ld_node(s.nodes + node);
+                    bool h0, h1; float tn0, tn1;
+                    node_test(r, nq, best.t, h0, h1, tn0, tn1);
+                    const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+                    const bool swap = tn1 < tn0;
+                    if (h0 && h1) { stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }
+                    else if (h0 || h1) node = h0 ? c0 : c1;
+                    else node = stack[--sp];
+                }
+                if (PTC_NODE_INNER == 0 || __popc(__ballot_sync(FULL, (uint32_t)node < (uint32_t)PTC_SENTINEL)) < PTC_NODE_INNER) break;
             }
         }
     }
