@@ -40,6 +40,8 @@ WORKLOADS = {
     "dragon_1080p": dict(scene="dragon", width=1920, height=1080, max_bounces=4, config_index=1),
     "classroom_1080p": dict(scene="classroom", width=1920, height=1080, max_bounces=4, config_index=3),
     "san_miguel_4k": dict(scene="san_miguel", width=3840, height=2160, max_bounces=4, config_index=4),
+    # non-reference quality mode: shadow rays with any-hit early-out + MIS; rays include the shadow rays
+    "classroom_1080p_mis": dict(scene="classroom", width=1920, height=1080, max_bounces=4, config_index=3, light_sampling=1),
 }
 
 
@@ -116,7 +118,7 @@ def cpu_baseline(pkg, w, scene, camera, seconds, accum_mode, nthreads=0, first_f
     """Times the oracle (CPU restatement of the reference's WGSL path) on whole frames of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binding as oracle
-    cfg = pkg.make_config(w["width"], w["height"], max_bounces=w["max_bounces"], accum_mode=accum_mode)
+    cfg = pkg.make_config(w["width"], w["height"], max_bounces=w["max_bounces"], accum_mode=accum_mode, light_sampling=w.get("light_sampling", 0))
     orc = oracle.OracleScene(scene, cfg)
     cores = nthreads if nthreads > 0 else (os.cpu_count() or 1)
     color = np.zeros((w["height"], w["width"], 4), np.float32)
@@ -145,7 +147,7 @@ def run_reference(args):
     steps, warm = min(args.steps, 8), min(args.warmup, 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binding as oracle
-    cfg = pkg.make_config(w["width"], w["height"], max_bounces=w["max_bounces"])
+    cfg = pkg.make_config(w["width"], w["height"], max_bounces=w["max_bounces"], light_sampling=w.get("light_sampling", 0))
     orc = oracle.OracleScene(scene, cfg)
     cores = os.cpu_count() or 1
     color = np.zeros((w["height"], w["width"], 4), np.float32)
@@ -198,7 +200,7 @@ def main():
     T = pkg.types
     W, H, K, Wm = w["width"], w["height"], args.steps, max(args.warmup, 3)
     accum = T.ACCUM_SUM if world > 1 else T.ACCUM_MEAN
-    cfg = pkg.make_config(W, H, max_bounces=w["max_bounces"], accum_mode=accum)
+    cfg = pkg.make_config(W, H, max_bounces=w["max_bounces"], accum_mode=accum, light_sampling=w.get("light_sampling", 0))
     step = pkg.RTStep.create(scene, cfg, device=local)
     out = torch.zeros(H, W, 4, device=f"cuda:{local}", dtype=torch.float32)
     step.set_output(out.data_ptr())                       # the caller injects the accumulation target (raytracer.rs:86)
@@ -320,7 +322,8 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "spp_per_s": K * world / (ms * 1e-3),
-        "config": {"workload": f"{w['scene']} stand-in {W}x{H}, MAX_BOUNCES={w['max_bounces']}, 1 spp per step, {bvh['triangles']} triangles",
+        "config": {"workload": f"{w['scene']} stand-in {W}x{H}, MAX_BOUNCES={w['max_bounces']}, 1 spp per step, {bvh['triangles']} triangles"
+                               + (", PTC_LIGHTS_MIS (non-reference mode: one any-hit shadow ray per opaque hit, counted as a ray)" if w.get("light_sampling") else ""),
                    "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: each frame streams ~%.0f MB of path-state queues; the %.1f MB BVH is L2-resident by design" % (
                        W * H * 144 / 1e6, (bvh["node_bytes"] + bvh["triangle_bytes"]) / 1e6)},

@@ -122,6 +122,17 @@ enum ptc_accum_mode {
     PTC_ACCUM_SUM  = 1   /* rgb += c, a += 1: associative, used for frame-sharded multi-GPU + reduce */
 };
 
+/* Light sampling.  The reference ships SEND_TO_LIGHT_PROBABILITY = 0 (shader_definitions.rs:19): emitters are found by
+ * BSDF sampling alone, and its light branch (pathtracer/pathtracer.wgsl:21-73,175-191) never applies the weights it
+ * computes.  PTC_LIGHTS_MIS is this library's completion of that direction, a NON-PARITY quality mode with
+ * the same expected image: at every opaque hit whose path continues, one shadow ray (any-hit traversal, early out) to a
+ * uniform point of a uniformly chosen emissive triangle, combined with the BSDF-sampled emitter hits by the balance
+ * heuristic.  Definition: include/ptmath.h (pt_ggx_reflect_pdf, pt_light_inv_pdf, pt_mis_weight), DESIGN.md section 9. */
+enum ptc_light_sampling {
+    PTC_LIGHTS_REFERENCE = 0,
+    PTC_LIGHTS_MIS       = 1
+};
+
 /* compat flags */
 #define PTC_COMPAT_NONE 0u
 
@@ -136,8 +147,9 @@ typedef struct ptc_config {
     uint32_t env_texture_index;        /* sky.wgsl:10 hard-codes 9 */
     uint32_t accum_mode;               /* enum ptc_accum_mode */
     uint32_t compat_flags;
-    uint32_t bvh_width;                /* 0 = library default; 2 = BVH2; 8 = wide compressed */
-    uint32_t reserved[7];
+    uint32_t bvh_width;                /* 0 = library default; 2 = BVH2 */
+    uint32_t light_sampling;           /* enum ptc_light_sampling; PTC_LIGHTS_MIS requires send_to_light_probability == 0 */
+    uint32_t reserved[6];
 } ptc_config;
 
 /* Planes readable from a step. */

@@ -192,6 +192,34 @@ PT_HD int pt_ray_tri(pt_v3 o, pt_v3 d, pt_v3 v0, pt_v3 e1, pt_v3 e2,
     return 1;
 }
 
+/* ---- light sampling with multiple importance sampling (PTC_LIGHTS_MIS) -----
+ * Project-defined (the reference's light branch is unfinished: it computes weights it never applies), shared by oracle
+ * and kernels.  The reference scatters by sampling a GGX half vector h about the shading normal n (theta =
+ * atan(alpha sqrt(u/(1-u))), bsdf.wgsl:155-187), mirroring v about it, and multiplying the throughput by
+ * albedo (1 - metallic) with pdf = 1 -- so, seen as an estimator, its BSDF*cos IS  albedo (1 - metallic) * p_b(wi),
+ * p_b being the solid-angle density of that sampling:  p_b(wi) = D(h) (n.h) / (4 v.h),  h = normalize(v + wi),
+ * D = alpha^2 / (pi ((n.h)^2 (alpha^2 - 1) + 1)^2). */
+PT_HD float pt_ggx_reflect_pdf(pt_v3 n, pt_v3 v, pt_v3 wi, float alpha) {
+    pt_v3 h = pt_normalize(pt_add(v, wi));
+    float nh = pt_dot(n, h), vh = pt_dot(v, h);
+    if (!(nh > 0.0f) || !(vh > 1.0e-6f)) return 0.0f;
+    float a2 = alpha * alpha;
+    float den = pt_fma(nh * nh, a2 - 1.0f, 1.0f);
+    float dd = pt_div(a2, (PT_PI * den) * den);
+    return pt_div(dd * nh, 4.0f * vh);
+}
+/* 1 / p_l: p_l = solid-angle density, seen from the shading point, of choosing one of num_lights emissive triangles
+ * uniformly and a uniform point on it = dist^2 / (cos_l * area * num_lights); emitters are two-sided (an emissive hit
+ * counts from either side in the reference), hence |.|.  dir = unit vector towards the point, dist2 its squared distance. */
+PT_HD float pt_light_inv_pdf(pt_v3 v0, pt_v3 v1, pt_v3 v2, pt_v3 dir, float dist2, float num_lights) {
+    pt_v3 ng = pt_cross(pt_sub(v1, v0), pt_sub(v2, v0));           /* |ng| = 2 area */
+    return pt_div((pt_abs(pt_dot(ng, dir)) * 0.5f) * num_lights, dist2);
+}
+/* balance heuristic written on x = p_b / p_l: weight of the BSDF-sampled emitter hit, p_b / (p_b + p_l) = x / (1 + x);
+ * and, because BSDF*cos = a * p_b, also the whole factor of the light-sampled term, (a p_b / p_l) * p_l / (p_b + p_l).
+ * 1 - 1/(1+x) stays finite for x = inf. */
+PT_HD float pt_mis_weight(float pdf_b, float inv_pdf_l) { return 1.0f - pt_div(1.0f, 1.0f + pdf_b * inv_pdf_l); }
+
 #define PT_RAY_TMIN 0.01f      /* rt_helpers.wgsl:49 RayDesc(.., 0.01, 10000.0, ..) */
 #define PT_RAY_TMAX 10000.0f
 

@@ -78,6 +78,9 @@ struct Scene {
     std::vector<ptc_material> materials;
     std::vector<Tex> textures;
     std::vector<ptc_triangle> lights;     // pt.rs:206-243
+    std::vector<uint32_t> light_tri;      // PTC_LIGHTS_MIS: global triangle id of lights[i]
+    std::vector<uint32_t> light_of_tri;   //                 global triangle id -> light index (0xFFFFFFFF: none)
+    bool has_lights = false;              //                 false when lights holds only the dummy entry
     std::vector<uint32_t> tri_mesh;       // global triangle -> mesh (instance_index)
     ptc_config cfg;
     // traversal structure
@@ -362,7 +365,8 @@ float get_schlick_weight(float adotb) {                                   // bsd
     return m * m * m * m * m;
 }
 
-struct BSDFResult { pt_v3 color; float pdf; pt_v3 ray_outgoing; pt_v3 p; };
+struct BSDFResult { pt_v3 color; float pdf; pt_v3 ray_outgoing; pt_v3 p;
+                    pt_v3 shading_normal; float alpha; bool refracted; };   // the last three feed PTC_LIGHTS_MIS only
 
 BSDFResult disney_bsdf(Rng& rng, pt_v3 p, pt_v3 ray_incoming, pt_v3 normal_in, const SampledMaterial& m) {   // bsdf.wgsl:195-231
     // bsdf_prep_data, bsdf.wgsl:39-87
@@ -413,13 +417,15 @@ BSDFResult disney_bsdf(Rng& rng, pt_v3 p, pt_v3 ray_incoming, pt_v3 normal_in, c
     res.pdf = pdf;
     res.ray_outgoing = outgoing;
     res.p = pt_add(p, pt_scale(normal, off));
+    res.shading_normal = normal; res.alpha = alpha_x; res.refracted = refracted != 0.0f;
     return res;
 }
 
 // ---------------------------------------------------------------------------
 // integrator — src/shaders/pathtracer/pathtracer/pathtracer.wgsl
 // ---------------------------------------------------------------------------
-struct ScatteredRay { pt_v3 origin, direction, attenuation, normal; bool hit_prediction; };
+struct ScatteredRay { pt_v3 origin, direction, attenuation, normal; bool hit_prediction;
+                      pt_v3 shading_normal; float alpha; bool refracted; };
 
 ScatteredRay scatter(Rng& rng, pt_v3 ro, pt_v3 rd, const Intersection& is) {       // :76-101
     pt_v3 p = pt_fma3(rd, is.ri.t, ro);
@@ -431,6 +437,7 @@ ScatteredRay scatter(Rng& rng, pt_v3 ro, pt_v3 rd, const Intersection& is) {    
     s.origin = result.p; s.direction = result.ray_outgoing;
     s.attenuation = pt_mk3(pt_div(result.color.x, result.pdf), pt_div(result.color.y, result.pdf), pt_div(result.color.z, result.pdf));
     s.normal = n; s.hit_prediction = true;
+    s.shading_normal = result.shading_normal; s.alpha = result.alpha; s.refracted = result.refracted;
     return s;
 }
 
@@ -451,6 +458,7 @@ ScatteredRay light_scatter(Rng& rng, pt_v3 ro, pt_v3 rd, const ptc_triangle& tri
     ScatteredRay s;
     s.origin = p; s.direction = dir; s.attenuation = is.material.albedo; s.normal = n;
     s.hit_prediction = pt_dot(dir, n) > 0.0f;
+    s.shading_normal = n; s.alpha = 1.0f; s.refracted = true;
     return s;
 }
 
@@ -469,6 +477,9 @@ RayColorResult ray_color(const Scene& sc, Rng& rng, pt_v3 ro, pt_v3 rd, uint32_t
     pt_v3 accumulated = pt_mk3(0.0f, 0.0f, 0.0f);
     RayColorResult res; std::memset(&res, 0, sizeof(res));
     res.first_inst = res.first_geom = 0xFFFFFFFFu;
+    // PTC_LIGHTS_MIS (ptcore_types.h; not in the reference): light sampling + balance heuristic, same expectation
+    const bool mis = sc.cfg.light_sampling == PTC_LIGHTS_MIS && sc.has_lights;
+    float pdf_prev = -1.0f;               // density with which the previous hit's scattering produced curr_rd; < 0: weight 1
     for (uint32_t i = 0; i <= sc.cfg.max_bounces; ++i) {
         Intersection is = trace_ray(sc, curr_ro, curr_rd, brute, c);
         if (i == 0) { res.first_inst = is.instance_index; res.first_geom = is.geometry_index; }
@@ -484,9 +495,52 @@ RayColorResult ray_color(const Scene& sc, Rng& rng, pt_v3 ro, pt_v3 rd, uint32_t
                 if (!scattered.hit_prediction) scattered = scatter(rng, curr_ro, curr_rd, is);   // :183-189
             }
             pt_v3 prev_rd = curr_rd;
-            curr_ro = scattered.origin; curr_rd = scattered.direction;
             const SampledMaterial& m = is.material;
-            accumulated = pt_add(accumulated, pt_mul(m.emissive, color_mask));       // :200
+            pt_v3 emitted = m.emissive;
+            pt_v3 light_sample = pt_mk3(0.0f, 0.0f, 0.0f); bool light_sample_on = false;   // added AFTER the emission term below
+            if (mis) {
+                if (is.hit_light && pdf_prev >= 0.0f && sc.light_of_tri[is.ri.tri] != 0xFFFFFFFFu) {
+                    // an emitter found by BSDF sampling, weighted against the light sample taken at the previous hit
+                    const ptc_triangle& L = sc.lights[sc.light_of_tri[is.ri.tri]];
+                    float inv_pl = pt_light_inv_pdf(v3(L.v0), v3(L.v1), v3(L.v2), prev_rd, is.ri.t * is.ri.t, (float)sc.lights.size());
+                    emitted = pt_scale(emitted, pt_mis_weight(pdf_prev, inv_pl));
+                }
+                const bool opaque = m.transmission_weight == 0.0f;
+                if (!is.hit_light && i < sc.cfg.max_bounces && opaque) {
+                    // one shadow ray from the scattered origin to a uniform point of a uniformly chosen emissive triangle
+                    uint32_t li = rand_int(rng) % (uint32_t)sc.lights.size();
+                    const ptc_triangle& L = sc.lights[li];
+                    float r1 = rand_float(rng), r2 = rand_float(rng);
+                    float s1 = pt_sqrt(r1);
+                    float w0 = 1.0f - s1, w1 = s1 * (1.0f - r2), w2 = s1 * r2;
+                    pt_v3 q = pt_mk3(L.v0[0] * w0 + L.v1[0] * w1 + L.v2[0] * w2, L.v0[1] * w0 + L.v1[1] * w1 + L.v2[1] * w2,
+                                     L.v0[2] * w0 + L.v1[2] * w1 + L.v2[2] * w2);
+                    pt_v3 to = pt_sub(q, scattered.origin);
+                    float dist2 = pt_dot(to, to), dist = pt_sqrt(dist2);
+                    pt_v3 dir = pt_scale(to, pt_div(1.0f, dist));
+                    float wgt = pt_mis_weight(pt_ggx_reflect_pdf(scattered.shading_normal, pt_neg(prev_rd), dir, scattered.alpha),
+                                              pt_light_inv_pdf(v3(L.v0), v3(L.v1), v3(L.v2), dir, dist2, (float)sc.lights.size()));
+                    // radiance of the sampled point: the emissive tap of the light triangle's material at its uv
+                    uint32_t lt = sc.light_tri[li];
+                    const ptc_mesh& lm = sc.meshes[sc.tri_mesh[lt]];
+                    const ptc_vertex* lv[3];
+                    for (int k = 0; k < 3; ++k) lv[k] = &sc.vertices[sc.indices[(size_t)lt * 3 + k]];
+                    float lu = lv[0]->uv[0] * w0 + lv[1]->uv[0] * w1 + lv[2]->uv[0] * w2;
+                    float lvv = lv[0]->uv[1] * w0 + lv[1]->uv[1] * w1 + lv[2]->uv[1] * w2;
+                    pt_v3 le = sample_texture_color(sc, sc.materials[lm.material_index].emissive_texture_idx, lu, lvv);
+                    pt_v3 carried = pt_scale(pt_mul(le, scattered.attenuation), wgt);
+                    bool wanted = !scattered.refracted && dist > PT_RAY_TMIN && pt_dot(carried, pt_mk3(1.0f, 1.0f, 1.0f)) > 0.0f;
+                    if (wanted) {
+                        Hit blocker = closest_bvh(sc, scattered.origin, dir, c);     // occluded iff something lies in (tmin, 0.999 dist)
+                        if (!(blocker.hit && blocker.t < dist * 0.999f)) { light_sample = pt_mul(carried, color_mask); light_sample_on = true; }
+                    }
+                }
+                pdf_prev = (!scattered.refracted && opaque)
+                               ? pt_ggx_reflect_pdf(scattered.shading_normal, pt_neg(prev_rd), scattered.direction, scattered.alpha) : -1.0f;
+            }
+            curr_ro = scattered.origin; curr_rd = scattered.direction;
+            accumulated = pt_add(accumulated, pt_mul(emitted, color_mask));          // :200
+            if (light_sample_on) accumulated = pt_add(accumulated, light_sample);
             color_mask = pt_mul(color_mask, scattered.attenuation);                  // :202
             if (is.hit_light) break;                                                 // :204-206
             if (i == 0) {                                                            // :208-223
@@ -600,7 +654,12 @@ orc_scene* orc_scene_create(const ptc_scene_view* view, const ptc_config* cfg) {
         std::memcpy(tri.v2, sc.vertices[ix[2]].position, 12);
         std::memcpy(tri.normal, sc.vertices[ix[0]].normal, 12);
         sc.lights.push_back(tri);
+        sc.light_tri.push_back(t);
     }
+    sc.has_lights = !sc.lights.empty();
+    sc.light_of_tri.assign(ntri, 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < sc.light_tri.size(); ++i) sc.light_of_tri[sc.light_tri[i]] = i;
+    if (!sc.has_lights) sc.light_tri.push_back(0);
     if (sc.lights.empty()) { ptc_triangle z; std::memset(&z, 0, sizeof(z)); sc.lights.push_back(z); }   // pt.rs:232-239
     build_bvh(sc);
     return o;

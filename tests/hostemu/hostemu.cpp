@@ -54,6 +54,7 @@ emu_scene* emu_create(const ptc_scene_view* v, const ptc_config* cfg) {
     ds.shade = e->ps.shade.data(); ds.mats = e->ps.mats.data(); ds.texs = e->texs.data(); ds.lights = e->ps.lights.data();
     ds.num_nodes = (uint32_t)e->ps.bvh.nodes.size(); ds.num_tris = e->ps.num_tris;
     ds.num_lights = (uint32_t)e->ps.lights.size(); ds.env_tex = cfg->env_texture_index;
+    ds.light_of_tri = e->ps.light_of_tri.data(); ds.num_real_lights = e->ps.num_real_lights;
     return e;
 }
 
@@ -66,6 +67,7 @@ void emu_path_cfg(const void* ev, const ptc_uniforms* un_in, PathCfg* pc, ptc_un
     *out_un = *un_in; out_un->num_lights = e->ds.num_lights;
     pc->width = e->cfg.width; pc->height = e->cfg.height; pc->max_bounces = e->cfg.max_bounces;
     pc->send_to_light_probability = e->cfg.send_to_light_probability; pc->accum_mode = e->cfg.accum_mode; pc->is_grabbed = un_in->is_grabbed;
+    pc->light_sampling = e->cfg.light_sampling;
 }
 
 __attribute__((visibility("default")))
@@ -84,6 +86,7 @@ int emu_render_frame(const emu_scene* e, const ptc_uniforms* un_in, float* color
     const uint32_t W = e->cfg.width, H = e->cfg.height;
     PathCfg pc; pc.width = W; pc.height = H; pc.max_bounces = e->cfg.max_bounces;
     pc.send_to_light_probability = e->cfg.send_to_light_probability; pc.accum_mode = e->cfg.accum_mode; pc.is_grabbed = un.is_grabbed;
+    pc.light_sampling = e->cfg.light_sampling;
     if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
     if (nthreads <= 0) nthreads = 1;
     std::atomic<uint32_t> next_row(0);
@@ -102,6 +105,7 @@ int emu_render_frame(const emu_scene* e, const ptc_uniforms* un_in, float* color
                     HitRec h = trace_closest_bvh2(e->ds, ps.o, ps.d, cnt);
                     rays[tid]++; nn[tid] += cnt[0]; nt[tid] += cnt[1];
                     BounceOut bo = shade_bounce(e->ds, pc, ps, h, seg);
+                    rays[tid] += bo.shadow_rays;
                     if (seg == 0) {
                         if (depth) depth[pi] = bo.first_t;
                         if (normal) { normal[pi * 4] = bo.first_normal.x; normal[pi * 4 + 1] = bo.first_normal.y; normal[pi * 4 + 2] = bo.first_normal.z; normal[pi * 4 + 3] = 1.0f; }

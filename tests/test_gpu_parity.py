@@ -357,3 +357,40 @@ def test_san_miguel_4k_c5(ptc, standins, oracle):
     scene, cam = standins.san_miguel()
     assert scene.num_triangles > 10_000_000
     band_parity(ptc, standins, oracle, scene, cam, 3840, 2160, 1, (1200, 1208))
+
+
+@pytest.mark.parametrize("which", ["lit_room", "soup", "classroom"])
+def test_light_sampling_mis_bit_exact(ptc, standins, oracle, which):
+    """PTC_LIGHTS_MIS through the wavefront (k_shade<MIS> queues shadow rays, k_trace<ANY> resolves them with the
+    any-hit early-out and adds into the next queue's accumulated colour) equals the oracle's restatement bit for bit;
+    the device ray counter includes the shadow rays."""
+    if which == "lit_room":
+        scene, cam = standins.lit_room()
+    elif which == "soup":
+        scene, cam = standins.random_soup(6000, seed=3, textured=True)
+    else:
+        scene, cam = standins.classroom(detail=0.3)
+    W, H = 320, 200
+    cfg = ptc.make_config(W, H, max_bounces=5, light_sampling=ptc.types.LIGHTS_MIS)
+    camera = standins.make_camera(cam, W, H)
+    step = ptc.RTStep.create(scene, cfg)
+    orc = oracle.OracleScene(scene, cfg)
+    ref, rays = None, 0
+    for f in (1, 2, 3):
+        u = camera.uniforms(frame=f)
+        step.update(u); step.render()
+        ref = orc.render_frame(u, None if ref is None else ref["color"])
+        rays += ref["rays"]
+    step.poll(True)
+    check_all_planes(ptc, step, ref)
+    s = step.stats()
+    assert s["rays_traced"] == rays
+    assert s["kernel_launches"] == 3 * (1 + 2 * 6 + 5)            # one any-hit launch per bounce that can take a light sample
+    step.destroy()
+
+
+def test_light_sampling_mis_rejects_reference_light_branch(ptc, standins):
+    scene, _ = standins.lit_room()
+    cfg = ptc.make_config(16, 16, light_sampling=ptc.types.LIGHTS_MIS, send_to_light_probability=0.5)
+    with pytest.raises(Exception):
+        ptc.RTStep.create(scene, cfg)

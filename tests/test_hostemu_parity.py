@@ -126,3 +126,20 @@ def test_empty_and_single_triangle_scenes(ptc, standins, oracle, hostemu):
     ro, re = both(ptc, standins, oracle, hostemu, sc, {"position": (0, 0, 0), "fov": 60.0, "target": (1, 0, 0)}, 32, 24, 2)
     assert_identical(ro, re)
     assert (ro["hit_id"][..., 0] == 0).any()
+
+
+@pytest.mark.parametrize("which", ["lit_room", "soup", "classroom"])
+def test_light_sampling_mis_mode(ptc, standins, oracle, hostemu, which):
+    """PTC_LIGHTS_MIS (shadow rays + balance heuristic, a non-parity quality mode defined in include/ptmath.h): the
+    product's device code and the oracle's independent restatement agree bit for bit, shadow rays included in the count."""
+    if which == "lit_room":
+        scene, cam = standins.lit_room()
+    elif which == "soup":
+        scene, cam = standins.random_soup(5000, seed=7, textured=True)          # glass, emissive and textured materials
+    else:
+        scene, cam = standins.classroom(detail=0.04)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 120, 80, 3, max_bounces=5, light_sampling=ptc.types.LIGHTS_MIS)
+    assert_identical(ro, re)
+    r0, _ = both(ptc, standins, oracle, hostemu, scene, cam, 120, 80, 3, max_bounces=5)
+    assert ro["rays"] > r0["rays"]                                              # shadow rays were traced
+    assert np.array_equal(ro["hit_id"], r0["hit_id"])                           # primary visibility is untouched

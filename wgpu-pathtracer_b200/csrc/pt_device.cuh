@@ -121,8 +121,9 @@ struct DevScene {
     const MatDev* mats;
     const TexDev* texs;
     const ptc_triangle* lights;
+    const uint32_t* light_of_tri;   // global triangle id -> index into lights[] (0xFFFFFFFF: not emissive); PTC_LIGHTS_MIS only
     uint32_t num_nodes, num_tris, num_lights, env_tex;
-    uint32_t num_pages, _pad;
+    uint32_t num_pages, num_real_lights;   // num_real_lights = 0 when lights[] holds only the dummy entry of pt.rs:232-239
     unsigned long long page_obj[PTC_MAX_TEX_PAGES];   // cudaTextureObject_t per atlas page (device build only)
     float grid_base[3], grid_extent[3];               // quantisation grid of the node boxes (bvh_build.h QuantGrid)
 };
@@ -131,6 +132,7 @@ struct PathCfg {
     uint32_t width, height, max_bounces;
     float send_to_light_probability;
     uint32_t accum_mode, is_grabbed;
+    uint32_t light_sampling;      // ptc_light_sampling
 };
 
 // ---- RNG: src/shaders/common/random.wgsl:7-36 ---------------------------------
@@ -408,6 +410,7 @@ struct PathState {
     pt_v3 o, d;          // current segment
     pt_v3 mask, acc;     // color_mask, accumulated_color (pathtracer/pathtracer.wgsl:155-156)
     uint32_t rng;
+    float pdf = -1.0f;   // PTC_LIGHTS_MIS: p_b of d (< 0: none)
 };
 
 struct BounceOut {
@@ -416,6 +419,7 @@ struct BounceOut {
     pt_v3 radiance;               // valid when !alive: ray_color's result
     // first-hit aux (valid when bounce == 0)
     float first_t; pt_v3 first_normal, first_albedo;
+    uint32_t shadow_rays;         // PTC_LIGHTS_MIS: any-hit rays this bounce traced (0 or 1)
 };
 
 // The resolved material at a hit (rt_helpers.wgsl:17-42 minus its dead taps).
@@ -433,8 +437,9 @@ PT_HD uint32_t pt_ctz(uint32_t x) {
 
 // scatter + disney_bsdf: pathtracer/pathtracer.wgsl:76-101, bsdf.wgsl:39-87,120-231.
 // Returns origin/direction/attenuation; n_ff receives the face-forwarded geometric-interpolated normal.
+struct ScatterAux { pt_v3 ns; float alpha; bool refracted; };   // shading normal, GGX alpha, lobe taken (PTC_LIGHTS_MIS)
 PT_HD void scatter_regular(uint32_t& rng, pt_v3 ro, pt_v3 rd, float t, pt_v3 n, const MatEval& m,
-                           pt_v3& out_o, pt_v3& out_d, pt_v3& atten, pt_v3& n_ff) {
+                           pt_v3& out_o, pt_v3& out_d, pt_v3& atten, pt_v3& n_ff, ScatterAux* aux = nullptr) {
     pt_v3 p = pt_fma3(rd, t, ro);
     pt_v3 v = pt_neg(rd);
     bool front = pt_dot(rd, n) < 0.0f;
@@ -473,6 +478,7 @@ PT_HD void scatter_regular(uint32_t& rng, pt_v3 ro, pt_v3 rd, float t, pt_v3 n, 
     pt_v3 col = pt_scale(m.albedo, 1.0f - m.metallic);
     atten = pt_mk3(pt_div(col.x, 1.0f), pt_div(col.y, 1.0f), pt_div(col.z, 1.0f));   // color / pdf, pdf == 1
     n_ff = nf;
+    if (aux) { aux->ns = ns; aux->alpha = alpha; aux->refracted = refr != 0.0f; }
 }
 
 // One iteration of ray_color's loop body (pathtracer/pathtracer.wgsl:159-233) for a
@@ -494,12 +500,33 @@ struct SurfaceOut {
     pt_v3 next_o, next_d;         // scattered ray (SURF_CONTINUE)
     uint32_t rng;
     float first_t; pt_v3 first_normal, first_albedo;   // first-hit aux (bounce 0)
+    // PTC_LIGHTS_MIS (see ptcore_types.h): the shadow ray of this hit starts at next_o
+    float light_q;                // SURF_LIGHT: 1 / p_l of the emitter that was hit, seen from the ray origin
+    float pdf_next;               // p_b of next_d, or -1: the next emitter hit takes weight 1 (refraction, transmissive material)
+    bool nee;                     // a shadow ray is wanted
+    pt_v3 nee_d; float nee_tmax;  // its direction and far end
+    pt_v3 nee_c;                  // radiance it carries per unit of the path's throughput BEFORE this bounce
 };
 
+// emissive colour of triangle `tri` at barycentric weights (w0, w1, w2): sample_material's emissive tap, rt_helpers.wgsl:17-42
+PT_HD pt_v3 emissive_at(const DevScene& s, uint32_t tri, float w0, float w1, float w2) {
+    const TriShade& ts = s.shade[tri];
+    const F4 q0 = ld4(&ts.q[0]), q1 = ld4(&ts.q[1]), q2 = ld4(&ts.q[2]), q3 = ld4(&ts.q[3]);
+    const MatDev* mp = s.mats + f2u(q3.w);
+    if (!(mp->tex_mask & (1u << SLOT_EMISSIVE))) return pt_mk3(mp->emissive[0], mp->emissive[1], mp->emissive[2]);
+    const float u = q0.w * w0 + q2.w * w1 + q3.y * w2;
+    const float v = q1.w * w0 + q3.x * w1 + q3.z * w2;
+    const pt_v4 c = sample_tex(s, mp->tex[SLOT_EMISSIVE], u, v);
+    return pt_mk3(c.x, c.y, c.z);
+}
+
+template <bool MIS>
 PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_o, pt_v3 ray_d, uint32_t rng_in, const HitRec& hit, uint32_t bounce) {
     SurfaceOut out;
     out.first_t = 0.0f; out.first_normal = pt_mk3(0.0f, 0.0f, 0.0f); out.first_albedo = pt_mk3(0.0f, 0.0f, 0.0f);
     out.atten = pt_mk3(0.0f, 0.0f, 0.0f); out.next_o = ray_o; out.next_d = ray_d; out.rng = rng_in;
+    out.light_q = 0.0f; out.pdf_next = -1.0f; out.nee = false; out.nee_d = ray_d; out.nee_tmax = 0.0f; out.nee_c = pt_mk3(0.0f, 0.0f, 0.0f);
+    const bool mis = MIS && cfg.light_sampling == PTC_LIGHTS_MIS && s.num_real_lights != 0;
     const bool miss = hit.tri == 0xFFFFFFFFu;
     pt_v3 n = pt_mk3(0.0f, 0.0f, 0.0f);
     float u = 0.0f, v = 0.0f;
@@ -564,9 +591,39 @@ PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_
         if (pt_dot(dir, n0) > 0.0f) { so = p; sd = dir; atten = m.albedo; sn = n0; }
         else regular = true;                                                // :183-189
     }
-    if (regular) scatter_regular(rng, ray_o, ray_d, hit.t, n, m, so, sd, atten, sn);
+    ScatterAux aux; aux.ns = n; aux.alpha = 1.0f; aux.refracted = true;
+    if (regular) scatter_regular(rng, ray_o, ray_d, hit.t, n, m, so, sd, atten, sn, mis ? &aux : nullptr);
 
-    out.light = m.emissive; out.atten = atten; out.rng = rng;
+    out.light = m.emissive; out.atten = atten;
+    if (mis && hit_light) {                                                 // 1 / p_l of the emitter this BSDF-sampled ray found
+        const uint32_t li = s.light_of_tri[hit.tri];
+        out.light_q = -1.0f;                                                // not in the light list (cannot be light-sampled): weight 1
+        if (li != 0xFFFFFFFFu) {
+            const ptc_triangle& L = s.lights[li];
+            out.light_q = pt_light_inv_pdf(pt_mk3(L.v0[0], L.v0[1], L.v0[2]), pt_mk3(L.v1[0], L.v1[1], L.v1[2]), pt_mk3(L.v2[0], L.v2[1], L.v2[2]),
+                                           ray_d, hit.t * hit.t, (float)s.num_lights);
+        }
+    }
+    if (mis && !hit_light && bounce < cfg.max_bounces && m.transmission == 0.0f) {
+        // one light sample per opaque hit whose path continues (draw order: light index, then the two of helpers.wgsl:7-18)
+        const uint32_t li = rng_next_u32(rng) % s.num_lights;
+        const ptc_triangle& L = s.lights[li];
+        const float r1 = rng_next_f32(rng), r2 = rng_next_f32(rng);
+        const float s1 = pt_sqrt(r1);
+        const float w0 = 1.0f - s1, w1 = s1 * (1.0f - r2), w2 = s1 * r2;
+        const pt_v3 v0 = pt_mk3(L.v0[0], L.v0[1], L.v0[2]), v1 = pt_mk3(L.v1[0], L.v1[1], L.v1[2]), v2 = pt_mk3(L.v2[0], L.v2[1], L.v2[2]);
+        const pt_v3 q = pt_mk3(v0.x * w0 + v1.x * w1 + v2.x * w2, v0.y * w0 + v1.y * w1 + v2.y * w2, v0.z * w0 + v1.z * w1 + v2.z * w2);
+        const pt_v3 to = pt_sub(q, so);
+        const float dist2 = pt_dot(to, to), dist = pt_sqrt(dist2);
+        const pt_v3 dir = pt_scale(to, pt_div(1.0f, dist));
+        const float wgt = pt_mis_weight(pt_ggx_reflect_pdf(aux.ns, pt_neg(ray_d), dir, aux.alpha), pt_light_inv_pdf(v0, v1, v2, dir, dist2, (float)s.num_lights));
+        const pt_v3 le = emissive_at(s, L._pad0, w0, w1, w2);               // _pad0 carries the light's global triangle id (scene_prep)
+        out.nee_c = pt_scale(pt_mul(le, atten), wgt);
+        out.nee_d = dir; out.nee_tmax = dist * 0.999f;
+        out.nee = !aux.refracted && dist > PT_RAY_TMIN && pt_dot(out.nee_c, pt_mk3(1.0f, 1.0f, 1.0f)) > 0.0f;
+    }
+    if (mis && !aux.refracted && m.transmission == 0.0f) out.pdf_next = pt_ggx_reflect_pdf(aux.ns, pt_neg(ray_d), sd, aux.alpha);
+    out.rng = rng;
     if (hit_light) { out.kind = SURF_LIGHT; return out; }                   // :204-206
     if (bounce == 0) {                                                      // :208-223
         out.first_t = hit.t;
@@ -582,9 +639,13 @@ PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_
 
 // The part of the loop body that touches the path's running values (pathtracer/pathtracer.wgsl:200-206, 229-232):
 // returns true when the path continues (mask / acc updated), else `radiance` is ray_color's result.
-PT_HD bool combine_path(const SurfaceOut& so, pt_v3& mask, pt_v3& acc, pt_v3& radiance) {
+// pdf_prev (PTC_LIGHTS_MIS): p_b of the direction that led here, < 0 = weight 1 (camera ray, refraction); an emitter found
+// by BSDF sampling is weighted against the light sample the previous hit took towards it.
+PT_HD bool combine_path(const SurfaceOut& so, pt_v3& mask, pt_v3& acc, pt_v3& radiance, float pdf_prev = -1.0f) {
     if (so.kind == SURF_MISS) { radiance = pt_add(acc, pt_mul(so.light, mask)); return false; }
-    acc = pt_add(acc, pt_mul(so.light, mask));                             // :200
+    pt_v3 le = so.light;
+    if (so.kind == SURF_LIGHT && pdf_prev >= 0.0f && so.light_q >= 0.0f) le = pt_scale(le, pt_mis_weight(pdf_prev, so.light_q));
+    acc = pt_add(acc, pt_mul(le, mask));                                   // :200
     mask = pt_mul(mask, so.atten);                                          // :202
     if (so.kind != SURF_CONTINUE) { radiance = acc; return false; }
     return true;
@@ -592,14 +653,21 @@ PT_HD bool combine_path(const SurfaceOut& so, pt_v3& mask, pt_v3& acc, pt_v3& ra
 
 // whole loop body in one call (host build of the tests)
 PT_HD BounceOut shade_bounce(const DevScene& s, const PathCfg& cfg, const PathState& ps, const HitRec& hit, uint32_t bounce) {
-    const SurfaceOut so = shade_surface(s, cfg, ps.o, ps.d, ps.rng, hit, bounce);
+    const SurfaceOut so = shade_surface<true>(s, cfg, ps.o, ps.d, ps.rng, hit, bounce);
     BounceOut out;
-    out.next = ps;
+    out.next = ps; out.shadow_rays = 0;
     out.radiance = pt_mk3(0.0f, 0.0f, 0.0f);
     out.first_t = so.first_t; out.first_normal = so.first_normal; out.first_albedo = so.first_albedo;
     pt_v3 mask = ps.mask, acc = ps.acc;
-    out.alive = combine_path(so, mask, acc, out.radiance);
-    if (out.alive) { out.next.o = so.next_o; out.next.d = so.next_d; out.next.mask = mask; out.next.acc = acc; out.next.rng = so.rng; }
+    out.alive = combine_path(so, mask, acc, out.radiance, ps.pdf);
+    if (out.alive) {
+        out.next.o = so.next_o; out.next.d = so.next_d; out.next.mask = mask; out.next.acc = acc; out.next.rng = so.rng; out.next.pdf = so.pdf_next;
+        // PTC_LIGHTS_MIS: the shadow ray is resolved here (the wavefront queues it for the any-hit kernel instead)
+        if (so.nee) {
+            out.shadow_rays = 1;
+            if (!trace_any_bvh2(s, so.next_o, so.nee_d, so.nee_tmax)) out.next.acc = pt_add(out.next.acc, pt_mul(so.nee_c, ps.mask));
+        }
+    }
     return out;
 }
 

@@ -106,9 +106,14 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, cons
 #endif
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
+// ANY (PTC_LIGHTS_MIS shadow rays): the same scheduler with an any-hit early-out — ray_d.w is the far end of the
+// segment, the first accepted triangle retires the lane, and a ray that found nothing adds `contrib[ray]` to the
+// accumulated colour of its path (`acc`, indexed by the slot in ray_o.w; at most one shadow ray per slot per launch).
+template <bool ANY>
 __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
                                                           U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
-                                                          uint32_t* cursor, unsigned long long* total_rays) {
+                                                          uint32_t* cursor, unsigned long long* total_rays,
+                                                          const F4* __restrict__ contrib, F4* __restrict__ acc) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     const uint32_t n = *count_ptr;
@@ -127,7 +132,13 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
         if (idle == FULL || (!exhausted && __popc(idle) >= PTC_REFILL_VOTE)) {
             // ---- retire finished rays, refill idle lanes ----
             if (node == PTC_SENTINEL && ray != kNoRay) {
-                reinterpret_cast<uint4*>(hits)[ray] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+                if (!ANY) reinterpret_cast<uint4*>(hits)[ray] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+                else if (best.tri == 0xFFFFFFFFu) {
+                    const F4 c = ld4_stream(contrib + ray);
+                    F4* a = acc + __float_as_uint(best.b1);                // the slot travelled in best.b1
+                    const F4 v = *a;
+                    st4_stream(a, v.x + c.x, v.y + c.y, v.z + c.z, v.w);
+                }
                 ray = kNoRay;
             }
             if (!exhausted) {
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
                     const F4 ro = ld4(ray_o + i), rd = ld4(ray_d + i);
                     o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z);
                     r = make_ray_slab(s, o, d);
-                    best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
+                    best.t = ANY ? rd.w : PT_RAY_TMAX; best.b1 = ANY ? ro.w : 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
                     stack[0] = PTC_SENTINEL; sp = 1;
                     tri_i = tri_end = 0;
                     if (s.num_nodes != 0 && ray_is_finite(o, d)) node = 0;
@@ -161,11 +172,12 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
                     const F4* tp = s.tris + (size_t)tri_i * 4;
                     F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
                     float t, b1, b2;
-                    if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                    if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, ANY ? best.t : PT_RAY_TMAX, &t, &b1, &b2)) {
                         const uint32_t id = f2u(a.w);
-                        if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+                        if (ANY) { best.tri = id; node = PTC_SENTINEL; tri_i = tri_end = 0; }        // occluded: done
+                        else if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
                     }
-                    if (++tri_i == tri_end) node = stack[--sp];
+                    if ((!ANY || node < 0) && ++tri_i == tri_end) node = stack[--sp];
                 }
                 if (PTC_TRI_INNER == 0 || __popc(__ballot_sync(FULL, node < 0)) < PTC_TRI_INNER) break;
             }
@@ -210,9 +222,12 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_any(DevScene s, const F
 // FIRST (segment 0): throughput and accumulated colour are the constants (1,1,1) / (0,0,0) of ray_color's entry
 // (pathtracer/pathtracer.wgsl:155-156), so raygen does not write those queue entries and this kernel does not read them;
 // it also carries the first-hit aux outputs, which later segments do not.
-template <bool FIRST>
+// MIS (PTC_LIGHTS_MIS, a separate instantiation so the reference path keeps its register budget): the hit also takes a
+// light sample; its shadow ray is queued (second ballot compaction) for k_trace<true>, which adds the carried radiance to
+// this path's slot of the next queue before the next shade reads it.  mask.w carries p_b of the scattered direction.
+template <bool FIRST, bool MIS>
 __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(DevScene s, PathCfg cfg, Queue qin, Queue qout, const U4* __restrict__ hits,
-                                                          FrameCounters* fc, uint32_t segment, Planes planes) {
+                                                          FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh) {
     const uint32_t n = fc->count[segment];
     uint32_t* next_count = &fc->count[segment + 1];
     const uint32_t lane = threadIdx.x & 31;
@@ -222,6 +237,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
         bool alive = false;
         uint32_t pixel = 0, rng = 0;
         pt_v3 no = pt_mk3(0.0f, 0.0f, 0.0f), nd = no, mask = pt_mk3(1.0f, 1.0f, 1.0f), acc = no;
+        bool nee = false; pt_v3 nee_d = no, nee_c = no; float nee_tmax = 0.0f, pdf_next = -1.0f;
         if (i < n) {
             SurfaceOut so;
             {
@@ -229,7 +245,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 const uint4 hr = __ldcs(reinterpret_cast<const uint4*>(hits) + i);
                 pixel = __float_as_uint(o.w);
                 HitRec h; h.t = __uint_as_float(hr.x); h.b1 = __uint_as_float(hr.y); h.b2 = __uint_as_float(hr.z); h.tri = hr.w;
-                so = shade_surface(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
+                so = shade_surface<MIS>(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
                 if (FIRST) {                                          // pathtracer/pathtracer.wgsl:270-273
                     planes.depth[pixel] = so.first_t;
                     reinterpret_cast<float4*>(planes.normal)[pixel] = make_float4(so.first_normal.x, so.first_normal.y, so.first_normal.z, 1.0f);
@@ -237,13 +253,16 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                     planes.hit_tri[pixel] = h.tri;
                 }
             }
+            float pdf_prev = -1.0f;
             if (!FIRST) {
                 asm volatile("" ::: "memory");                        // keep these two loads AFTER the BSDF code (register pressure)
                 const F4 m = ld4_stream(qin.mask + i), a = ld4_stream(qin.acc + i);
                 mask = pt_mk3(m.x, m.y, m.z); acc = pt_mk3(a.x, a.y, a.z);
+                if (MIS) pdf_prev = m.w;
             }
+            if (MIS) { nee = so.nee; nee_d = so.nee_d; nee_tmax = so.nee_tmax; nee_c = pt_mul(so.nee_c, mask); pdf_next = so.pdf_next; }
             pt_v3 radiance;
-            alive = combine_path(so, mask, acc, radiance);
+            alive = combine_path(so, mask, acc, radiance, pdf_prev);
             no = so.next_o; nd = so.next_d; rng = so.rng;
             if (!alive) accumulate_pixel(planes.color + pixel, radiance, cfg.accum_mode, cfg.is_grabbed);   // pathtracer.wgsl:32-42
         }
@@ -257,8 +276,23 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
                 st4_stream(qout.ray_o + slot, no.x, no.y, no.z, __uint_as_float(pixel));
                 st4_stream(qout.ray_d + slot, nd.x, nd.y, nd.z, __uint_as_float(rng));
-                st4_stream(qout.mask + slot, mask.x, mask.y, mask.z, 0.0f);
+                st4_stream(qout.mask + slot, mask.x, mask.y, mask.z, MIS ? pdf_next : 0.0f);
                 st4_stream(qout.acc + slot, acc.x, acc.y, acc.z, 0.0f);
+                if (MIS) pixel = slot;                                    // the shadow entry names the path by its slot
+            }
+        }
+        if (MIS) {
+            const uint32_t sb = __ballot_sync(0xffffffffu, alive && nee);
+            if (sb) {
+                uint32_t k0 = 0;
+                if (lane == 0) k0 = atomicAdd(&fc->shadow_count[segment], (uint32_t)__popc(sb));
+                k0 = __shfl_sync(0xffffffffu, k0, 0);
+                if (alive && nee) {
+                    const uint32_t k = k0 + __popc(sb & ((1u << lane) - 1u));
+                    st4_stream(sh.ray_o + k, no.x, no.y, no.z, __uint_as_float(pixel));
+                    st4_stream(sh.ray_d + k, nee_d.x, nee_d.y, nee_d.z, nee_tmax);
+                    st4_stream(sh.contrib + k, nee_c.x, nee_c.y, nee_c.z, 0.0f);
+                }
             }
         }
     }
@@ -270,13 +304,24 @@ void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounte
 }
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays) {
-    if (impl == 0) k_trace<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
+    if (impl == 0) k_trace<false><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
-                  FrameCounters* fc, uint32_t segment, Planes planes) {
-    if (segment == 0) k_shade<true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes);
-    else k_shade<false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes);
+                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh) {
+    const bool mis = cfg.light_sampling == PTC_LIGHTS_MIS && s.num_real_lights != 0;
+    if (!mis) {
+        if (segment == 0) k_shade<true, false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
+        else k_shade<false, false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
+    } else {
+        if (segment == 0) k_shade<true, true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
+        else k_shade<false, true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
+    }
+}
+void launch_trace_shadow(cudaStream_t st, int grid, const DevScene& s, ShadowQueue sh, F4* acc_next, FrameCounters* fc, uint32_t segment,
+                         unsigned long long* total_rays) {
+    k_trace<true><<<grid, kTraceThreads, 0, st>>>(s, sh.ray_o, sh.ray_d, nullptr, &fc->shadow_count[segment], &fc->shadow_cursor[segment], total_rays,
+                                                  sh.contrib, acc_next);
 }
 
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
@@ -284,7 +329,7 @@ __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor) {
     // cursor[0] = work cursor (zeroed by caller), cursor[1] = count
     k_set_u32<<<1, 1, 0, st>>>(cursor + 1, n);
-    if (impl == 0) k_trace<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
+    if (impl == 0) k_trace<false><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
 }
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor) {
@@ -380,7 +425,7 @@ static int persistent_grid(const void* kernel, int threads, int device) {
     if (sms < 1) sms = 1;
     return sms * per_sm;          // a multiple of the SM count (148 on B200): every SM holds its full share of resident CTAs
 }
-int trace_grid_size(int device, int impl) { return persistent_grid(impl == 0 ? (const void*)k_trace : (const void*)k_trace_simple, kTraceThreads, device); }
-int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false>, kShadeThreads, device); }
+int trace_grid_size(int device, int impl) { return persistent_grid(impl == 0 ? (const void*)k_trace<false> : (const void*)k_trace_simple, kTraceThreads, device); }
+int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false, false>, kShadeThreads, device); }
 
 }  // namespace ptc

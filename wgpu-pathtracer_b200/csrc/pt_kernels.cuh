@@ -21,6 +21,14 @@ struct FrameCounters {
     uint32_t count[PTC_MAX_SEGMENTS + 1];   // count[b] = rays alive entering segment b
     uint32_t trace_cursor[PTC_MAX_SEGMENTS];
     uint32_t shade_cursor[PTC_MAX_SEGMENTS];
+    uint32_t shadow_count[PTC_MAX_SEGMENTS];   // PTC_LIGHTS_MIS: shadow rays queued by shade(b)
+    uint32_t shadow_cursor[PTC_MAX_SEGMENTS];
+};
+
+struct ShadowQueue {      // PTC_LIGHTS_MIS: one entry per light sample awaiting its visibility test
+    F4* ray_o;            // origin.xyz, slot of the path in the NEXT path queue (bits)
+    F4* ray_d;            // direction.xyz, far end of the segment
+    F4* contrib;          // radiance to add to that path's accumulated colour when nothing blocks the segment
 };
 
 struct Queue {            // SoA path state, one slot per live path
@@ -42,7 +50,10 @@ void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounte
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays);
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
-                  FrameCounters* fc, uint32_t segment, Planes planes);
+                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh);
+// PTC_LIGHTS_MIS: any-hit traversal of the shadow rays shade(segment) queued; unoccluded ones add into acc_next
+void launch_trace_shadow(cudaStream_t st, int grid, const DevScene& s, ShadowQueue sh, F4* acc_next, FrameCounters* fc, uint32_t segment,
+                         unsigned long long* total_rays);
 // standalone traversal of caller rays (tests/tools)
 void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor);
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor);

@@ -49,6 +49,8 @@ struct ptc_step {
     // scene (device)
     F4* d_nodes = nullptr; F4* d_tris = nullptr; TriShade* d_shade = nullptr;
     MatDev* d_mats = nullptr; TexDev* d_texs = nullptr; ptc_triangle* d_lights = nullptr;
+    uint32_t* d_light_of_tri = nullptr;            // PTC_LIGHTS_MIS only
+    ShadowQueue shq{};                             // PTC_LIGHTS_MIS only
     std::vector<cudaArray_t> pages; std::vector<cudaTextureObject_t> page_objs;   // texture atlas pages
     uint32_t num_textures = 0; uint64_t atlas_bytes = 0;
     DevScene scene{};
@@ -147,6 +149,7 @@ static void free_frame_buffers(ptc_step* s) {
         s->q[i] = Queue{};
     }
     cudaFree(s->d_hits); s->d_hits = nullptr;
+    cudaFree(s->shq.ray_o); cudaFree(s->shq.ray_d); cudaFree(s->shq.contrib); s->shq = ShadowQueue{};
     cudaFree(s->qp.ray_o); cudaFree(s->qp.ray_d); s->qp = Queue{}; cudaFree(s->d_hits_p); s->d_hits_p = nullptr;
     cudaFree(s->owned_color); s->owned_color = nullptr;
     cudaFree(s->planes.depth); cudaFree(s->planes.normal); cudaFree(s->planes.albedo); cudaFree(s->planes.hit_tri);
@@ -164,6 +167,9 @@ static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
         CK(cudaMalloc(&s->q[i].mask, (size_t)n * 16)); CK(cudaMalloc(&s->q[i].acc, (size_t)n * 16));
     }
     CK(cudaMalloc(&s->d_hits, (size_t)n * 16));
+    if (s->cfg.light_sampling == PTC_LIGHTS_MIS) {
+        CK(cudaMalloc(&s->shq.ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->shq.ray_d, (size_t)n * 16)); CK(cudaMalloc(&s->shq.contrib, (size_t)n * 16));
+    }
     CK(cudaMalloc(&s->qp.ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->qp.ray_d, (size_t)n * 16)); CK(cudaMalloc(&s->d_hits_p, (size_t)n * 16));
     CK(cudaMalloc(&s->owned_color, (size_t)n * 16));
     CK(cudaMalloc(&s->planes.depth, (size_t)n * 4));
@@ -282,10 +288,15 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
     s->num_lights = (uint32_t)ps.lights.size();
     CK(cudaMalloc(&s->d_lights, ps.lights.size() * sizeof(ptc_triangle)));
     CK(cudaMemcpy(s->d_lights, ps.lights.data(), ps.lights.size() * sizeof(ptc_triangle), cudaMemcpyHostToDevice));
+    if (s->cfg.light_sampling == PTC_LIGHTS_MIS && !ps.light_of_tri.empty()) {
+        CK(cudaMalloc(&s->d_light_of_tri, ps.light_of_tri.size() * 4));
+        CK(cudaMemcpy(s->d_light_of_tri, ps.light_of_tri.data(), ps.light_of_tri.size() * 4, cudaMemcpyHostToDevice));
+    }
 
     DevScene& ds = s->scene;
     ds.nodes = reinterpret_cast<const NodeQ*>(s->d_nodes); ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
     ds.num_nodes = (uint32_t)dev.nodes.size(); ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
+    ds.light_of_tri = s->d_light_of_tri; ds.num_real_lights = s->d_light_of_tri ? ps.num_real_lights : 0;
     ds.num_pages = (uint32_t)s->page_objs.size();
     for (int a = 0; a < 3; ++a) { ds.grid_base[a] = dev.grid.base[a]; ds.grid_extent[a] = dev.grid.extent[a]; }
     for (size_t p = 0; p < s->page_objs.size(); ++p) ds.page_obj[p] = (unsigned long long)s->page_objs[p];
@@ -301,7 +312,7 @@ static void destroy_step(ptc_step* s) {
     free_frame_buffers(s);
     for (auto o : s->page_objs) if (o) cudaDestroyTextureObject(o);
     for (auto a : s->pages) if (a) cudaFreeArray(a);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_shade); cudaFree(s->d_mats); cudaFree(s->d_texs); cudaFree(s->d_lights);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_shade); cudaFree(s->d_mats); cudaFree(s->d_texs); cudaFree(s->d_lights); cudaFree(s->d_light_of_tri);
     cudaFree(s->d_fc); cudaFree(s->d_total_rays);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->snap_ready) cudaEventDestroy(s->snap_ready);
@@ -328,6 +339,8 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     if (config->samples_per_pixel != 1) { set_error("samples_per_pixel must be 1 (SAMPLES_PER_PIXEL, shader_definitions.rs:17); call ptc_render once per sample"); return PTC_ERR_INVALID; }
     if (config->max_bounces + 1 > PTC_MAX_SEGMENTS) { set_error("max_bounces too large"); return PTC_ERR_INVALID; }
     if (config->accum_mode > PTC_ACCUM_SUM) { set_error("bad accum_mode"); return PTC_ERR_INVALID; }
+    if (config->light_sampling > PTC_LIGHTS_MIS) { set_error("bad light_sampling"); return PTC_ERR_INVALID; }
+    if (config->light_sampling == PTC_LIGHTS_MIS && config->send_to_light_probability != 0.0f) { set_error("PTC_LIGHTS_MIS requires send_to_light_probability == 0"); return PTC_ERR_INVALID; }
     int ndev = ptc_device_count();
     if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
     if (cuda_device < 0 || cuda_device >= ndev) { set_error("cuda_device out of range"); return PTC_ERR_INVALID; }
@@ -376,6 +389,8 @@ PTC_API int ptc_render(ptc_step* s) {
     FrameCounters* fc = s->d_fc + (s->fc_next++ % kFcRing);
     PathCfg pc; pc.width = s->cfg.width; pc.height = s->cfg.height; pc.max_bounces = s->cfg.max_bounces;
     pc.send_to_light_probability = s->cfg.send_to_light_probability; pc.accum_mode = s->cfg.accum_mode; pc.is_grabbed = s->uniforms.is_grabbed;
+    pc.light_sampling = s->cfg.light_sampling;
+    const bool mis = pc.light_sampling == PTC_LIGHTS_MIS && s->scene.num_real_lights != 0;
     if (s->profiling && s->ev_used > 60000) prof_collect(s);
     // segment 0: raygen + traversal of the primary rays.  Prefetched on the low-priority stream unless stage timing is on
     // (profiling keeps every launch on one stream so the per-stage times are exclusive).
@@ -389,15 +404,18 @@ PTC_API int ptc_render(ptc_step* s) {
     launch_trace(st0, s->trace_grid, s->trace_impl, s->scene, s->qp, s->d_hits_p, fc, 0, s->d_total_rays);
     if (prefetch) { CK(cudaEventRecord(s->primary_done, st0)); CK(cudaStreamWaitEvent(s->stream, s->primary_done, 0)); }
     prof_mark(s, 2);
-    launch_shade(s->stream, s->shade_grid, s->scene, pc, s->qp, s->q[1], s->d_hits_p, fc, 0, s->planes);
+    launch_shade(s->stream, s->shade_grid, s->scene, pc, s->qp, s->q[1], s->d_hits_p, fc, 0, s->planes, s->shq);
     if (s->overlap) CK(cudaEventRecord(s->primary_free, s->stream));
     s->launches += 3;
+    // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
+    if (mis && s->cfg.max_bounces >= 1) { prof_mark(s, 1); launch_trace_shadow(s->stream, s->trace_grid, s->scene, s->shq, s->q[1].acc, fc, 0, s->d_total_rays); s->launches++; }
     for (uint32_t seg = 1; seg <= s->cfg.max_bounces; ++seg) {
         prof_mark(s, 1);
         launch_trace(s->stream, s->trace_grid, s->trace_impl, s->scene, s->q[seg & 1], s->d_hits, fc, seg, s->d_total_rays);
         prof_mark(s, 2);
-        launch_shade(s->stream, s->shade_grid, s->scene, pc, s->q[seg & 1], s->q[(seg + 1) & 1], s->d_hits, fc, seg, s->planes);
+        launch_shade(s->stream, s->shade_grid, s->scene, pc, s->q[seg & 1], s->q[(seg + 1) & 1], s->d_hits, fc, seg, s->planes, s->shq);
         s->launches += 2;
+        if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(s->stream, s->trace_grid, s->scene, s->shq, s->q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
     }
     prof_mark(s, -1);
     CK(cudaGetLastError());

@@ -94,6 +94,7 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
 
     // emissive triangle list (pt.rs:206-243): a triangle is a light iff its material's emissive texture index != 4
     out.lights.clear();
+    out.light_of_tri.assign(ntri, 0xFFFFFFFFu);
     for (uint32_t t = 0; t < ntri; ++t) {
         uint32_t mat = v->meshes[out.tri_mesh[t]].material_index;
         if (v->materials[mat].emissive_texture_idx == 4) continue;
@@ -101,8 +102,11 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
         const uint32_t* ix = &v->indices[(size_t)t * 3];
         std::memcpy(L.v0, v->vertices[ix[0]].position, 12); std::memcpy(L.v1, v->vertices[ix[1]].position, 12);
         std::memcpy(L.v2, v->vertices[ix[2]].position, 12); std::memcpy(L.normal, v->vertices[ix[0]].normal, 12);
+        L._pad0 = t;
+        out.light_of_tri[t] = (uint32_t)out.lights.size();
         out.lights.push_back(L);
     }
+    out.num_real_lights = (uint32_t)out.lights.size();
     if (out.lights.empty()) { ptc_triangle z; std::memset(&z, 0, sizeof(z)); out.lights.push_back(z); }   // pt.rs:232-239
     return PTC_OK;
 }

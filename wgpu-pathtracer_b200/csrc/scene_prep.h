@@ -17,7 +17,9 @@ struct PreparedScene {
     DevBvh2 bvh;                          // device-layout nodes + leaf-ordered triangles
     std::vector<TriShade> shade;          // global triangle order
     std::vector<MatDev> mats;
-    std::vector<ptc_triangle> lights;     // never empty (dummy entry, pt.rs:232-239)
+    std::vector<ptc_triangle> lights;     // never empty (dummy entry, pt.rs:232-239); _pad0 = the light's global triangle id
+    std::vector<uint32_t> light_of_tri;   // global triangle -> index into lights (0xFFFFFFFF: not emissive)
+    uint32_t num_real_lights = 0;         // 0 when lights holds only the dummy entry
     std::vector<uint32_t> tri_mesh;       // global triangle -> mesh (instance_index)
     std::vector<ptc_mesh> meshes;
     uint32_t num_tris = 0;

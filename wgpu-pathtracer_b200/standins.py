@@ -413,6 +413,49 @@ def furnace(env=None, ke=(0.75, 0.5, 0.25)):
     return sc, {"position": (0.0, 0.0, 0.0), "fov": 60.0, "target": (1.0, 0.0, 0.0)}
 
 
+LIT_ROOM_MTL = """newmtl wall
+Kd 0.75 0.75 0.75
+Pr 0.9
+
+newmtl red
+Kd 0.8 0.15 0.1
+Pr 0.7
+
+newmtl green
+Kd 0.15 0.7 0.2
+Pr 0.5
+
+newmtl lamp
+Kd 0.8 0.8 0.8
+Ke 24 22 18
+
+newmtl glow
+Kd 0.5 0.5 0.5
+Ke 2 3 5
+"""
+
+
+def lit_room(env=None):
+    """Light-sampling fixture: a CLOSED room under a black sky, lit only by a small ceiling lamp and a dim glowing
+    block; a box casts a shadow.  Whatever reaches the image came from an emissive triangle, so the two estimators
+    (BSDF sampling alone / PTC_LIGHTS_MIS) can be compared on their converged means."""
+    black = np.zeros((16, 32, 4), dtype=F); black[..., 3] = 1.0
+    sc = Scene(env or Texture(black))
+    parts = [
+        ("floor", "wall", grid((0, 0, -1), (0, 0, 2), (2, 0, 0), 2, 2)),
+        ("ceiling", "wall", grid((0, 2, -1), (2, 0, 0), (0, 0, 2), 2, 2)),
+        ("back", "wall", grid((2, 0, -1), (0, 2, 0), (0, 0, 2), 2, 2)),
+        ("front", "wall", grid((0, 0, -1), (0, 0, 2), (0, 2, 0), 2, 2)),
+        ("left", "red", grid((0, 0, -1), (2, 0, 0), (0, 2, 0), 2, 2)),
+        ("right", "green", grid((0, 0, 1), (0, 2, 0), (2, 0, 0), 2, 2)),
+        ("blocker", "wall", transform(box((-0.3, 0, -0.3), (0.3, 0.9, 0.3)), rot_y=0.4, translate=(1.2, 0, 0.2))),
+        ("lamp", "lamp", grid((0.9, 1.99, -0.2), (0.4, 0, 0), (0, 0, 0.4), 1, 1)),
+        ("glow", "glow", transform(box((-0.1, 0, -0.1), (0.1, 0.2, 0.1)), translate=(0.6, 0.0, -0.6))),
+    ]
+    sc.load_obj(obj_text=_obj_text(parts), mtl_text=LIT_ROOM_MTL, obj_dir="standin")
+    return sc, {"position": (0.15, 1.0, 0.0), "fov": 70.0, "target": (1.5, 0.8, 0.0)}
+
+
 def empty(env=None):
     """No geometry: every pixel equals the sky lookup of its primary direction."""
     return Scene(env or make_envmap(256, 128)), {"position": (0.0, 0.0, 0.0), "fov": 60.0, "target": (1.0, 0.0, 0.0)}
@@ -625,7 +668,7 @@ def san_miguel(env=None, n_plants=2000, leaves_per_plant=2500, tex_size=256):
     return sc, cam
 
 
-BUILDERS = {"cornell": cornell, "dragon": dragon, "sponza": sponza, "furnace": furnace, "empty": empty,
+BUILDERS = {"cornell": cornell, "dragon": dragon, "sponza": sponza, "furnace": furnace, "empty": empty, "lit_room": lit_room,
             "classroom": classroom, "san_miguel": san_miguel}
 
 
