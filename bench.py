@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--workload", default="sponza_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh-build", default="sah", choices=["sah", "lbvh"], help="sah: binned SAH on the host (default); lbvh: linear BVH built by CUDA kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,8 +201,11 @@ def main():
     T = pkg.types
     W, H, K, Wm = w["width"], w["height"], args.steps, max(args.warmup, 3)
     accum = T.ACCUM_SUM if world > 1 else T.ACCUM_MEAN
-    cfg = pkg.make_config(W, H, max_bounces=w["max_bounces"], accum_mode=accum, light_sampling=w.get("light_sampling", 0))
+    cfg = pkg.make_config(W, H, max_bounces=w["max_bounces"], accum_mode=accum, light_sampling=w.get("light_sampling", 0),
+                          bvh_build=T.BVH_LBVH_DEVICE if args.bvh_build == "lbvh" else T.BVH_SAH_HOST)
+    t_create = time.perf_counter()
     step = pkg.RTStep.create(scene, cfg, device=local)
+    t_create = time.perf_counter() - t_create
     out = torch.zeros(H, W, 4, device=f"cuda:{local}", dtype=torch.float32)
     step.set_output(out.data_ptr())                       # the caller injects the accumulation target (raytracer.rs:86)
     ext = torch.cuda.ExternalStream(step.stream, device=local)
@@ -324,6 +328,8 @@ def main():
         "spp_per_s": K * world / (ms * 1e-3),
         "config": {"workload": f"{w['scene']} stand-in {W}x{H}, MAX_BOUNCES={w['max_bounces']}, 1 spp per step, {bvh['triangles']} triangles"
                                + (", PTC_LIGHTS_MIS (non-reference mode: one any-hit shadow ray per opaque hit, counted as a ray)" if w.get("light_sampling") else ""),
+                   "bvh": {"build": "lbvh (CUDA kernels)" if bvh["built_on_device"] else "binned SAH (host threads)", "build_ms": bvh["build_us"] / 1e3,
+                           "nodes": bvh["nodes"], "max_depth": bvh["max_depth"], "ptc_create_s": t_create},
                    "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: each frame streams ~%.0f MB of path-state queues; the %.1f MB BVH is L2-resident by design" % (
                        W * H * 144 / 1e6, (bvh["node_bytes"] + bvh["triangle_bytes"]) / 1e6)},

@@ -116,8 +116,12 @@ PTC_API int ptc_get_profile(ptc_step* step, double ms[3], uint64_t launches[3]);
 PTC_API int ptc_num_lights(ptc_step* step, uint32_t* out);
 
 /* BVH facts for reports: out[0]=nodes, out[1]=triangles, out[2]=node bytes,
- * out[3]=triangle bytes, out[4]=max depth, out[5]=build milliseconds */
+ * out[3]=triangle bytes, out[4]=max depth, out[5]=build milliseconds, out[6]=1 when built by CUDA kernels
+ * (ptc_config.bvh_build = PTC_BVH_LBVH_DEVICE), out[7]=build microseconds */
 PTC_API int ptc_bvh_info(ptc_step* step, uint64_t out[8]);
+/* FNV-1a hashes of the device-resident node array (out[0]) and leaf-ordered triangle array (out[1]), read back from
+ * the GPU (unit-test entry: the device-built tree must equal the host restatement of the same build word for word). */
+PTC_API int ptc_debug_bvh_hash(ptc_step* step, uint64_t out[2]);
 
 /* trace caller-supplied rays (closest hit) — unit-test / tooling entry point
  * for the traversal kernel.  rays: n x 8 floats (ox,oy,oz,_,dx,dy,dz,_) host

@@ -133,6 +133,13 @@ enum ptc_light_sampling {
     PTC_LIGHTS_MIS       = 1
 };
 
+/* Who builds the acceleration structure (the reference leaves it to the Vulkan driver, pt.rs:364-468).  Images do not
+ * depend on the choice: hit identity is defined on triangles, never on the tree. */
+enum ptc_bvh_build {
+    PTC_BVH_SAH_HOST    = 0,  /* binned SAH on the host cores: best trees, seconds for 10 M triangles (default) */
+    PTC_BVH_LBVH_DEVICE = 1   /* Morton-order linear BVH built by CUDA kernels: milliseconds, slower to trace */
+};
+
 /* compat flags */
 #define PTC_COMPAT_NONE 0u
 
@@ -149,7 +156,8 @@ typedef struct ptc_config {
     uint32_t compat_flags;
     uint32_t bvh_width;                /* 0 = library default; 2 = BVH2 */
     uint32_t light_sampling;           /* enum ptc_light_sampling; PTC_LIGHTS_MIS requires send_to_light_probability == 0 */
-    uint32_t reserved[6];
+    uint32_t bvh_build;                /* enum ptc_bvh_build */
+    uint32_t reserved[5];
 } ptc_config;
 
 /* Planes readable from a step. */

@@ -53,6 +53,7 @@ class HostEmu:
         L.emu_trace_rays.restype, L.emu_trace_rays.argtypes = i32, [vp, vp, u64, vp, vp]
         L.emu_trace_rays_any.restype, L.emu_trace_rays_any.argtypes = i32, [vp, vp, u64, vp]
         L.emu_bvh_info.restype, L.emu_bvh_info.argtypes = None, [vp, C.POINTER(u64)]
+        L.emu_bvh_hash.restype, L.emu_bvh_hash.argtypes = None, [vp, C.POINTER(u64)]
         L.emu_rayproject.restype, L.emu_rayproject.argtypes = None, [C.POINTER(T.Uniforms), C.POINTER(T.Uniforms), vp, vp]
         L.emu_blit.restype, L.emu_blit.argtypes = None, [vp, u64, vp]
         self.L = L
@@ -111,6 +112,11 @@ class HostEmuScene:
         a = (C.c_uint64 * 4)()
         self.L.emu_bvh_info(self._h, a)
         return {"nodes": a[0], "triangles": a[1], "max_depth": a[2], "build_ms": a[3]}
+
+    def bvh_hash(self):
+        a = (C.c_uint64 * 2)()
+        self.L.emu_bvh_hash(self._h, a)
+        return a[0], a[1]
 
     def __del__(self):
         try:

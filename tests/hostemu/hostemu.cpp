@@ -73,6 +73,15 @@ void emu_path_cfg(const void* ev, const ptc_uniforms* un_in, PathCfg* pc, ptc_un
 __attribute__((visibility("default")))
 void emu_destroy(emu_scene* e) { delete e; }
 
+// FNV-1a of the host-built node / triangle arrays (compared with ptc_debug_bvh_hash of the device-built tree)
+__attribute__((visibility("default")))
+void emu_bvh_hash(const emu_scene* e, uint64_t out[2]) {
+    auto fnv = [](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; uint64_t h = 1469598103934665603ull;
+                                             for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } return h; };
+    out[0] = fnv(e->ps.bvh.nodes.data(), e->ps.bvh.nodes.size() * sizeof(DevNode2));
+    out[1] = fnv(e->ps.bvh.tris.data(), e->ps.bvh.tris.size() * sizeof(DevTri));
+}
+
 __attribute__((visibility("default")))
 void emu_bvh_info(const emu_scene* e, uint64_t out[4]) {
     out[0] = e->ps.bvh.nodes.size(); out[1] = e->ps.bvh.tris.size(); out[2] = e->ps.max_depth; out[3] = (uint64_t)e->ps.build_ms;

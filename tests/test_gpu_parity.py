@@ -357,6 +357,22 @@ def test_san_miguel_4k_c5(ptc, standins, oracle):
     scene, cam = standins.san_miguel()
     assert scene.num_triangles > 10_000_000
     band_parity(ptc, standins, oracle, scene, cam, 3840, 2160, 1, (1200, 1208))
+    # scene ingest at scale: the same 10.7 M triangles through the device LBVH build — a different tree, the
+    # same image, bit for bit, over the whole 4K frame
+    T = ptc.types
+    W, H = 3840, 2160
+    u = standins.make_camera(cam, W, H).uniforms(frame=1)
+    planes = []
+    for build in (T.BVH_SAH_HOST, T.BVH_LBVH_DEVICE):
+        step = ptc.RTStep.create(scene, ptc.make_config(W, H, bvh_build=build))
+        info = step.bvh_info()
+        print("san_miguel bvh_build", build, info)
+        assert info["built_on_device"] == (build == T.BVH_LBVH_DEVICE) and info["max_depth"] < 64
+        step.update(u); step.render(); step.poll(True)
+        planes.append((step.read(T.PLANE_COLOR), step.read(T.PLANE_HIT_ID), step.read(T.PLANE_DEPTH)))
+        step.destroy()
+    for a, b in zip(*planes):
+        assert np.array_equal(a, b, equal_nan=True)
 
 
 @pytest.mark.parametrize("which", ["lit_room", "soup", "classroom"])
@@ -394,3 +410,35 @@ def test_light_sampling_mis_rejects_reference_light_branch(ptc, standins):
     cfg = ptc.make_config(16, 16, light_sampling=ptc.types.LIGHTS_MIS, send_to_light_probability=0.5)
     with pytest.raises(Exception):
         ptc.RTStep.create(scene, cfg)
+
+
+@pytest.mark.parametrize("which", ["soup", "sponza", "cornell", "coincident"])
+def test_linear_bvh_device_build(ptc, standins, oracle, hostemu, which):
+    """PTC_BVH_LBVH_DEVICE: the tree built by CUDA kernels (Morton keys, CUB radix sort, Karras radix tree,
+    atomic bottom-up fit, collapse, quantised emit) equals the host restatement of the same build WORD FOR WORD (FNV hash
+    of node and triangle arrays), and renders the same image as the oracle, which uses its own SAH tree."""
+    from conftest import random_rays
+    T = ptc.types
+    if which == "soup":
+        scene, cam = standins.random_soup(20000, seed=5, textured=True)
+    elif which == "sponza":
+        scene, cam = standins.sponza(tex_size=64)
+    elif which == "cornell":
+        scene, cam = standins.cornell()
+    else:
+        scene, cam = standins.cornell()
+        tri = np.array([[1.0, 0.5, -0.3], [1.0, 1.2, 0.0], [1.0, 0.5, 0.3]], np.float32)
+        for _ in range(6):
+            scene.add_mesh(np.tile(tri, (100, 1)), np.tile([-1, 0, 0], (300, 1)), None, np.arange(300), 1)
+    step, ref = render_both(ptc, standins, oracle, scene, cam, 320, 200, 2, max_bounces=5, bvh_build=T.BVH_LBVH_DEVICE)
+    info = step.bvh_info()
+    assert info["built_on_device"] and info["max_depth"] < 64
+    emu = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_LBVH_DEVICE))
+    assert emu.bvh_info()["nodes"] == info["nodes"] and emu.bvh_info()["max_depth"] == info["max_depth"]
+    assert step.bvh_hash() == emu.bvh_hash(), "device-built BVH differs from the host restatement"
+    check_all_planes(ptc, step, ref)
+    rays = random_rays(50000, 13)
+    hits, ids = step.trace_rays(rays)
+    rh, rids, _ = oracle.OracleScene(scene, ptc.make_config(8, 8)).trace_rays(rays)
+    assert np.array_equal(hits, rh) and np.array_equal(ids, rids)
+    step.destroy()

@@ -143,3 +143,25 @@ def test_light_sampling_mis_mode(ptc, standins, oracle, hostemu, which):
     r0, _ = both(ptc, standins, oracle, hostemu, scene, cam, 120, 80, 3, max_bounces=5)
     assert ro["rays"] > r0["rays"]                                              # shadow rays were traced
     assert np.array_equal(ro["hit_id"], r0["hit_id"])                           # primary visibility is untouched
+
+
+@pytest.mark.parametrize("which", ["soup", "sponza", "cornell", "coincident"])
+def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which):
+    """PTC_BVH_LBVH_DEVICE, host restatement of the device build: a different tree, the same hits —
+    every plane bit-identical to the oracle, which uses its own SAH tree."""
+    if which == "soup":
+        scene, cam = standins.random_soup(5000, seed=7, textured=True)
+    elif which == "sponza":
+        scene, cam = standins.sponza(tex_size=32)
+    elif which == "cornell":
+        scene, cam = standins.cornell()
+    else:
+        # 600 coincident triangles (identical Morton keys: the tree falls back to index order) in front of a wall
+        scene, cam = standins.cornell()
+        tri = np.array([[1.0, 0.5, -0.3], [1.0, 1.2, 0.0], [1.0, 0.5, 0.3]], np.float32)
+        for _ in range(6):
+            scene.add_mesh(np.tile(tri, (100, 1)), np.tile([-1, 0, 0], (300, 1)), None, np.arange(300), 1)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 160, 100, 2, max_bounces=5, bvh_build=ptc.types.BVH_LBVH_DEVICE)
+    assert_identical(ro, re)
+    info = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=ptc.types.BVH_LBVH_DEVICE)).bvh_info()
+    assert info["max_depth"] < 64 and info["triangles"] == len(scene.indices) // 3

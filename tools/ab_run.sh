@@ -7,7 +7,7 @@ for spec in "$@"; do
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('Mrays/s %.1f  e2e %.1f  ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']), {k: round(v,2) for k,v in d['roofline']['stage_ms'].items()})
+        d=json.loads(l); print(d['config'].get('bvh')); print('Mrays/s %.1f  e2e %.1f  ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']), {k: round(v,2) for k,v in d['roofline']['stage_ms'].items()})
     else: print(l.rstrip())
 "
 done

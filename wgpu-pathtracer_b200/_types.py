@@ -30,7 +30,7 @@ class SceneView(C.Structure):
 class Config(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("max_bounces", u32), ("samples_per_pixel", u32),
                 ("send_to_light_probability", f32), ("env_texture_index", u32), ("accum_mode", u32),
-                ("compat_flags", u32), ("bvh_width", u32), ("light_sampling", u32), ("reserved", u32 * 6)]
+                ("compat_flags", u32), ("bvh_width", u32), ("light_sampling", u32), ("bvh_build", u32), ("reserved", u32 * 5)]
 
 
 class Stats(C.Structure):
@@ -64,6 +64,7 @@ assert VERTEX_DT.itemsize == 48 and MESH_DT.itemsize == 20 and MATERIAL_DT.items
 TEXEL_RGBA8, TEXEL_RGBA32F = 0, 1
 ACCUM_MEAN, ACCUM_SUM = 0, 1
 LIGHTS_REFERENCE, LIGHTS_MIS = 0, 1
+BVH_SAH_HOST, BVH_LBVH_DEVICE = 0, 1
 PLANE_COLOR, PLANE_DEPTH, PLANE_NORMAL, PLANE_ALBEDO, PLANE_HIT_ID, PLANE_DISPLAY, PLANE_REPROJECTED = 0, 1, 2, 3, 4, 5, 6
 TEX_CONSTANT, TEX_FILE, TEX_TEXELS = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_NOT_READY, ERR_IO, ERR_PARSE = 0, -1, -2, -3, -4, -5, -6, -7

@@ -1,6 +1,7 @@
 // bvh_build.cpp — binned-SAH BVH2 builder (host, multi-threaded) and device-layout emission.
 // See bvh_build.h for why the library owns this (reference: src/render_steps/pt.rs:364-468).
 #include "bvh_build.h"
+#include "lbvh.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -263,6 +264,92 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
         put_box(d, 0, bvh.nodes[l]); put_box(d, 1, bvh.nodes[l + 1]);
         d.w[3] = child_ref(l); d.w[7] = child_ref(l + 1);
     }
+}
+
+// ---- linear BVH: host restatement of bvh_gpu.cu --------------------------------------------------------------------
+void lbvh_frame(const float lo[3], const float hi[3], LbvhFrame& f) {
+    float mag = 0.0f;
+    for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::max(std::fabs(lo[a]), std::fabs(hi[a])), hi[a] - lo[a]));
+    f.pad = mag * 2e-5f + 1e-30f;                                  // as build_bvh2
+    for (int a = 0; a < 3; ++a) {                                  // as emit_bvh2
+        double ext = (double)hi[a] - (double)lo[a] + 2.0 * (double)f.pad;
+        double S = ext * (1.0 + 16.0 / 32768.0);
+        if (!(S > 1e-20)) S = 1e-20;
+        float Sf = std::nextafter((float)S, std::numeric_limits<float>::infinity());
+        float bf = std::nextafter((float)((double)lo[a] - (double)f.pad - 0.5 * ((double)Sf - ext)), -std::numeric_limits<float>::infinity());
+        f.grid.base[a] = bf; f.grid.extent[a] = Sf;
+        f.step[a] = (double)Sf / 32768.0;
+    }
+}
+
+void build_lbvh_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth) {
+    const int n = (int)ntri;
+    struct B6 { float lo[3], hi[3]; };
+    std::vector<B6> prim(ntri), node_box(ntri);
+    float slo[3], shi[3], clo[3], chi[3];
+    for (int a = 0; a < 3; ++a) { slo[a] = clo[a] = std::numeric_limits<float>::infinity(); shi[a] = chi[a] = -slo[a]; }
+    for (uint32_t i = 0; i < ntri; ++i) {
+        lbvh_tri_box(tri_pos + (size_t)i * 9, prim[i].lo, prim[i].hi);
+        for (int a = 0; a < 3; ++a) {
+            float c = 0.5f * (prim[i].lo[a] + prim[i].hi[a]);
+            slo[a] = fminf(slo[a], prim[i].lo[a]); shi[a] = fmaxf(shi[a], prim[i].hi[a]);
+            clo[a] = fminf(clo[a], c); chi[a] = fmaxf(chi[a], c);
+        }
+    }
+    float scale[3];
+    for (int a = 0; a < 3; ++a) { float ext = chi[a] - clo[a]; scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f; }
+    std::vector<uint64_t> key(ntri), keys(ntri);
+    std::vector<uint32_t> ids(ntri);
+    for (uint32_t i = 0; i < ntri; ++i) { key[i] = lbvh_key(tri_pos + (size_t)i * 9, clo, scale); ids[i] = i; }
+    std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    for (uint32_t i = 0; i < ntri; ++i) keys[i] = key[ids[i]];
+    std::vector<int> first(n), last(n), split(n), node_parent(n, -1), leaf_parent(n, -1);
+    std::vector<uint32_t> kept(n, 0), new_id(n, 0);
+    uint32_t num_nodes = 0;
+    for (int i = 0; i < n - 1; ++i) {
+        lbvh_node(keys.data(), n, i, first[i], last[i], split[i]);
+        const int f = first[i], l = last[i], s = split[i];
+        if (f == s) leaf_parent[s] = i; else node_parent[s] = i;
+        if (s + 1 == l) leaf_parent[s + 1] = i; else node_parent[s + 1] = i;
+        kept[i] = (uint32_t)(l - f + 1) > PTC_LBVH_MAX_LEAF ? 1u : 0u;
+    }
+    node_parent[0] = -1;
+    for (int i = 0; i < n - 1; ++i) { new_id[i] = num_nodes; num_nodes += kept[i]; }
+    // boxes bottom-up: a node's range strictly contains its children's, so increasing range size is a valid order
+    std::vector<int> order(n - 1);
+    for (int i = 0; i < n - 1; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return last[a] - first[a] < last[b] - first[b]; });
+    for (int i : order) {
+        const int f = first[i], l = last[i], s = split[i];
+        const B6& a = (f == s) ? prim[ids[s]] : node_box[s];
+        const B6& b = (s + 1 == l) ? prim[ids[s + 1]] : node_box[s + 1];
+        for (int x = 0; x < 3; ++x) { node_box[i].lo[x] = fminf(a.lo[x], b.lo[x]); node_box[i].hi[x] = fmaxf(a.hi[x], b.hi[x]); }
+    }
+    uint32_t depth = 0;
+    for (int k = 0; k < n; ++k) {
+        uint32_t d = 0;
+        for (int a = leaf_parent[k]; a >= 0; a = node_parent[a]) d += kept[a];
+        depth = std::max(depth, d);
+    }
+    max_depth = depth + 1;
+    LbvhFrame fr; lbvh_frame(slo, shi, fr);
+    out.grid = fr.grid;
+    out.nodes.assign(num_nodes, DevNode2{});
+    for (int i = 0; i < n - 1; ++i) {
+        if (!kept[i]) continue;
+        const int f = first[i], l = last[i], s = split[i];
+        DevNode2 d;
+        const int cf[2] = {f, s + 1}, cl[2] = {s, l}, ci[2] = {s, s + 1};
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t cnt = (uint32_t)(cl[c] - cf[c] + 1);
+            const B6& b = (cnt == 1) ? prim[ids[cf[c]]] : node_box[ci[c]];
+            lbvh_put_box(&d.w[c * 4], b.lo, b.hi, fr.pad, fr.grid.base, fr.step);
+            d.w[c * 4 + 3] = cnt <= PTC_LBVH_MAX_LEAF ? ~(((uint32_t)cf[c] << 3) | (cnt - 1u)) : new_id[ci[c]];
+        }
+        out.nodes[new_id[i]] = d;
+    }
+    out.tris.resize(ntri);
+    for (uint32_t i = 0; i < ntri; ++i) lbvh_put_tri(out.tris[i].q, tri_pos + (size_t)ids[i] * 9, ids[i]);
 }
 
 }  // namespace ptc

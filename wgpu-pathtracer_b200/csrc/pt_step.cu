@@ -3,6 +3,7 @@
 #include "../../include/ptcore.h"
 #include "bvh_build.h"
 #include "scene_prep.h"
+#include "bvh_gpu.h"
 #include "pt_kernels.cuh"
 #include "pt_error.h"
 
@@ -187,14 +188,43 @@ static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
 
 static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
     PreparedScene ps;
-    int rc = prepare_scene(v, s->cfg, ps);
+    int rc = prepare_scene(v, s->cfg, ps, /*caller_builds_bvh=*/true);
     if (rc != PTC_OK) return rc;
     s->meshes = ps.meshes; s->tri_mesh = ps.tri_mesh;
+    QuantGrid grid = ps.bvh.grid;
+    size_t num_nodes = ps.bvh.nodes.size();
+    if (!ps.tri_pos.empty()) {
+        // PTC_BVH_LBVH_DEVICE: the tree is built by CUDA kernels from the triangle positions (bvh_gpu.cu)
+        float* d_pos = nullptr;
+        CK(cudaMalloc(&d_pos, ps.tri_pos.size() * 4));
+        cudaError_t ce = cudaMemcpyAsync(d_pos, ps.tri_pos.data(), ps.tri_pos.size() * 4, cudaMemcpyHostToDevice, s->stream);
+        GpuBvh g;
+        rc = ce == cudaSuccess ? build_lbvh_device(d_pos, ps.num_tris, s->stream, g) : PTC_ERR_CUDA;
+        cudaFree(d_pos);
+        if (rc != PTC_OK) { if (ce != cudaSuccess) set_error(std::string("position upload: ") + cudaGetErrorString(ce)); return rc; }
+        if (g.max_depth >= PTC_STACK_SIZE) {
+            // degenerate input (tree deeper than the traversal stack): take the host SAH tree instead, as scene_prep does
+            cudaFree(g.nodes); cudaFree(g.tris);
+            ptc_config c2 = s->cfg; c2.bvh_build = PTC_BVH_SAH_HOST;
+            ps = PreparedScene();
+            if ((rc = prepare_scene(v, c2, ps, false)) != PTC_OK) return rc;
+            grid = ps.bvh.grid; num_nodes = ps.bvh.nodes.size();
+        } else {
+            s->d_nodes = reinterpret_cast<F4*>(g.nodes); s->d_tris = reinterpret_cast<F4*>(g.tris);
+            grid = g.grid; num_nodes = g.num_nodes;
+            s->bvh_info[0] = g.num_nodes; s->bvh_info[1] = g.num_tris;
+            s->bvh_info[2] = (uint64_t)g.num_nodes * sizeof(DevNode2); s->bvh_info[3] = (uint64_t)g.num_tris * sizeof(DevTri);
+            s->bvh_info[4] = g.max_depth; s->bvh_info[5] = (uint64_t)(g.build_ms + 0.5f); s->bvh_info[6] = 1;   // [6]: 1 = built on the device
+            s->bvh_info[7] = (uint64_t)(g.build_ms * 1000.0f);                                                    // [7]: build time in microseconds
+        }
+    }
     const DevBvh2& dev = ps.bvh;
-    s->bvh_info[0] = dev.nodes.size(); s->bvh_info[1] = dev.tris.size();
-    s->bvh_info[2] = dev.nodes.size() * sizeof(DevNode2); s->bvh_info[3] = dev.tris.size() * sizeof(DevTri);
-    s->bvh_info[4] = ps.max_depth; s->bvh_info[5] = (uint64_t)ps.build_ms;
-    if (!dev.nodes.empty()) {
+    if (!s->d_nodes) {
+        s->bvh_info[0] = dev.nodes.size(); s->bvh_info[1] = dev.tris.size();
+        s->bvh_info[2] = dev.nodes.size() * sizeof(DevNode2); s->bvh_info[3] = dev.tris.size() * sizeof(DevTri);
+        s->bvh_info[4] = ps.max_depth; s->bvh_info[5] = (uint64_t)ps.build_ms; s->bvh_info[7] = (uint64_t)(ps.build_ms * 1000.0);
+    }
+    if (!s->d_nodes && !dev.nodes.empty()) {
         CK(cudaMalloc(&s->d_nodes, dev.nodes.size() * sizeof(DevNode2)));
         CK(cudaMemcpy(s->d_nodes, dev.nodes.data(), dev.nodes.size() * sizeof(DevNode2), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&s->d_tris, dev.tris.size() * sizeof(DevTri)));
@@ -295,10 +325,10 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
 
     DevScene& ds = s->scene;
     ds.nodes = reinterpret_cast<const NodeQ*>(s->d_nodes); ds.tris = s->d_tris; ds.shade = s->d_shade; ds.mats = s->d_mats; ds.texs = s->d_texs; ds.lights = s->d_lights;
-    ds.num_nodes = (uint32_t)dev.nodes.size(); ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
+    ds.num_nodes = (uint32_t)num_nodes; ds.num_tris = ps.num_tris; ds.num_lights = s->num_lights; ds.env_tex = s->cfg.env_texture_index;
     ds.light_of_tri = s->d_light_of_tri; ds.num_real_lights = s->d_light_of_tri ? ps.num_real_lights : 0;
     ds.num_pages = (uint32_t)s->page_objs.size();
-    for (int a = 0; a < 3; ++a) { ds.grid_base[a] = dev.grid.base[a]; ds.grid_extent[a] = dev.grid.extent[a]; }
+    for (int a = 0; a < 3; ++a) { ds.grid_base[a] = grid.base[a]; ds.grid_extent[a] = grid.extent[a]; }
     for (size_t p = 0; p < s->page_objs.size(); ++p) ds.page_obj[p] = (unsigned long long)s->page_objs[p];
     return PTC_OK;
 }
@@ -340,6 +370,7 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     if (config->max_bounces + 1 > PTC_MAX_SEGMENTS) { set_error("max_bounces too large"); return PTC_ERR_INVALID; }
     if (config->accum_mode > PTC_ACCUM_SUM) { set_error("bad accum_mode"); return PTC_ERR_INVALID; }
     if (config->light_sampling > PTC_LIGHTS_MIS) { set_error("bad light_sampling"); return PTC_ERR_INVALID; }
+    if (config->bvh_build > PTC_BVH_LBVH_DEVICE) { set_error("bad bvh_build"); return PTC_ERR_INVALID; }
     if (config->light_sampling == PTC_LIGHTS_MIS && config->send_to_light_probability != 0.0f) { set_error("PTC_LIGHTS_MIS requires send_to_light_probability == 0"); return PTC_ERR_INVALID; }
     int ndev = ptc_device_count();
     if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
@@ -707,6 +738,22 @@ PTC_API int ptc_debug_sample(ptc_step* s, int texture_index, const float* in, ui
     }
     cudaFree(d_in); cudaFree(d_out);
     return rc;
+}
+
+static uint64_t fnv1a(const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+PTC_API int ptc_debug_bvh_hash(ptc_step* s, uint64_t out[2]) {
+    if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    std::vector<unsigned char> nodes((size_t)s->bvh_info[2]), tris((size_t)s->bvh_info[3]);
+    if (!nodes.empty()) CK(cudaMemcpy(nodes.data(), s->d_nodes, nodes.size(), cudaMemcpyDeviceToHost));
+    if (!tris.empty()) CK(cudaMemcpy(tris.data(), s->d_tris, tris.size(), cudaMemcpyDeviceToHost));
+    out[0] = fnv1a(nodes.data(), nodes.size()); out[1] = fnv1a(tris.data(), tris.size());
+    return PTC_OK;
 }
 
 PTC_API int ptc_debug_unorm8(int cuda_device, float* out512) {

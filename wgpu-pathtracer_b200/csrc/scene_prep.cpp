@@ -1,6 +1,7 @@
 // scene_prep.cpp — see scene_prep.h.
 #include "scene_prep.h"
 #include "pt_error.h"
+#include "lbvh.cuh"
 
 #include <cstring>
 
@@ -16,7 +17,7 @@ static void texel_of(const ptc_texture_desc& t, float out[4]) {   // the (0,0) t
     }
 }
 
-int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene& out) {
+int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene& out, bool caller_builds_bvh) {
     const uint64_t ntri64 = v->num_indices / 3;
     if (v->num_indices % 3 != 0) { set_error("index count is not a multiple of 3"); return PTC_ERR_INVALID; }
     if (ntri64 >= (1ull << 28)) { set_error("too many triangles"); return PTC_ERR_INVALID; }
@@ -46,10 +47,21 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
     std::vector<float> pos((size_t)ntri * 9);
     for (uint32_t t = 0; t < ntri; ++t)
         for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], v->vertices[v->indices[(size_t)t * 3 + k]].position, 12);
-    Bvh2 bvh; build_bvh2(pos.data(), ntri, 4, 0, bvh);
-    if (bvh.max_depth >= PTC_STACK_SIZE) { set_error("BVH too deep for the traversal stack"); return PTC_ERR_INVALID; }
-    emit_bvh2(bvh, pos.data(), out.bvh);
-    out.max_depth = bvh.max_depth; out.build_ms = bvh.build_ms;
+    const bool lbvh = cfg.bvh_build == PTC_BVH_LBVH_DEVICE && ntri > PTC_LBVH_MAX_LEAF;
+    if (lbvh && caller_builds_bvh) out.tri_pos = pos;
+    else {
+        bool sah = !lbvh;
+        if (lbvh) {
+            build_lbvh_host(pos.data(), ntri, out.bvh, out.max_depth);
+            if (out.max_depth >= PTC_STACK_SIZE) { out.bvh = DevBvh2{}; sah = true; }     // degenerate input: fall back to the SAH tree
+        }
+        if (sah) {
+            Bvh2 bvh; build_bvh2(pos.data(), ntri, 4, 0, bvh);
+            if (bvh.max_depth >= PTC_STACK_SIZE) { set_error("BVH too deep for the traversal stack"); return PTC_ERR_INVALID; }
+            emit_bvh2(bvh, pos.data(), out.bvh);
+            out.max_depth = bvh.max_depth; out.build_ms = bvh.build_ms;
+        }
+    }
 
     // per-triangle shading records: re-pack of vertices[] / indices[] / instance_infos[] (rt_helpers.wgsl:57-67)
     out.shade.resize(ntri);

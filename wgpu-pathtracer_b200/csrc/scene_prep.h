@@ -22,12 +22,15 @@ struct PreparedScene {
     uint32_t num_real_lights = 0;         // 0 when lights holds only the dummy entry
     std::vector<uint32_t> tri_mesh;       // global triangle -> mesh (instance_index)
     std::vector<ptc_mesh> meshes;
+    std::vector<float> tri_pos;           // 9 floats per triangle; filled only when the caller builds the BVH itself
     uint32_t num_tris = 0;
     uint32_t max_depth = 0;
     double build_ms = 0.0;
 };
 
 // returns PTC_OK or a negative ptc_status with set_error() called
-int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene& out);
+// caller_builds_bvh: leave out.bvh empty and hand the triangle positions over in out.tri_pos (the product's device build);
+// otherwise cfg.bvh_build selects the host builder (binned SAH, or the host restatement of the device LBVH build).
+int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene& out, bool caller_builds_bvh = false);
 
 }  // namespace ptc

@@ -12,12 +12,13 @@ from ._lib import PtcError, check, lib
 
 
 def make_config(width, height, max_bounces=4, samples_per_pixel=1, send_to_light_probability=0.0,
-                env_texture_index=9, accum_mode=T.ACCUM_MEAN, light_sampling=0):
+                env_texture_index=9, accum_mode=T.ACCUM_MEAN, light_sampling=0, bvh_build=0):
     """The reference's compile-time constants (src/shaders/shader_definitions.rs:3-26) as a run-time struct."""
     c = T.Config()
     c.width, c.height, c.max_bounces, c.samples_per_pixel = width, height, max_bounces, samples_per_pixel
     c.send_to_light_probability, c.env_texture_index, c.accum_mode = send_to_light_probability, env_texture_index, accum_mode
     c.light_sampling = light_sampling          # ptc_light_sampling: 0 = reference behaviour, 1 = shadow rays + MIS (non-parity)
+    c.bvh_build = bvh_build                    # ptc_bvh_build: 0 = binned SAH on the host, 1 = linear BVH built on the GPU
     return c
 
 
@@ -115,7 +116,13 @@ class RTStep:
     def bvh_info(self):
         a = (C.c_uint64 * 8)()
         check(lib().ptc_bvh_info(self._h, a))
-        return {"nodes": a[0], "triangles": a[1], "node_bytes": a[2], "triangle_bytes": a[3], "max_depth": a[4], "build_ms": a[5]}
+        return {"nodes": a[0], "triangles": a[1], "node_bytes": a[2], "triangle_bytes": a[3], "max_depth": a[4], "build_ms": a[5],
+                "built_on_device": bool(a[6]), "build_us": a[7]}
+
+    def bvh_hash(self):
+        a = (C.c_uint64 * 2)()
+        check(lib().ptc_debug_bvh_hash(self._h, a))
+        return a[0], a[1]
 
     def trace_rays(self, rays):
         """rays: (n, 8) float32 [ox,oy,oz,_,dx,dy,dz,_] -> (t, b1, b2, tri, ids) through the traversal kernel."""
