@@ -219,6 +219,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The image reduce goes through the library's own entry point, ptc_reduce = one ncclReduce on the step's
+    # stream, with the communicator torch.distributed already holds; torch's dist.reduce is the fallback if that
+    # communicator cannot be reached from Python.
+    comm, reduce_how = None, None
+    if dist is not None:
+        try:
+            warm = torch.zeros(1, device=f"cuda:{local}"); dist.all_reduce(warm); torch.cuda.synchronize()   # the communicator exists after the first collective
+            comm = dist.distributed_c10d._get_default_group()._get_backend(torch.device("cuda", local))._comm_ptr()
+            reduce_how = "ptc_reduce (ncclReduce of the SUM-mode colour planes on the step's stream)"
+        except Exception as e:                               # pragma: no cover
+            comm, reduce_how = None, f"torch.distributed.reduce (ProcessGroupNCCL._comm_ptr unavailable: {type(e).__name__})"
+
+    def reduce_image():
+        if comm is not None:
+            step.reduce(comm, 0)
+        else:
+            with torch.cuda.stream(ext):
+                dist.reduce(out, dst=0)
+
     # ---- device-resident timing ---------------------------------------------------------------------------------
     uniforms = [camera.uniforms(frame=frame_of(i)) for i in range(Wm + K)]
     for i in range(Wm):
@@ -237,8 +256,7 @@ def main():
     for i in range(K):
         step.update(uniforms[Wm + i]); step.render()
     if dist is not None:
-        with torch.cuda.stream(ext):
-            dist.reduce(out, dst=0)
+        reduce_image()
     e1.record(ext)
     e1.synchronize()
     barrier()
@@ -283,8 +301,7 @@ def main():
             step.blit()                                        # BlitStep: tonemap + sRGB encode of the accumulated image (1 kernel)
             step.read_async(T.PLANE_DISPLAY, pinned.data_ptr())  # D2H of the frame a user sees, overlapped on the copy stream
         if dist is not None:
-            with torch.cuda.stream(ext):
-                dist.reduce(out, dst=0)
+            reduce_image()
         step.poll(True)
         step.read_wait()
         barrier()
@@ -330,7 +347,7 @@ def main():
                                + (", PTC_LIGHTS_MIS (non-reference mode: one any-hit shadow ray per opaque hit, counted as a ray)" if w.get("light_sampling") else ""),
                    "bvh": {"build": "lbvh (CUDA kernels)" if bvh["built_on_device"] else "binned SAH (host threads)", "build_ms": bvh["build_us"] / 1e3,
                            "nodes": bvh["nodes"], "max_depth": bvh["max_depth"], "ptc_create_s": t_create},
-                   "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated" if world > 1 else "single GPU",
+                   "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated; image reduce: {reduce_how}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: each frame streams ~%.0f MB of path-state queues; the %.1f MB BVH is L2-resident by design" % (
                        W * H * 144 / 1e6, (bvh["node_bytes"] + bvh["triangle_bytes"]) / 1e6)},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 4,

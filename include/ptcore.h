@@ -103,8 +103,16 @@ PTC_API int ptc_read_wait(ptc_step* step);
 PTC_API void* ptc_device_ptr(ptc_step* step, int plane);
 
 /* the CUDA stream frames are enqueued on (a cudaStream_t), for callers that
- * order their own work (e.g. an NCCL reduce of the COLOR plane) after it */
+ * order their own work after it */
 PTC_API void* ptc_stream(ptc_step* step);
+
+/* Multi-GPU: frames are sharded over one step per GPU, each accumulating with PTC_ACCUM_SUM; this enqueues,
+ * on the step's stream, the in-place sum of the COLOR planes (rgb sums + sample counts, width*height*4 floats) of every
+ * rank of `nccl_comm` into rank `root` — one ncclReduce(ncclFloat32, ncclSum), after the frames already enqueued.  The
+ * reference has no counterpart (single GPU).  `nccl_comm` is the caller's ncclComm_t; the library binds to the NCCL the
+ * process has already loaded (dlopen RTLD_NOLOAD "libnccl.so.2"), else loads the system one, so the communicator and the
+ * call always come from the same NCCL.  Returns PTC_ERR_INVALID when no NCCL can be found. */
+PTC_API int ptc_reduce(ptc_step* step, void* nccl_comm, int root);
 
 PTC_API int ptc_get_stats(ptc_step* step, ptc_stats* out);
 

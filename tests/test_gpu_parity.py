@@ -442,3 +442,34 @@ def test_linear_bvh_device_build(ptc, standins, oracle, hostemu, which):
     rh, rids, _ = oracle.OracleScene(scene, ptc.make_config(8, 8)).trace_rays(rays)
     assert np.array_equal(hits, rh) and np.array_equal(ids, rids)
     step.destroy()
+
+
+def test_ptc_reduce_binds_process_nccl(ptc, standins):
+    """ptc_reduce with the communicator torch.distributed holds: on one rank the sum over ranks is the image
+    itself — this checks the run-time binding to the process's NCCL and the call on the step's stream; the 2-GPU sum is
+    exercised by `bench.py --gpus 2` and, without GPUs, by tests/test_multirank_cpu.py."""
+    import os
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip("process group already initialised")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        t = torch.zeros(1, device="cuda:0"); dist.all_reduce(t); torch.cuda.synchronize()
+        comm = dist.distributed_c10d._get_default_group()._get_backend(torch.device("cuda", 0))._comm_ptr()
+        T = ptc.types
+        scene, cam = standins.cornell()
+        step = ptc.RTStep.create(scene, ptc.make_config(96, 64, accum_mode=T.ACCUM_SUM))
+        camera = standins.make_camera(cam, 96, 64)
+        for f in (1, 2):
+            step.update(camera.uniforms(frame=f)); step.render()
+        step.poll(True)
+        before = step.read(T.PLANE_COLOR)
+        step.reduce(comm, 0); step.poll(True)
+        assert np.array_equal(step.read(T.PLANE_COLOR), before) and (before[..., 3] == 2).all()
+        with pytest.raises(ptc.PtcError):
+            step.reduce(0, 0)
+        step.destroy()
+    finally:
+        dist.destroy_process_group()

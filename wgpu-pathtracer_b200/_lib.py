@@ -53,6 +53,7 @@ def lib():
         "ptc_get_profile": (i32, [vp, P(C.c_double), P(u64)]),
         "ptc_num_lights": (i32, [vp, P(u32)]),
         "ptc_bvh_info": (i32, [vp, P(u64)]),
+        "ptc_reduce": (i32, [vp, vp, i32]),
         "ptc_debug_bvh_hash": (i32, [vp, P(u64)]),
         "ptc_trace_rays": (i32, [vp, vp, u64, vp, vp]),
         "ptc_trace_rays_any": (i32, [vp, vp, u64, vp]),

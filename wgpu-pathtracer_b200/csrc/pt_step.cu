@@ -8,6 +8,7 @@
 #include "pt_error.h"
 
 #include <algorithm>
+#include <dlfcn.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -738,6 +739,30 @@ PTC_API int ptc_debug_sample(ptc_step* s, int texture_index, const float* in, ui
     }
     cudaFree(d_in); cudaFree(d_out);
     return rc;
+}
+
+// ---- ptc_reduce: NCCL bound at run time (no link dependency; the communicator's own library is the one called) ---------
+typedef int (*nccl_reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);   // ncclReduce(send, recv, count, dtype, op, root, comm, stream)
+typedef const char* (*nccl_errstr_fn)(int);
+static nccl_reduce_fn g_nccl_reduce = nullptr;
+static nccl_errstr_fn g_nccl_errstr = nullptr;
+static bool bind_nccl() {
+    if (g_nccl_reduce) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl_reduce = (nccl_reduce_fn)dlsym(h, "ncclReduce");
+    g_nccl_errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+    return g_nccl_reduce != nullptr;
+}
+PTC_API int ptc_reduce(ptc_step* s, void* nccl_comm, int root) {
+    if (!s || !nccl_comm) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (!bind_nccl()) { set_error("ptc_reduce: no NCCL (libnccl.so.2) loaded or loadable in this process"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const int kNcclFloat32 = 7, kNcclSum = 0;                     // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
+    int r = g_nccl_reduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
+    if (r != 0) { set_error(std::string("ncclReduce: ") + (g_nccl_errstr ? g_nccl_errstr(r) : "error")); return PTC_ERR_CUDA; }
+    return PTC_OK;
 }
 
 static uint64_t fnv1a(const void* p, size_t n) {

@@ -59,6 +59,11 @@ class RTStep:
     def set_output(self, device_ptr):
         check(lib().ptc_set_output(self._h, C.c_void_p(device_ptr) if device_ptr else None))
 
+    def reduce(self, nccl_comm, root=0):
+        """Sum the per-rank SUM-mode accumulation buffers into `root` with one ncclReduce on the step's stream (ptc_reduce).
+        nccl_comm: the ncclComm_t as an integer (e.g. torch's ProcessGroupNCCL._comm_ptr())."""
+        check(lib().ptc_reduce(self._h, C.c_void_p(int(nccl_comm)), int(root)))
+
     def reset_accumulation(self):
         check(lib().ptc_reset_accumulation(self._h))
 
