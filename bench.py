@@ -348,6 +348,7 @@ def main():
                    "bvh": {"build": "lbvh (CUDA kernels)" if bvh["built_on_device"] else "binned SAH (host threads)", "build_ms": bvh["build_us"] / 1e3,
                            "nodes": bvh["nodes"], "max_depth": bvh["max_depth"], "ptc_create_s": t_create},
                    "baseline_config_index": w["config_index"], "parallelism": f"frame-sharded x{world}, scene replicated; image reduce: {reduce_how}" if world > 1 else "single GPU",
+                   "frame_parts": step.stats()["frame_parts"],
                    "l2": "inputs larger than L2: each frame streams ~%.0f MB of path-state queues; the %.1f MB BVH is L2-resident by design" % (
                        W * H * 144 / 1e6, (bvh["node_bytes"] + bvh["triangle_bytes"]) / 1e6)},
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 4,
@@ -361,7 +362,8 @@ def main():
                      "rays_per_launch": rank_rays / max(trace_n, 1), "avg_launch_ms": trace_ms / max(trace_n, 1), "launches": int(trace_n),
                      "kernel_share_of_step": trace_ms / stage_total if stage_total > 0 else None,
                      "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_pass_steps": P,
-                     "note": "stage times from a separate single-stream pass (no primary-ray prefetch) so that durations are exclusive"},
+                     "note": "stage times from a separate pass with stage timing on: the frame runs as ONE wavefront on one stream (no frame parts, no primary-ray prefetch), "
+                             "so each launch covers a whole segment and its CUDA-event duration is exclusive; the timed region itself runs %d concurrent parts" % step.stats()["frame_parts"]},
         "cpu_baseline": ({k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} if (base and world == 1) else None),
     }
     print(json.dumps(line, allow_nan=False))

@@ -176,7 +176,8 @@ typedef struct ptc_stats {
     uint64_t rays_traced;      /* trace_ray invocations since create/reset (path segments incl. the escaping one) */
     uint64_t frames_rendered;
     uint64_t kernel_launches;  /* CUDA kernels this library launched */
-    uint64_t reserved[5];
+    uint64_t frame_parts;      /* independent wavefronts a frame is split into (each runs raygen + (trace, shade) x segments) */
+    uint64_t reserved[4];
 } ptc_stats;
 
 /* status codes */

@@ -34,7 +34,7 @@ class Config(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("rays_traced", u64), ("frames_rendered", u64), ("kernel_launches", u64), ("reserved", u64 * 5)]
+    _fields_ = [("rays_traced", u64), ("frames_rendered", u64), ("kernel_launches", u64), ("frame_parts", u64), ("reserved", u64 * 4)]
 
 
 class HostCamera(C.Structure):  # include/ptcore.h ptc_host_camera (camera.rs:5-28)

@@ -10,10 +10,11 @@ constexpr int kShadeThreads = 128;
 #endif
 
 // ---- raygen: rand_init + primary ray (pathtracer.wgsl:27, pathtracer/pathtracer.wgsl:240-250) ----
-__global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameCounters* fc, uint32_t npix) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) fc->count[0] = npix;
-    if (i >= npix) return;
+__global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;       // slot in this part's queue
+    if (j == 0) fc->count[0] = n;
+    if (j >= n) return;
+    const uint32_t i = (((j >> 5) * num_parts + part) << 5) | (j & 31u);   // slot in the frame's order: warps are dealt round-robin to the parts
     // Queue slot i -> pixel: 8x4 pixel tiles, one tile per warp, so the 32 primary rays of a warp (and the paths that
     // descend from them, which k_shade compacts in queue order) share BVH nodes and texture lines; a scanline run of 32
     // pixels diverges sooner.  Pixels outside the tile-aligned part (right strip, then bottom strip) follow in row
@@ -39,8 +40,8 @@ __global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameC
     }
     uint32_t rng; pt_v3 ro, rd;
     gen_primary(un.camera, x, y, rng, ro, rd);
-    st4_stream(q.ray_o + i, ro.x, ro.y, ro.z, __uint_as_float(y * W + x));
-    st4_stream(q.ray_d + i, rd.x, rd.y, rd.z, __uint_as_float(rng));
+    st4_stream(q.ray_o + j, ro.x, ro.y, ro.z, __uint_as_float(y * W + x));
+    st4_stream(q.ray_d + j, rd.x, rd.y, rd.z, __uint_as_float(rng));
     // color_mask = 1 and accumulated_color = 0 at segment 0 are constants of k_shade<true>: not stored
 }
 
@@ -299,8 +300,8 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
-void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t npix) {
-    k_raygen<<<(npix + 255) / 256, 256, 0, st>>>(un, q, fc, npix);
+void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part) {
+    k_raygen<<<(n + 255) / 256, 256, 0, st>>>(un, q, fc, n, num_parts, part);
 }
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays) {

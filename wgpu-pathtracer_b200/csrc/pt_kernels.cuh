@@ -46,7 +46,8 @@ struct Planes {
     uint32_t* hit_tri;    // primary-hit global triangle id (0xFFFFFFFF = miss)
 };
 
-void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t npix);
+// part `part` of `num_parts`: its n queue slots are the warps t = part, part + num_parts, ... of the frame's slot order
+void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part);
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays);
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,

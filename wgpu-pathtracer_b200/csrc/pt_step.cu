@@ -39,20 +39,33 @@ struct ptc_step {
     bool have_uniforms = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t snap_ready = nullptr, copy_done = nullptr;
-    // Primary-ray prefetch: raygen + the segment-0 traversal of frame f+1 depend on nothing frame f produces, so they run on
-    // a second, lower-priority stream and fill the SMs that frame f's persistent kernels leave idle while their longest
-    // rays finish (ncu: ~20 % of a trace launch's SM cycles).  Everything that touches the image stays on `stream`, in
-    // frame order, so results are unchanged.  Segment 0 has its own ray / hit buffers (`qp`, `d_hits_p`).
-    cudaStream_t prefetch_stream = nullptr;
-    cudaEvent_t primary_done = nullptr, primary_free = nullptr;
+    // Frame parts.  The queue slots of a frame (8x4-pixel tiles, one per warp) are dealt round-robin to `num_parts` parts;
+    // each part is an independent wavefront (own queues, counters, stream) over its own pixels.  Persistent kernels leave
+    // SMs idle while their longest rays finish (ncu: ~20 % of a trace launch's SM cycles); with several parts in flight
+    // the block scheduler fills those slots with the other parts' kernels (measured: +8 % with 2 parts, +14 % with 3).
+    // Parts own disjoint pixels, every pixel is still written exactly once per frame and a part's stream keeps frames in
+    // order, so the image is bit-identical to the one-part schedule.  `stream` is the step's ordering stream: it waits for
+    // every part after each frame, and anything that touches the planes between frames (blit, reduce, reset, reads) runs
+    // on it; a part's first kernel that touches the planes waits for such work (`ev_main`).
+    // Within a part, raygen + the primary-ray traversal of frame f+1 depend on nothing frame f produces: they run on the
+    // part's second, lower-priority stream with their own ray / hit buffers (`qp`, `d_hits_p`) while frame f is still bouncing.
+    struct FramePart {
+        cudaStream_t stream = nullptr, prefetch_stream = nullptr;
+        cudaEvent_t done = nullptr, primary_done = nullptr, primary_free = nullptr;
+        Queue q[2]{}; U4* d_hits = nullptr; ShadowQueue shq{};
+        Queue qp{}; U4* d_hits_p = nullptr;
+        uint32_t n = 0;                            // queue slots (= pixels) of this part
+    };
     bool overlap = true;
-    Queue qp{}; U4* d_hits_p = nullptr;
+    static const uint32_t kMaxParts = 8;
+    FramePart parts[kMaxParts + 1];              // [kMaxParts]: the whole frame as ONE part, allocated when stage timing is first enabled
+    uint32_t num_parts = 1, want_parts = 0;      // want_parts: PTC_PARTS override, 0 = by frame size
+    cudaEvent_t ev_main = nullptr; bool main_dirty = false;
 
     // scene (device)
     F4* d_nodes = nullptr; F4* d_tris = nullptr; TriShade* d_shade = nullptr;
     MatDev* d_mats = nullptr; TexDev* d_texs = nullptr; ptc_triangle* d_lights = nullptr;
     uint32_t* d_light_of_tri = nullptr;            // PTC_LIGHTS_MIS only
-    ShadowQueue shq{};                             // PTC_LIGHTS_MIS only
     std::vector<cudaArray_t> pages; std::vector<cudaTextureObject_t> page_objs;   // texture atlas pages
     uint32_t num_textures = 0; uint64_t atlas_bytes = 0;
     DevScene scene{};
@@ -62,8 +75,7 @@ struct ptc_step {
     uint64_t bvh_info[8] = {0};
 
     // frame buffers
-    Queue q[2]{}; U4* d_hits = nullptr;
-    FrameCounters* d_fc = nullptr;                 // ring of kFcRing counter blocks
+    FrameCounters* d_fc = nullptr;                 // ring of kFcRing x kMaxParts counter blocks
     uint32_t fc_next = 0;
     unsigned long long* d_total_rays = nullptr;
     Planes planes{}; F4* owned_color = nullptr; F4* d_snapshot = nullptr; size_t snapshot_bytes = 0;
@@ -146,13 +158,17 @@ static int unorm8_hw_exact() {
 }
 
 static void free_frame_buffers(ptc_step* s) {
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(s->q[i].ray_o); cudaFree(s->q[i].ray_d); cudaFree(s->q[i].mask); cudaFree(s->q[i].acc);
-        s->q[i] = Queue{};
+    for (uint32_t p = 0; p <= ptc_step::kMaxParts; ++p) {
+        ptc_step::FramePart& P = s->parts[p];
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(P.q[i].ray_o); cudaFree(P.q[i].ray_d); cudaFree(P.q[i].mask); cudaFree(P.q[i].acc);
+            P.q[i] = Queue{};
+        }
+        cudaFree(P.d_hits); P.d_hits = nullptr;
+        cudaFree(P.qp.ray_o); cudaFree(P.qp.ray_d); P.qp = Queue{}; cudaFree(P.d_hits_p); P.d_hits_p = nullptr;
+        cudaFree(P.shq.ray_o); cudaFree(P.shq.ray_d); cudaFree(P.shq.contrib); P.shq = ShadowQueue{};
+        P.n = 0;
     }
-    cudaFree(s->d_hits); s->d_hits = nullptr;
-    cudaFree(s->shq.ray_o); cudaFree(s->shq.ray_d); cudaFree(s->shq.contrib); s->shq = ShadowQueue{};
-    cudaFree(s->qp.ray_o); cudaFree(s->qp.ray_d); s->qp = Queue{}; cudaFree(s->d_hits_p); s->d_hits_p = nullptr;
     cudaFree(s->owned_color); s->owned_color = nullptr;
     cudaFree(s->planes.depth); cudaFree(s->planes.normal); cudaFree(s->planes.albedo); cudaFree(s->planes.hit_tri);
     cudaFree(s->d_snapshot); s->d_snapshot = nullptr; s->snapshot_bytes = 0;
@@ -160,19 +176,36 @@ static void free_frame_buffers(ptc_step* s) {
     s->planes = Planes{};
 }
 
+static int alloc_part(ptc_step* s, ptc_step::FramePart& P, uint32_t n) {
+    P.n = n;
+    const size_t m = std::max<size_t>(n, 1);
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&P.q[i].ray_o, m * 16)); CK(cudaMalloc(&P.q[i].ray_d, m * 16));
+        CK(cudaMalloc(&P.q[i].mask, m * 16)); CK(cudaMalloc(&P.q[i].acc, m * 16));
+    }
+    CK(cudaMalloc(&P.d_hits, m * 16));
+    CK(cudaMalloc(&P.qp.ray_o, m * 16)); CK(cudaMalloc(&P.qp.ray_d, m * 16)); CK(cudaMalloc(&P.d_hits_p, m * 16));
+    if (s->cfg.light_sampling == PTC_LIGHTS_MIS) {
+        CK(cudaMalloc(&P.shq.ray_o, m * 16)); CK(cudaMalloc(&P.shq.ray_d, m * 16)); CK(cudaMalloc(&P.shq.contrib, m * 16));
+    }
+    return PTC_OK;
+}
+
 static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
     if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull) { set_error("bad frame size"); return PTC_ERR_INVALID; }
     uint32_t n = w * h;
     s->npix = n; s->cfg.width = w; s->cfg.height = h;
-    for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&s->q[i].ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->q[i].ray_d, (size_t)n * 16));
-        CK(cudaMalloc(&s->q[i].mask, (size_t)n * 16)); CK(cudaMalloc(&s->q[i].acc, (size_t)n * 16));
+    // slots are dealt to the parts warp by warp: warp t (slots 32t .. 32t+31) belongs to part t % num_parts
+    // Parts by frame size (measured, profiles/r01f): the tail a part hides is a fixed ~30-50 us per launch, so mid-size frames
+    // gain most (1080p: 3 parts +8 % Sponza, +22 % classroom); at 4K launches are long and a third part only costs locality.
+    uint32_t want = s->want_parts ? s->want_parts : (n < (1u << 20) ? 2u : (n < (1u << 22) ? 3u : 2u));
+    s->num_parts = std::max(1u, std::min(std::min(want, (uint32_t)ptc_step::kMaxParts), n / 8192u));
+    const uint32_t nw = n >> 5, rem = n & 31u, NP = s->num_parts;
+    for (uint32_t p = 0; p < NP; ++p) {
+        int rc = alloc_part(s, s->parts[p], 32u * (nw > p ? (nw - p + NP - 1) / NP : 0u) + (nw % NP == p ? rem : 0u));
+        if (rc != PTC_OK) return rc;
     }
-    CK(cudaMalloc(&s->d_hits, (size_t)n * 16));
-    if (s->cfg.light_sampling == PTC_LIGHTS_MIS) {
-        CK(cudaMalloc(&s->shq.ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->shq.ray_d, (size_t)n * 16)); CK(cudaMalloc(&s->shq.contrib, (size_t)n * 16));
-    }
-    CK(cudaMalloc(&s->qp.ray_o, (size_t)n * 16)); CK(cudaMalloc(&s->qp.ray_d, (size_t)n * 16)); CK(cudaMalloc(&s->d_hits_p, (size_t)n * 16));
+    if (s->profiling) { int rc = alloc_part(s, s->parts[ptc_step::kMaxParts], n); if (rc != PTC_OK) return rc; }
     CK(cudaMalloc(&s->owned_color, (size_t)n * 16));
     CK(cudaMalloc(&s->planes.depth, (size_t)n * 4));
     CK(cudaMalloc(&s->planes.normal, (size_t)n * 16));
@@ -184,6 +217,7 @@ static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
     CK(cudaMemsetAsync(s->planes.normal, 0, (size_t)n * 16, s->stream));
     CK(cudaMemsetAsync(s->planes.albedo, 0, (size_t)n * 16, s->stream));
     CK(cudaMemsetAsync(s->planes.hit_tri, 0xFF, (size_t)n * 4, s->stream));
+    s->main_dirty = true;
     return PTC_OK;
 }
 
@@ -337,7 +371,7 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
 static void destroy_step(ptc_step* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    if (s->prefetch_stream) cudaStreamSynchronize(s->prefetch_stream);
+    for (auto& P : s->parts) { if (P.prefetch_stream) cudaStreamSynchronize(P.prefetch_stream); if (P.stream) cudaStreamSynchronize(P.stream); }
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     free_frame_buffers(s);
@@ -348,9 +382,14 @@ static void destroy_step(ptc_step* s) {
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->snap_ready) cudaEventDestroy(s->snap_ready);
     if (s->copy_done) cudaEventDestroy(s->copy_done);
-    if (s->primary_done) cudaEventDestroy(s->primary_done);
-    if (s->primary_free) cudaEventDestroy(s->primary_free);
-    if (s->prefetch_stream) cudaStreamDestroy(s->prefetch_stream);
+    if (s->ev_main) cudaEventDestroy(s->ev_main);
+    for (auto& P : s->parts) {
+        if (P.done) cudaEventDestroy(P.done);
+        if (P.primary_done) cudaEventDestroy(P.primary_done);
+        if (P.primary_free) cudaEventDestroy(P.primary_free);
+        if (P.prefetch_stream) cudaStreamDestroy(P.prefetch_stream);
+        if (P.stream) cudaStreamDestroy(P.stream);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -383,17 +422,26 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     do {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);         // numerically lower = higher priority
+        { const char* e = getenv("PTC_PARTS"); if (e && atoi(e) >= 1) s->want_parts = (uint32_t)atoi(e); }
+        bool parts_ok = true;
+        for (uint32_t pi = 0; pi < ptc_step::kMaxParts; ++pi) {
+            ptc_step::FramePart& P = s->parts[pi];
+            parts_ok = parts_ok && cudaStreamCreateWithPriority(&P.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+                       cudaStreamCreateWithPriority(&P.prefetch_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&P.primary_done, cudaEventDisableTiming) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&P.primary_free, cudaEventDisableTiming) == cudaSuccess;
+        }
         { const char* e = getenv("PTC_OVERLAP"); s->overlap = !(e && std::strcmp(e, "0") == 0); }
+        if (!parts_ok) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
         if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&s->prefetch_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->primary_done, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->primary_free, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming) != cudaSuccess ||
             cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
         if ((rc = upload_scene(s, scene)) != PTC_OK) break;
         if ((rc = alloc_frame_buffers(s, config->width, config->height)) != PTC_OK) break;
-        if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
+        if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing * ptc_step::kMaxParts) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
         cudaMemsetAsync(s->d_total_rays, 0, 8, s->stream);
         { const char* e = getenv("PTC_TRACE_IMPL"); s->trace_impl = (e && std::strcmp(e, "simple") == 0) ? 1 : 0; }
         s->trace_grid = trace_grid_size(cuda_device, s->trace_impl);
@@ -418,38 +466,48 @@ PTC_API int ptc_render(ptc_step* s) {
     if (!s->have_uniforms) { set_error("ptc_render before ptc_update"); return PTC_ERR_INVALID; }
     if (s->uniforms.camera.width != s->cfg.width || s->uniforms.camera.height != s->cfg.height) { set_error("uniform size differs from step size; call ptc_resize"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
-    FrameCounters* fc = s->d_fc + (s->fc_next++ % kFcRing);
     PathCfg pc; pc.width = s->cfg.width; pc.height = s->cfg.height; pc.max_bounces = s->cfg.max_bounces;
     pc.send_to_light_probability = s->cfg.send_to_light_probability; pc.accum_mode = s->cfg.accum_mode; pc.is_grabbed = s->uniforms.is_grabbed;
     pc.light_sampling = s->cfg.light_sampling;
     const bool mis = pc.light_sampling == PTC_LIGHTS_MIS && s->scene.num_real_lights != 0;
     if (s->profiling && s->ev_used > 60000) prof_collect(s);
-    // segment 0: raygen + traversal of the primary rays.  Prefetched on the low-priority stream unless stage timing is on
-    // (profiling keeps every launch on one stream so the per-stage times are exclusive).
-    const bool prefetch = s->overlap && !s->profiling;
-    cudaStream_t st0 = prefetch ? s->prefetch_stream : s->stream;
-    if (prefetch) CK(cudaStreamWaitEvent(st0, s->primary_free, 0));          // the previous frame's shade(0) has consumed qp / d_hits_p
-    CK(cudaMemsetAsync(fc, 0, sizeof(FrameCounters), st0));
-    prof_mark(s, 0);
-    launch_raygen(st0, s->uniforms, s->qp, fc, s->npix);
-    prof_mark(s, 1);
-    launch_trace(st0, s->trace_grid, s->trace_impl, s->scene, s->qp, s->d_hits_p, fc, 0, s->d_total_rays);
-    if (prefetch) { CK(cudaEventRecord(s->primary_done, st0)); CK(cudaStreamWaitEvent(s->stream, s->primary_done, 0)); }
-    prof_mark(s, 2);
-    launch_shade(s->stream, s->shade_grid, s->scene, pc, s->qp, s->q[1], s->d_hits_p, fc, 0, s->planes, s->shq);
-    if (s->overlap) CK(cudaEventRecord(s->primary_free, s->stream));
-    s->launches += 3;
-    // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
-    if (mis && s->cfg.max_bounces >= 1) { prof_mark(s, 1); launch_trace_shadow(s->stream, s->trace_grid, s->scene, s->shq, s->q[1].acc, fc, 0, s->d_total_rays); s->launches++; }
-    for (uint32_t seg = 1; seg <= s->cfg.max_bounces; ++seg) {
+    // work enqueued on the ordering stream since the last frame (blit, reduce, reset, an asynchronous read's snapshot) must
+    // be over before this frame touches the planes; raygen and the primary-ray traversal do not, and are not held back
+    const bool wait_main = s->main_dirty && !s->profiling;
+    if (wait_main) CK(cudaEventRecord(s->ev_main, s->stream));
+    s->main_dirty = false;
+    const uint32_t ring = s->fc_next++ % kFcRing;
+    // stage timing renders the frame as ONE part on the ordering stream, so that the per-stage CUDA-event times are exclusive
+    // and each launch covers a whole segment of the frame (same image: pixels do not care which part they are in)
+    const uint32_t nparts = s->profiling ? 1u : s->num_parts;
+    for (uint32_t p = 0; p < nparts; ++p) {
+        ptc_step::FramePart& P = s->parts[s->profiling ? ptc_step::kMaxParts : p];
+        cudaStream_t st = s->profiling ? s->stream : P.stream;
+        const bool prefetch = s->overlap && !s->profiling;
+        cudaStream_t st0 = prefetch ? P.prefetch_stream : st;
+        FrameCounters* fc = s->d_fc + ((size_t)ring * ptc_step::kMaxParts + p);
+        if (prefetch) CK(cudaStreamWaitEvent(st0, P.primary_free, 0));      // the previous frame's shade(0) has consumed qp / d_hits_p
+        CK(cudaMemsetAsync(fc, 0, sizeof(FrameCounters), st0));
+        prof_mark(s, 0);
+        launch_raygen(st0, s->uniforms, P.qp, fc, P.n, nparts, p);
         prof_mark(s, 1);
-        launch_trace(s->stream, s->trace_grid, s->trace_impl, s->scene, s->q[seg & 1], s->d_hits, fc, seg, s->d_total_rays);
-        prof_mark(s, 2);
-        launch_shade(s->stream, s->shade_grid, s->scene, pc, s->q[seg & 1], s->q[(seg + 1) & 1], s->d_hits, fc, seg, s->planes, s->shq);
-        s->launches += 2;
-        if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(s->stream, s->trace_grid, s->scene, s->shq, s->q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
+        launch_trace(st0, s->trace_grid, s->trace_impl, s->scene, P.qp, P.d_hits_p, fc, 0, s->d_total_rays);
+        if (prefetch) { CK(cudaEventRecord(P.primary_done, st0)); CK(cudaStreamWaitEvent(st, P.primary_done, 0)); }
+        if (wait_main) CK(cudaStreamWaitEvent(st, s->ev_main, 0));
+        s->launches += 1;
+        for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
+            if (seg) { prof_mark(s, 1); launch_trace(st, s->trace_grid, s->trace_impl, s->scene, P.q[seg & 1], P.d_hits, fc, seg, s->d_total_rays); }
+            prof_mark(s, 2);
+            launch_shade(st, s->shade_grid, s->scene, pc, seg ? P.q[seg & 1] : P.qp, P.q[(seg + 1) & 1], seg ? P.d_hits : P.d_hits_p, fc, seg, s->planes, P.shq);
+            if (seg == 0 && prefetch) CK(cudaEventRecord(P.primary_free, st));
+            s->launches += 2;
+            // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
+            if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(st, s->trace_grid, s->scene, P.shq, P.q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
+        }
+        if (!s->profiling) { CK(cudaEventRecord(P.done, st)); CK(cudaStreamWaitEvent(s->stream, P.done, 0)); }
     }
     prof_mark(s, -1);
+    if (s->profiling) s->main_dirty = true;           // the next unprofiled frame's parts must wait for this one
     CK(cudaGetLastError());
     s->frames++;
     return PTC_OK;
@@ -491,6 +549,7 @@ PTC_API int ptc_reset_accumulation(ptc_step* s) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     CK(cudaMemsetAsync(s->planes.color, 0, (size_t)s->npix * 16, s->stream));
+    s->main_dirty = true;
     return PTC_OK;
 }
 
@@ -498,6 +557,7 @@ PTC_API int ptc_blit(ptc_step* s, const void* src_device_rgba32f) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     if (!s->d_display) CK(cudaMalloc(&s->d_display, (size_t)s->npix * 4));
+    s->main_dirty = true;
     launch_blit(s->stream, src_device_rgba32f ? (const F4*)src_device_rgba32f : s->planes.color, s->d_display, s->npix);
     s->launches += 1;
     CK(cudaGetLastError());
@@ -514,6 +574,7 @@ PTC_API int ptc_rayproject(ptc_step* s, const ptc_uniforms* prev, const ptc_unif
         CK(cudaMalloc(&s->d_reprojected, (size_t)s->npix * 16)); CK(cudaMalloc(&s->d_owner, (size_t)s->npix * 4));
         CK(cudaMemsetAsync(s->d_reprojected, 0, (size_t)s->npix * 16, s->stream)); CK(cudaMemsetAsync(s->d_owner, 0, (size_t)s->npix * 4, s->stream));
     }
+    s->main_dirty = true;
     launch_reproject(s->stream, cur->camera, prev->camera, s->planes.depth, s->d_owner, src_device_rgba32f ? (const F4*)src_device_rgba32f : s->planes.color, s->d_reprojected);
     s->launches += 2;
     CK(cudaGetLastError());
@@ -576,6 +637,7 @@ PTC_API int ptc_read_async(ptc_step* s, int plane, void* dst_pinned) {
         CK(cudaMalloc(&s->d_snapshot, bytes)); s->snapshot_bytes = bytes;
     }
     // the previous host copy must have drained the snapshot before it is overwritten
+    s->main_dirty = true;
     CK(cudaStreamWaitEvent(s->stream, s->copy_done, 0));
     CK(cudaMemcpyAsync(s->d_snapshot, src, bytes, cudaMemcpyDeviceToDevice, s->stream));
     CK(cudaEventRecord(s->snap_ready, s->stream));
@@ -607,7 +669,7 @@ PTC_API int ptc_get_stats(ptc_step* s, ptc_stats* out) {
     unsigned long long rays = 0;
     CK(cudaMemcpyAsync(&rays, s->d_total_rays, 8, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    out->rays_traced = rays; out->frames_rendered = s->frames; out->kernel_launches = s->launches;
+    out->rays_traced = rays; out->frames_rendered = s->frames; out->kernel_launches = s->launches; out->frame_parts = s->num_parts;
     return PTC_OK;
 }
 
@@ -615,6 +677,11 @@ PTC_API int ptc_set_profiling(ptc_step* s, int enable) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     prof_collect(s);
+    if (enable && s->parts[ptc_step::kMaxParts].n == 0) {
+        CK(cudaStreamSynchronize(s->stream));
+        int rc = alloc_part(s, s->parts[ptc_step::kMaxParts], s->npix);
+        if (rc != PTC_OK) return rc;
+    }
     s->profiling = enable != 0;
     for (int k = 0; k < 3; ++k) { s->prof_ms[k] = 0.0; s->prof_n[k] = 0; }
     return PTC_OK;
@@ -760,6 +827,7 @@ PTC_API int ptc_reduce(ptc_step* s, void* nccl_comm, int root) {
     if (!bind_nccl()) { set_error("ptc_reduce: no NCCL (libnccl.so.2) loaded or loadable in this process"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     const int kNcclFloat32 = 7, kNcclSum = 0;                     // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
+    s->main_dirty = true;
     int r = g_nccl_reduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
     if (r != 0) { set_error(std::string("ncclReduce: ") + (g_nccl_errstr ? g_nccl_errstr(r) : "error")); return PTC_ERR_CUDA; }
     return PTC_OK;
