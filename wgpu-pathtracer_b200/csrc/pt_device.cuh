@@ -143,7 +143,10 @@ PT_HD uint32_t rng_next_u32(uint32_t& state) {
     uint32_t word = ((s >> ((s >> 28) + 4u)) ^ s) * 277803737u;
     return (word >> 22) ^ word;
 }
-PT_HD float rng_next_f32(uint32_t& state) { return pt_div(pt_u32_to_f32(rng_next_u32(state)), 4294967296.0f); }
+// f32(u) / f32(0xffffffff) = rn(u) / 2^32 (random.wgsl:34-36).  Scaling by a power of two is exact (no underflow: the
+// smallest non-zero value is 2^-32), so the multiplication IS the division bit for bit — minus the ~10 instructions
+// of an IEEE divide, 5-7 times per hit.  (The oracle keeps the division; the parity tests compare the two.)
+PT_HD float rng_next_f32(uint32_t& state) { return pt_u32_to_f32(rng_next_u32(state)) * 2.3283064365386963e-10f; }
 PT_HD uint32_t rng_seed(uint32_t x, uint32_t y, uint32_t width, uint32_t frame) {
     return rng_jenkins(((x + y * width) * 1u) ^ rng_jenkins(frame));
 }
@@ -351,8 +354,13 @@ PT_HD void fetch_quad(const DevScene& s, const TexDev& t, int x0, int x1, int y0
     const float fx0 = (float)(t.ax + (uint32_t)x0) + 0.5f, fx1 = (float)(t.ax + (uint32_t)x1) + 0.5f;
     const float fy0 = (float)(t.ay + (uint32_t)y0) + 0.5f, fy1 = (float)(t.ay + (uint32_t)y1) + 0.5f;
     float4 pa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), pb = pa, pc = pa, pd = pa;
-    for (uint32_t p = 0; p < s.num_pages; ++p) {             // uniform trip count, uniform handle
-        if (t.page == p) {
+    // Fully unrolled over the page slots so that every handle is read at a LITERAL index of the kernel-parameter
+    // array: with a run-time trip count the compiler rewrote `if (t.page == p) .. page_obj[p]` into page_obj[t.page] —
+    // a per-lane handle after all, and each TEX became an R2UR / BRA.U.ANY loop over the warp's distinct handles
+    // (120 R2UR + 369 PLOP3 in k_shade's SASS).
+#pragma unroll
+    for (uint32_t p = 0; p < PTC_MAX_TEX_PAGES; ++p) {
+        if (p < s.num_pages && t.page == p) {
             const cudaTextureObject_t obj = (cudaTextureObject_t)s.page_obj[p];
             pa = tex2D<float4>(obj, fx0, fy0); pb = tex2D<float4>(obj, fx1, fy0);
             pc = tex2D<float4>(obj, fx0, fy1); pd = tex2D<float4>(obj, fx1, fy1);
