@@ -3,7 +3,10 @@
 
 namespace ptc {
 
-constexpr int kTraceThreads = 128;
+#ifndef PTC_TRACE_THREADS
+#define PTC_TRACE_THREADS 64            // 2 warps per CTA: a CTA's SM slot is released as soon as both are done (128: -0.8 %, 256: -2.3 %)
+#endif
+constexpr int kTraceThreads = PTC_TRACE_THREADS;
 constexpr int kShadeThreads = 128;
 #ifndef PTC_SHADE_MIN_BLOCKS
 #define PTC_SHADE_MIN_BLOCKS 8            // <= 64 registers: 32 resident warps per SM to cover the gather latency
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, cons
 #define PTC_REFILL_VOTE 16
 #endif
 #ifndef PTC_TRACE_MIN_BLOCKS
-#define PTC_TRACE_MIN_BLOCKS 10          // 48 registers (8 bytes spilled): 40 resident warps per SM; 9 (56 registers) measured 0.6-2 % slower
+#define PTC_TRACE_MIN_BLOCKS 20          // x 64 threads: 48 registers (8 bytes spilled), 40 resident warps per SM; 36 warps at 56 registers measured 0.6-2 % slower
 #endif
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
@@ -164,7 +167,15 @@ __global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(D
             continue;
         }
         const uint32_t at_leaf = __ballot_sync(FULL, node < 0);
-        if (__popc(at_leaf) >= PTC_TRI_VOTE || (at_leaf | idle) == FULL) {
+#ifdef PTC_TRI_VOTE_FIXED
+        const uint32_t tri_vote = PTC_TRI_VOTE;
+#else
+        // the vote scales with the live lanes (a quarter of them): in a thinly populated warp — the tail of a launch, when the
+        // cursor is exhausted and every remaining ray's latency is the launch's latency — a lane must not wait at a leaf for
+        // seven others that will never come
+        const uint32_t tri_vote = max(1u, min((uint32_t)PTC_TRI_VOTE, (32u - (uint32_t)__popc(idle)) >> 2));
+#endif
+        if ((uint32_t)__popc(at_leaf) >= tri_vote || (at_leaf | idle) == FULL) {
             // ---- triangle phase: one triangle per waiting lane ----
 #pragma unroll 1
             for (;;) {
