@@ -473,3 +473,30 @@ def test_ptc_reduce_binds_process_nccl(ptc, standins):
         step.destroy()
     finally:
         dist.destroy_process_group()
+
+
+def test_frame_parts_do_not_change_the_image(ptc, standins, oracle, monkeypatch):
+    """A frame is dealt warp by warp to several concurrent wavefronts (frame parts, pt_step.cu): whatever the number of
+    parts — and with a frame size that leaves partial tiles and a partial last warp — every plane equals the oracle's."""
+    T = ptc.types
+    scene, cam = standins.random_soup(6000, seed=3, textured=True)
+    W, H, frames = 333, 217, 3                                            # 72 261 pixels: not a multiple of 8, 4 or 32
+    cfg = ptc.make_config(W, H, max_bounces=5)
+    camera = standins.make_camera(cam, W, H)
+    orc = oracle.OracleScene(scene, cfg)
+    ref = None
+    for f in range(1, frames + 1):
+        ref = orc.render_frame(camera.uniforms(frame=f), None if ref is None else ref["color"])
+    seen = set()
+    for parts in ("1", "2", "3", "5", "8"):
+        monkeypatch.setenv("PTC_PARTS", parts)
+        step = ptc.RTStep.create(scene, cfg)
+        for f in range(1, frames + 1):
+            step.update(camera.uniforms(frame=f)); step.render()
+            if f == 2:
+                step.blit(); step.read(T.PLANE_DISPLAY)                   # work on the ordering stream between frames
+        step.poll(True)
+        seen.add(step.stats()["frame_parts"])
+        check_all_planes(ptc, step, ref)
+        step.destroy()
+    assert seen == {1, 2, 3, 5, 8}

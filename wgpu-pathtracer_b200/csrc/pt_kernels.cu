@@ -7,9 +7,12 @@ namespace ptc {
 #define PTC_TRACE_THREADS 64            // 2 warps per CTA: a CTA's SM slot is released as soon as both are done (128: -0.8 %, 256: -2.3 %)
 #endif
 constexpr int kTraceThreads = PTC_TRACE_THREADS;
-constexpr int kShadeThreads = 128;
+#ifndef PTC_SHADE_THREADS
+#define PTC_SHADE_THREADS 64
+#endif
+constexpr int kShadeThreads = PTC_SHADE_THREADS;
 #ifndef PTC_SHADE_MIN_BLOCKS
-#define PTC_SHADE_MIN_BLOCKS 8            // <= 64 registers: 32 resident warps per SM to cover the gather latency
+#define PTC_SHADE_MIN_BLOCKS 16           // x 64 threads, <= 64 registers: 32 resident warps per SM to cover the gather latency
 #endif
 
 // ---- raygen: rand_init + primary ray (pathtracer.wgsl:27, pathtracer/pathtracer.wgsl:240-250) ----
