@@ -335,10 +335,17 @@ def main():
     stage_total = sum(v["ms"] for v in prof.values())
     achieved = bytes_per_ray * rank_rays / (trace_ms * 1e-3) / 1e9 if (base and trace_ms > 0) else None
     bvh = step.bvh_info()
-    traffic = None                                          # dram bytes per k_trace launch from the committed ncu --set full capture
+    traffic = l2_traffic = None                             # dram / L2 bytes per k_trace launch from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "trace_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
+        tj = json.load(open(tp)).get(args.workload, {})
+        traffic, l2_traffic = tj.get("dram_bytes_per_launch"), tj.get("l2_bytes_per_launch")
+    # second denominator: the BVH of every configuration but San Miguel is L2-resident, so the traversal's memory
+    # ceiling is the L2, measured live with a streaming read of a 32 MiB resident buffer
+    import ctypes
+    l2_peak = ctypes.c_double(0.0)
+    if pkg.lib().ptc_debug_l2_bandwidth(local, 32 << 20, 400, ctypes.byref(l2_peak)) != 0:
+        l2_peak = None
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -360,6 +367,12 @@ def main():
                      "frac": achieved / peak if achieved is not None else None, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                      "rays_per_launch": rank_rays / max(trace_n, 1), "avg_launch_ms": trace_ms / max(trace_n, 1), "launches": int(trace_n),
+                     "l2": {"peak_gbs": l2_peak.value if l2_peak is not None else None,
+                            "peak_how": "measured live: ptc_debug_l2_bandwidth, 32 MiB resident buffer read 400 times with ld.global.cg.v4",
+                            "frac_of_l2_peak": (achieved / l2_peak.value) if (achieved is not None and l2_peak is not None and l2_peak.value > 0) else None,
+                            "traffic": l2_traffic,
+                            "achieved_gbs": (l2_traffic / (trace_ms / max(trace_n, 1) * 1e-3) / 1e9) if (l2_traffic and trace_n) else None,
+                            "note": "frac_of_l2_peak = the same algorithmic GB/s against the L2 ceiling; traffic = lts__t_sectors.sum x 32 B per whole-frame k_trace launch (ncu --set full, profiles/), achieved_gbs = that over the live launch duration"},
                      "kernel_share_of_step": trace_ms / stage_total if stage_total > 0 else None,
                      "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_pass_steps": P,
                      "note": "stage times from a separate pass with stage timing on: the frame runs as ONE wavefront on one stream (no frame parts, no primary-ray prefetch), "

@@ -158,6 +158,11 @@ PTC_API int ptc_debug_sample(ptc_step* step, int texture_index, const float* in,
  * equals i/255 rounded to nearest, the reference's to_rgba32f, texture.rs:241), 0 when it divides in the kernel, < 0 on error. */
 PTC_API int ptc_debug_unorm8(int cuda_device, float* out512);
 
+/* measured L2 read bandwidth of the device in GB/s: a persistent grid streams an L2-resident buffer (`bytes`, e.g. 32 MiB
+ * on a 126 MB L2) `iters` times with 128-bit loads; CUDA-event timed.  The second denominator of the traversal roofline:
+ * every configuration but San Miguel keeps its BVH in L2. */
+PTC_API int ptc_debug_l2_bandwidth(int cuda_device, uint64_t bytes, uint32_t iters, double* gbs);
+
 PTC_API const char* ptc_last_error(void);
 PTC_API const char* ptc_version(void);
 PTC_API int ptc_device_count(void);

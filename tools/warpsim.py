@@ -47,10 +47,7 @@ def main():
     cfg = ptc.make_config(W, H)
     es = emu.scene(scene, cfg)
     un = st.make_camera(cam, W, H).uniforms(frame=1)
-    policies = [("current", dict(policy=0, tri_vote=10, refill_vote=16))]
-    import itertools
-    for ni, ti, tv, rv in itertools.product((8, 12, 16), (0, 4, 8), (8, 12, 16), (12, 16, 22)):
-        policies.append((f"n{ni} t{ti} tv{tv} rv{rv}", dict(policy=0, tri_vote=tv, refill_vote=rv, node_inner=ni, tri_inner=ti)))
+    policies = [("fixed vote", dict(policy=0, tri_vote=8, refill_vote=16, node_inner=12, tri_inner=8))]
     for seg in segs:
         buf = np.zeros((W * H, 8), np.float32)
         n = int(L.emu_collect_rays(es._h, C.byref(un), seg, buf.ctypes.data_as(C.c_void_p), W * H))
@@ -59,6 +56,18 @@ def main():
         orders = [("scanline", rays)]
         if seg == 0:
             orders.append(("tile8x4", np.ascontiguousarray(rays[tile_order(W, H)])))
+        else:
+            octant = (rays[:, 4] < 0).astype(np.int64) * 4 + (rays[:, 5] < 0) * 2 + (rays[:, 6] < 0)
+            orders.append(("binned by direction octant", np.ascontiguousarray(rays[np.argsort(octant, kind="stable")])))
+            # a spatial sort of the origins (Morton order on a 2^7 grid), then octant
+            lo, hi = rays[:, :3].min(0), rays[:, :3].max(0)
+            q = np.clip(((rays[:, :3] - lo) / np.maximum(hi - lo, 1e-9) * 128).astype(np.int64), 0, 127)
+            m = np.zeros(len(rays), np.int64)
+            for b in range(7):
+                for a in range(3):
+                    m |= ((q[:, a] >> b) & 1) << (3 * b + a)
+            orders.append(("Morton(origin) sort", np.ascontiguousarray(rays[np.argsort(m, kind="stable")])))
+            orders.append(("octant, then Morton(origin)", np.ascontiguousarray(rays[np.lexsort((m, octant))])))
         for oname, r in orders:
             print(f"== {name} {W}x{H} segment {seg}: {n} rays, order {oname}")
             base = None

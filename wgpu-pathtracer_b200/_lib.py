@@ -59,6 +59,7 @@ def lib():
         "ptc_trace_rays_any": (i32, [vp, vp, u64, vp]),
         "ptc_debug_math": (i32, [i32, i32, vp, vp, vp, u64]),
         "ptc_debug_unorm8": (i32, [i32, vp]),
+        "ptc_debug_l2_bandwidth": (i32, [i32, u64, C.c_uint32, P(C.c_double)]),
         "ptc_debug_sample": (i32, [vp, i32, vp, u64, vp, i32]),
         "ptc_last_error": (C.c_char_p, []),
         "ptc_version": (C.c_char_p, []),

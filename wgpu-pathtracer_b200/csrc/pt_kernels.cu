@@ -412,6 +412,23 @@ void launch_blit(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n) {
     k_blit<<<(n + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<uchar4*>(dst_rgba8), n);
 }
 
+// ---- L2 read-bandwidth probe: a persistent grid streams an L2-resident buffer `iters` times (ld.global.cg: L2, not L1) ----
+__global__ void __launch_bounds__(256) k_l2_read(const float4* __restrict__ buf, uint64_t n16, uint32_t iters, float* sink) {
+    float acc = 0.0f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t it = 0; it < iters; ++it)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            float4 v;
+            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(buf + i));   // L2, not L1
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 123456.789f) *sink = acc;      // keeps the loads alive
+}
+void launch_l2_read(cudaStream_t st, int device, const void* buf, uint64_t bytes, uint32_t iters, float* sink) {
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    k_l2_read<<<(sms > 0 ? sms : 1) * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(buf), bytes / 16, iters, sink);
+}
+
 // ---- sample_tex / sky on caller-supplied coordinates (unit-test entry) ------------------------------------------------
 __global__ void k_sample(DevScene s, uint32_t tex, int sky, const float* __restrict__ in, float* __restrict__ out, uint32_t n, uint32_t tex_mod) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

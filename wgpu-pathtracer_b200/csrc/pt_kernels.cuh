@@ -64,6 +64,7 @@ void launch_reproject(cudaStream_t st, const ptc_camera& cam, const ptc_camera& 
 void launch_blit(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n);
 void launch_unorm_probe(cudaStream_t st, unsigned long long tex_obj, float* out512);   // x and w channels of a 256x1 RGBA8 ramp
 void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, const float* in, float* out, uint32_t n, uint32_t tex_mod);
+void launch_l2_read(cudaStream_t st, int device, const void* buf, uint64_t bytes, uint32_t iters, float* sink);   // L2 bandwidth probe
 void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n);
 
 int trace_grid_size(int device, int impl);   // impl 0 = k_trace (warp-cooperative), 1 = k_trace_simple

@@ -833,6 +833,29 @@ PTC_API int ptc_reduce(ptc_step* s, void* nccl_comm, int root) {
     return PTC_OK;
 }
 
+PTC_API int ptc_debug_l2_bandwidth(int cuda_device, uint64_t bytes, uint32_t iters, double* gbs) {
+    if (!gbs || bytes < 4096 || iters == 0) { set_error("bad argument"); return PTC_ERR_INVALID; }
+    if (ptc_device_count() <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
+    CK(cudaSetDevice(cuda_device));
+    bytes &= ~(uint64_t)15;
+    void* buf = nullptr; float* sink = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = PTC_OK; float ms = 0.0f;
+    do {
+        if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) { rc = PTC_ERR_OOM; set_error("l2 probe: allocation failed"); break; }
+        if (cudaMemset(buf, 0, bytes) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { rc = PTC_ERR_CUDA; set_error("l2 probe: setup failed"); break; }
+        launch_l2_read(nullptr, cuda_device, buf, bytes, 2, sink);                 // warm-up: brings the buffer into L2
+        cudaEventRecord(e0, nullptr);
+        launch_l2_read(nullptr, cuda_device, buf, bytes, iters, sink);
+        cudaEventRecord(e1, nullptr);
+        if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) { rc = PTC_ERR_CUDA; set_error("l2 probe: kernel failed"); break; }
+        *gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    return rc;
+}
+
 static uint64_t fnv1a(const void* p, size_t n) {
     const unsigned char* b = (const unsigned char*)p;
     uint64_t h = 1469598103934665603ull;

@@ -3,9 +3,29 @@
 #include "pt_error.h"
 #include "lbvh.cuh"
 
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 namespace ptc {
+
+// f(begin, end) over [0, n) on the host threads (scene preparation is per-triangle work on up to ~10^7 triangles)
+template <class F>
+static void parallel_for(uint64_t n, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (n < 65536 || nt == 1) { f((uint64_t)0, n); return; }
+    nt = (unsigned)std::min<uint64_t>(nt, 32);
+    std::vector<std::thread> th;
+    const uint64_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const uint64_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
 
 static void texel_of(const ptc_texture_desc& t, float out[4]) {   // the (0,0) texel as sample_texture_* sees it
     if (t.format == PTC_TEXEL_RGBA8) {
@@ -26,8 +46,13 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
     if (cfg.env_texture_index >= v->num_textures) { set_error("env_texture_index out of range"); return PTC_ERR_INVALID; }
     const uint32_t ntri = (uint32_t)ntri64;
     out.num_tris = ntri;
-    for (uint64_t i = 0; i < v->num_indices; ++i)
-        if (v->indices[i] >= v->num_vertices) { set_error("vertex index out of range"); return PTC_ERR_INVALID; }
+    {
+        std::atomic<bool> bad(false);
+        parallel_for(v->num_indices, [&](uint64_t b, uint64_t e) {
+            for (uint64_t i = b; i < e; ++i) if (v->indices[i] >= v->num_vertices) { bad = true; return; }
+        });
+        if (bad) { set_error("vertex index out of range"); return PTC_ERR_INVALID; }
+    }
     for (uint64_t i = 0; i < v->num_textures; ++i) {
         const ptc_texture_desc& t = v->textures[i];
         if (!t.texels || t.width == 0 || t.height == 0 || t.format > PTC_TEXEL_RGBA32F) { set_error("texture " + std::to_string(i) + " has no texels"); return PTC_ERR_INVALID; }
@@ -45,8 +70,10 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
 
     // BVH over every triangle
     std::vector<float> pos((size_t)ntri * 9);
-    for (uint32_t t = 0; t < ntri; ++t)
-        for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], v->vertices[v->indices[(size_t)t * 3 + k]].position, 12);
+    parallel_for(ntri, [&](uint64_t b, uint64_t e) {
+        for (uint64_t t = b; t < e; ++t)
+            for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], v->vertices[v->indices[(size_t)t * 3 + k]].position, 12);
+    });
     const bool lbvh = cfg.bvh_build == PTC_BVH_LBVH_DEVICE && ntri > PTC_LBVH_MAX_LEAF;
     if (lbvh && caller_builds_bvh) out.tri_pos = pos;
     else {
@@ -65,16 +92,18 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
 
     // per-triangle shading records: re-pack of vertices[] / indices[] / instance_infos[] (rt_helpers.wgsl:57-67)
     out.shade.resize(ntri);
-    for (uint32_t t = 0; t < ntri; ++t) {
-        const ptc_vertex* vx[3];
-        for (int k = 0; k < 3; ++k) vx[k] = &v->vertices[v->indices[(size_t)t * 3 + k]];
-        uint32_t mat = v->meshes[out.tri_mesh[t]].material_index;
-        TriShade& r = out.shade[t];
-        r.q[0] = F4{vx[0]->normal[0], vx[0]->normal[1], vx[0]->normal[2], vx[0]->uv[0]};
-        r.q[1] = F4{vx[1]->normal[0], vx[1]->normal[1], vx[1]->normal[2], vx[0]->uv[1]};
-        r.q[2] = F4{vx[2]->normal[0], vx[2]->normal[1], vx[2]->normal[2], vx[1]->uv[0]};
-        r.q[3] = F4{vx[1]->uv[1], vx[2]->uv[0], vx[2]->uv[1], u2f(mat)};
-    }
+    parallel_for(ntri, [&](uint64_t b, uint64_t e) {
+        for (uint64_t t = b; t < e; ++t) {
+            const ptc_vertex* vx[3];
+            for (int k = 0; k < 3; ++k) vx[k] = &v->vertices[v->indices[(size_t)t * 3 + k]];
+            uint32_t mat = v->meshes[out.tri_mesh[t]].material_index;
+            TriShade& r = out.shade[t];
+            r.q[0] = F4{vx[0]->normal[0], vx[0]->normal[1], vx[0]->normal[2], vx[0]->uv[0]};
+            r.q[1] = F4{vx[1]->normal[0], vx[1]->normal[1], vx[1]->normal[2], vx[0]->uv[1]};
+            r.q[2] = F4{vx[2]->normal[0], vx[2]->normal[1], vx[2]->normal[2], vx[1]->uv[0]};
+            r.q[3] = F4{vx[1]->uv[1], vx[2]->uv[0], vx[2]->uv[1], u2f(mat)};
+        }
+    });
 
     // materials: 1x1 textures folded to constants (sample_material, rt_helpers.wgsl:17-42)
     out.mats.resize(v->num_materials);
