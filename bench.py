@@ -194,6 +194,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines go to stderr: stdout carries the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
