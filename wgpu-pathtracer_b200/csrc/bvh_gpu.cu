@@ -1,5 +1,5 @@
 // bvh_gpu.cu — linear BVH build on the device: Morton keys -> radix sort (CUB) -> Karras radix tree ->
-// bottom-up box fit -> leaf collapse (<= 4 triangles) -> quantised 32-byte nodes + leaf-ordered triangles, i.e. exactly
+// bottom-up box fit -> leaf collapse (<= PTC_LBVH_MAX_LEAF triangles) -> quantised 32-byte nodes + leaf-ordered triangles, i.e. exactly
 // the arrays k_trace consumes (bvh_build.h), without the scene's geometry making a second trip through the host.
 // Per-element arithmetic lives in lbvh.cuh and is restated for the host in bvh_build.cpp (build_lbvh_host), which the
 // CPU-only tests run and against which tests/test_gpu_parity.py compares these kernels' output word for word.

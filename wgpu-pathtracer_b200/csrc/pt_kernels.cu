@@ -116,8 +116,14 @@ constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 // ANY (PTC_LIGHTS_MIS shadow rays): the same scheduler with an any-hit early-out — ray_d.w is the far end of the
 // segment, the first accepted triangle retires the lane, and a ray that found nothing adds `contrib[ray]` to the
 // accumulated colour of its path (`acc`, indexed by the slot in ray_o.w; at most one shadow ray per slot per launch).
-template <bool ANY>
-__global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+// MINB: resident CTAs per SM the register allocation is held to.  PTC_TRACE_MIN_BLOCKS (48 registers, 40 warps per SM) is
+// fastest while the BVH lives in L2; PTC_TRACE_MIN_BLOCKS_DENSE (40 registers and a few spills, 48 warps) wins +3 % when
+// traversal waits on HBM (San Miguel: 900 MB of nodes and triangles) and loses 2-4 % otherwise — the step picks by BVH size.
+#ifndef PTC_TRACE_MIN_BLOCKS_DENSE
+#define PTC_TRACE_MIN_BLOCKS_DENSE 24
+#endif
+template <bool ANY, int MINB>
+__global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
                                                           U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
                                                           uint32_t* cursor, unsigned long long* total_rays,
                                                           const F4* __restrict__ contrib, F4* __restrict__ acc) {
@@ -319,7 +325,8 @@ void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounte
 }
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays) {
-    if (impl == 0) k_trace<false><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
+    if (impl == 0) k_trace<false, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
+    else if (impl == 2) k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
@@ -335,7 +342,7 @@ void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& c
 }
 void launch_trace_shadow(cudaStream_t st, int grid, const DevScene& s, ShadowQueue sh, F4* acc_next, FrameCounters* fc, uint32_t segment,
                          unsigned long long* total_rays) {
-    k_trace<true><<<grid, kTraceThreads, 0, st>>>(s, sh.ray_o, sh.ray_d, nullptr, &fc->shadow_count[segment], &fc->shadow_cursor[segment], total_rays,
+    k_trace<true, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, sh.ray_o, sh.ray_d, nullptr, &fc->shadow_count[segment], &fc->shadow_cursor[segment], total_rays,
                                                   sh.contrib, acc_next);
 }
 
@@ -344,7 +351,8 @@ __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, const F4* ray_o, const F4* ray_d, U4* hits, uint32_t n, uint32_t* cursor) {
     // cursor[0] = work cursor (zeroed by caller), cursor[1] = count
     k_set_u32<<<1, 1, 0, st>>>(cursor + 1, n);
-    if (impl == 0) k_trace<false><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
+    if (impl == 0) k_trace<false, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
+    else if (impl == 2) k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
 }
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor) {
@@ -457,7 +465,10 @@ static int persistent_grid(const void* kernel, int threads, int device) {
     if (sms < 1) sms = 1;
     return sms * per_sm;          // a multiple of the SM count (148 on B200): every SM holds its full share of resident CTAs
 }
-int trace_grid_size(int device, int impl) { return persistent_grid(impl == 0 ? (const void*)k_trace<false> : (const void*)k_trace_simple, kTraceThreads, device); }
+int trace_grid_size(int device, int impl) {
+    const void* k = impl == 0 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS> : impl == 2 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE> : (const void*)k_trace_simple;
+    return persistent_grid(k, kTraceThreads, device);
+}
 int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false, false>, kShadeThreads, device); }
 
 }  // namespace ptc

@@ -67,7 +67,7 @@ void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, co
 void launch_l2_read(cudaStream_t st, int device, const void* buf, uint64_t bytes, uint32_t iters, float* sink);   // L2 bandwidth probe
 void launch_math(cudaStream_t st, int fn, const float* a, const float* b, float* out, uint32_t n);
 
-int trace_grid_size(int device, int impl);   // impl 0 = k_trace (warp-cooperative), 1 = k_trace_simple
+int trace_grid_size(int device, int impl);   // impl 0 = k_trace (48 registers), 1 = k_trace_simple, 2 = k_trace held to 40 registers (HBM-resident BVHs)
 int shade_grid_size(int device);
 
 }  // namespace ptc

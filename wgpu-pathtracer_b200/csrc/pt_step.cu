@@ -443,7 +443,13 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
         if ((rc = alloc_frame_buffers(s, config->width, config->height)) != PTC_OK) break;
         if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing * ptc_step::kMaxParts) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
         cudaMemsetAsync(s->d_total_rays, 0, 8, s->stream);
-        { const char* e = getenv("PTC_TRACE_IMPL"); s->trace_impl = (e && std::strcmp(e, "simple") == 0) ? 1 : 0; }
+        {   // traversal kernel variant: by BVH size (pt_kernels.cu), PTC_TRACE_IMPL = simple | std | dense overrides (A/B timing)
+            const char* e = getenv("PTC_TRACE_IMPL");
+            s->trace_impl = (s->bvh_info[2] + s->bvh_info[3]) > (96ull << 20) ? 2 : 0;
+            if (e && std::strcmp(e, "simple") == 0) s->trace_impl = 1;
+            if (e && std::strcmp(e, "std") == 0) s->trace_impl = 0;
+            if (e && std::strcmp(e, "dense") == 0) s->trace_impl = 2;
+        }
         s->trace_grid = trace_grid_size(cuda_device, s->trace_impl);
         s->shade_grid = shade_grid_size(cuda_device);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
