@@ -235,7 +235,9 @@ PT_HD void pt_bilinear_axis(float u, int n, int* i0, int* i1, float* f) {
     float fl = pt_floor(x);
     *f = x - fl;
     int i = (int)fl;
-    int a = i % n; if (a < 0) a += n;
+    int a;
+    if ((n & (n - 1)) == 0) a = i & (n - 1);        /* power-of-two size: the same residue (two's complement), without an integer division */
+    else { a = i % n; if (a < 0) a += n; }
     int b = a + 1; if (b >= n) b = 0;
     *i0 = a; *i1 = b;
 }

@@ -358,12 +358,20 @@ PT_HD void fetch_quad(const DevScene& s, const TexDev& t, int x0, int x1, int y0
     // array: with a run-time trip count the compiler rewrote `if (t.page == p) .. page_obj[p]` into page_obj[t.page] —
     // a per-lane handle after all, and each TEX became an R2UR / BRA.U.ANY loop over the warp's distinct handles
     // (120 R2UR + 369 PLOP3 in k_shade's SASS).
+    // A page no lane of the (converged part of the) warp needs is skipped by a uniform branch: predicated-off TEX
+    // instructions still cost their issue slots (ncu source page: 8 pages x 10 instructions per lookup before this).
+    const unsigned am = __activemask();
 #pragma unroll
     for (uint32_t p = 0; p < PTC_MAX_TEX_PAGES; ++p) {
-        if (p < s.num_pages && t.page == p) {
-            const cudaTextureObject_t obj = (cudaTextureObject_t)s.page_obj[p];
-            pa = tex2D<float4>(obj, fx0, fy0); pb = tex2D<float4>(obj, fx1, fy0);
-            pc = tex2D<float4>(obj, fx0, fy1); pd = tex2D<float4>(obj, fx1, fy1);
+        if (p < s.num_pages) {
+            const bool mine = t.page == p;
+            if (__ballot_sync(am, mine) != 0u) {
+                if (mine) {
+                    const cudaTextureObject_t obj = (cudaTextureObject_t)s.page_obj[p];
+                    pa = tex2D<float4>(obj, fx0, fy0); pb = tex2D<float4>(obj, fx1, fy0);
+                    pc = tex2D<float4>(obj, fx0, fy1); pd = tex2D<float4>(obj, fx1, fy1);
+                }
+            }
         }
     }
     a = pt_mk4(pa.x, pa.y, pa.z, pa.w); b = pt_mk4(pb.x, pb.y, pb.z, pb.w);
