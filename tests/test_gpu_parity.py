@@ -500,3 +500,25 @@ def test_frame_parts_do_not_change_the_image(ptc, standins, oracle, monkeypatch)
         check_all_planes(ptc, step, ref)
         step.destroy()
     assert seen == {1, 2, 3, 5, 8}
+
+
+def test_modes_combined_and_resize(ptc, standins, oracle):
+    """Light sampling + device-built LBVH + SUM accumulation together, then a resize to a frame size with a different number
+    of frame parts: still the oracle's image."""
+    T = ptc.types
+    scene, cam = standins.lit_room()
+    kw = dict(max_bounces=4, light_sampling=T.LIGHTS_MIS, bvh_build=T.BVH_LBVH_DEVICE, accum_mode=T.ACCUM_SUM)
+    step = ptc.RTStep.create(scene, ptc.make_config(400, 300, **kw))
+    for (W, H) in ((400, 300), (97, 61), (640, 360)):
+        step.resize(W, H)
+        camera = standins.make_camera(cam, W, H)
+        orc = oracle.OracleScene(scene, ptc.make_config(W, H, **kw))
+        ref = None
+        for f in (1, 2):
+            u = camera.uniforms(frame=f)
+            step.update(u); step.render()
+            ref = orc.render_frame(u, None if ref is None else ref["color"])
+        step.poll(True)
+        check_all_planes(ptc, step, ref)
+        assert (step.read(T.PLANE_COLOR)[..., 3] == 2).all()
+    step.destroy()

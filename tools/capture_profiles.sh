@@ -3,6 +3,7 @@
 # list of the bench command and one `ncu --set full` capture of the hot kernels.  usage: bash tools/capture_profiles.sh <tag>
 tag="$1"; out=gpurun_out/$tag; mkdir -p $out
 python -m pytest tests -m gpu -q 2>&1 | tail -5 > $out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1
 python bench.py > $out/bench_sponza_1080p.json 2> $out/bench_sponza_1080p.err
 python bench.py --impl reference --steps 4 --warmup 1 > $out/bench_reference_sponza_1080p.json 2>/dev/null
 for w in cornell_512:256 dragon_1080p:128 classroom_1080p:128 classroom_1080p_mis:64 san_miguel_4k:32; do
