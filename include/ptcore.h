@@ -91,6 +91,11 @@ PTC_API void ptc_destroy(ptc_step* step);
 /* synchronous device->host copy of one plane (enum ptc_plane) after all
  * enqueued frames; dst_pitch_bytes = 0 means tightly packed. */
 PTC_API int ptc_read(ptc_step* step, int plane, void* dst, size_t dst_pitch_bytes);
+/* the reverse for PTC_PLANE_COLOR: load an accumulation image (rgb mean or sum + sample count, as ptc_read returned it)
+ * after all enqueued frames.  Checkpoint / resume of a progressive render (the reference keeps its
+ * accumulation only in a GPU texture and cannot); continuing with the following frame numbers reproduces the uninterrupted
+ * run bit for bit.  src_pitch_bytes = 0 means tightly packed. */
+PTC_API int ptc_write(ptc_step* step, int plane, const void* src, size_t src_pitch_bytes);
 
 /* asynchronous variant for display / streaming: snapshots the plane on the
  * render stream (device->device), then copies the snapshot to `dst_pinned` on

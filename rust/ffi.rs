@@ -48,6 +48,12 @@ extern "C" {
     pub fn ptc_read_async(step: *mut ptc_step, plane: c_int, dst_pinned: *mut c_void) -> c_int;
     pub fn ptc_read_wait(step: *mut ptc_step) -> c_int;
     pub fn ptc_device_ptr(step: *mut ptc_step, plane: c_int) -> *mut c_void;
+    pub fn ptc_write(step: *mut ptc_step, plane: c_int, src: *const c_void, src_pitch_bytes: usize) -> c_int;          // checkpoint / resume
+    pub fn ptc_blit(step: *mut ptc_step, src_device_rgba32f: *const c_void) -> c_int;                                     // BlitStep::render
+    pub fn ptc_rayproject(step: *mut ptc_step, prev: *const crate::uniforms::Uniforms, cur: *const crate::uniforms::Uniforms,
+                          src_device_rgba32f: *const c_void) -> c_int;                                                  // RayprojectStep::render
+    pub fn ptc_reduce(step: *mut ptc_step, nccl_comm: *mut c_void, root: c_int) -> c_int;                                // multi-GPU image sum
+    pub fn ptc_stream(step: *mut ptc_step) -> *mut c_void;
     pub fn ptc_destroy(step: *mut ptc_step);
     pub fn ptc_last_error() -> *const c_char;
 }

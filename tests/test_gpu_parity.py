@@ -522,3 +522,31 @@ def test_modes_combined_and_resize(ptc, standins, oracle):
         check_all_planes(ptc, step, ref)
         assert (step.read(T.PLANE_COLOR)[..., 3] == 2).all()
     step.destroy()
+
+
+def test_checkpoint_resume_bit_exact(ptc, standins):
+    """ptc_write: a progressive render stopped after 2 frames, its accumulation image saved, loaded into a NEW step and
+    continued with frames 3-4, equals the uninterrupted 4-frame render bit for bit (running-mean and sum modes)."""
+    T = ptc.types
+    scene, cam = standins.cornell()
+    W, H = 160, 120
+    camera = standins.make_camera(cam, W, H)
+    for mode in (T.ACCUM_MEAN, T.ACCUM_SUM):
+        cfg = ptc.make_config(W, H, accum_mode=mode)
+        whole = ptc.RTStep.create(scene, cfg)
+        for f in (1, 2, 3, 4):
+            whole.update(camera.uniforms(frame=f)); whole.render()
+        first = ptc.RTStep.create(scene, cfg)
+        for f in (1, 2):
+            first.update(camera.uniforms(frame=f)); first.render()
+        saved = first.read(T.PLANE_COLOR)
+        first.destroy()
+        second = ptc.RTStep.create(scene, cfg)
+        second.write(saved)
+        for f in (3, 4):
+            second.update(camera.uniforms(frame=f)); second.render()
+        a, b = whole.read(T.PLANE_COLOR), second.read(T.PLANE_COLOR)
+        assert np.array_equal(a, b) and (a[..., 3] == 4).all()
+        with pytest.raises(ptc.PtcError):
+            second.write(saved, plane=T.PLANE_DEPTH)
+        whole.destroy(); second.destroy()

@@ -54,6 +54,7 @@ def lib():
         "ptc_num_lights": (i32, [vp, P(u32)]),
         "ptc_bvh_info": (i32, [vp, P(u64)]),
         "ptc_reduce": (i32, [vp, vp, i32]),
+        "ptc_write": (i32, [vp, i32, vp, C.c_size_t]),
         "ptc_debug_bvh_hash": (i32, [vp, P(u64)]),
         "ptc_trace_rays": (i32, [vp, vp, u64, vp, vp]),
         "ptc_trace_rays_any": (i32, [vp, vp, u64, vp]),

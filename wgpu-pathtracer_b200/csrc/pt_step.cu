@@ -602,6 +602,17 @@ static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
     return false;
 }
 
+PTC_API int ptc_write(ptc_step* s, int plane, const void* src, size_t pitch) {
+    if (!s || !src) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (plane != PTC_PLANE_COLOR) { set_error("ptc_write: only the accumulation plane (PTC_PLANE_COLOR) can be loaded"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    const size_t row = (size_t)s->cfg.width * 16;
+    s->main_dirty = true;
+    CK(cudaMemcpy2DAsync(s->planes.color, row, src, pitch ? pitch : row, row, s->cfg.height, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return PTC_OK;
+}
+
 PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
     if (!s || !dst) { set_error("null argument"); return PTC_ERR_INVALID; }
     void* src; size_t pb;

@@ -59,6 +59,12 @@ class RTStep:
     def set_output(self, device_ptr):
         check(lib().ptc_set_output(self._h, C.c_void_p(device_ptr) if device_ptr else None))
 
+    def write(self, image, plane=T.PLANE_COLOR):
+        """Load an accumulation image previously returned by read(PLANE_COLOR): checkpoint / resume (ptc_write)."""
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        assert image.shape == (self.config.height, self.config.width, 4)
+        check(lib().ptc_write(self._h, int(plane), image.ctypes.data_as(C.c_void_p), 0))
+
     def reduce(self, nccl_comm, root=0):
         """Sum the per-rank SUM-mode accumulation buffers into `root` with one ncclReduce on the step's stream (ptc_reduce).
         nccl_comm: the ncclComm_t as an integer (e.g. torch's ProcessGroupNCCL._comm_ptr())."""
