@@ -165,3 +165,55 @@ def test_load_obj_from_files_with_real_texture_decode(ptc, standins, tmp_path):
     r = sc.textures[11]
     assert r.texels.dtype == np.float32
     np.testing.assert_allclose(r.texels[1, 0], [4 * 4096 / 65535.0] * 3 + [1.0], rtol=1e-6)   # 16-bit -> /65535, grey -> rgb
+
+
+def _scene_arrays(sc):
+    return (sc.vertices.tobytes(), sc.indices.tobytes(), sc.meshes.tobytes(), sc.materials.tobytes())
+
+
+@pytest.mark.parametrize("chunk", [16, 37, 64, 200])
+def test_parallel_obj_parse_is_chunk_invariant(ptc, standins, monkeypatch, chunk):
+    """The OBJ text is scanned in parallel chunks cut at line ends (pt_host.cpp).  Whatever the cut — here
+    every few lines: through object / usemtl boundaries, between a face and the vertices its negative indices refer to,
+    through n-gons — the scene equals the one parsed as a single chunk."""
+    rng = np.random.RandomState(5)
+    lines = ["mtllib m.mtl", "# comment", "o first"]
+    nv = 0
+    for obj in range(6):
+        if obj:
+            lines.append(("o" if obj % 2 else "g") + f" part{obj}")
+        for blk in range(5):
+            k = int(rng.randint(3, 7))
+            for _ in range(k):
+                lines.append("v %.6g %.6g %.6g" % tuple(rng.uniform(-2, 2, 3)))
+                lines.append("vt %.6g %.6g" % tuple(rng.uniform(0, 1, 2)))
+                lines.append("vn %.6g %.6g %.6g" % tuple(rng.uniform(-1, 1, 3)))
+            nv += k
+            if blk % 2 == 0:
+                lines.append("usemtl " + "ab"[(obj + blk // 2) % 2])
+            lines.append("f " + " ".join(f"{-k + j}/{-k + j}/{-k + j}" for j in range(k)))              # relative n-gon
+            lines.append("f " + " ".join(f"{nv - k + j + 1}/{nv - k + j + 1}/{nv - k + j + 1}" for j in range(3)))   # absolute triangle
+            lines.append("   \t  ")
+            lines.append("l 1 2")
+    text = "\r\n".join(lines) + "\n"
+    scenes = []
+    for c in (None, chunk):
+        if c is None:
+            monkeypatch.delenv("PTC_OBJ_CHUNK_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("PTC_OBJ_CHUNK_BYTES", str(c))
+        sc = ptc.Scene(standins.make_envmap(8, 4))
+        sc.load_obj(obj_text=text, mtl_text=MTL, obj_dir="standin", decode=tiny_decode(ptc))
+        scenes.append(sc)
+    a, b = scenes
+    assert len(a.meshes) > 12 and _scene_arrays(a) == _scene_arrays(b)
+
+
+def test_obj_zero_and_plus_indices(ptc, standins):
+    """`0` in a vt / vn slot reads as absent (as the empty field does); in the v slot it is an error; `+3` is 3."""
+    base = "mtllib m.mtl\nusemtl a\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n"
+    sc = ptc.Scene(standins.make_envmap(8, 4))
+    sc.load_obj(obj_text=base + "f 1/0/1 +2//1 3/0/1\n", mtl_text=MTL, obj_dir="standin", decode=tiny_decode(ptc))
+    assert len(sc.indices) == 3
+    with pytest.raises(ptc.PtcError, match="bad face element"):
+        ptc.Scene(standins.make_envmap(8, 4)).load_obj(obj_text=base + "f 0 1 2\n", mtl_text=MTL, obj_dir="standin", decode=tiny_decode(ptc))

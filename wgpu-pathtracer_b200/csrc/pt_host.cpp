@@ -9,6 +9,9 @@
 #include "../../include/ptcore.h"
 #include "pt_error.h"
 
+#include <algorithm>
+#include <atomic>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +20,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -274,117 +278,264 @@ int parse_mtl(const std::string& text, std::vector<TobjMaterial>& mats, std::uno
 }
 
 // ---- tobj 4.0.3: OBJ ----------------------------------------------------------------------
-bool parse_index(const std::string& tok, size_t count, size_t* out) {
-    if (tok.empty()) { *out = kMissing; return true; }
-    char* end = nullptr; long long i = std::strtoll(tok.c_str(), &end, 10);
-    if (end == tok.c_str() || *end != '\0') return false;
-    if (i < 0) *out = (size_t)((long long)count + i); else *out = (size_t)(i - 1);
-    return true;
+// ---- OBJ parsing, in three passes (scene ingest at scale — the reference's tobj parse is serial) ----------
+//   1. the text is cut at line ends into one chunk per host thread; every chunk is scanned in place (no per-line strings):
+//      v / vt / vn values, face elements as written (1-based, or negative = relative to the count at that line), and the
+//      o / g / usemtl / mtllib lines as ordered events;
+//   2. one serial walk over the chunks' events turns them into models (tobj's split rules) — cheap, it touches no geometry;
+//   3. the models are exported in parallel: single_index de-duplication of (v, vt, vn) triples + triangulation per model.
+// The result is the same std::vector<TobjModel> the serial parser produced, in the same order.
+struct RawElem { long long v, vt, vn; };                 // 0 = absent
+struct RawFace { uint32_t first, count; uint32_t np, nt, nn; };   // elements [first, first+count) of the chunk; v/vt/vn counts of the chunk before this line
+struct ObjEvent { int kind; uint32_t face_pos; std::string arg; };  // kind 0 = o/g, 1 = usemtl, 2 = mtllib; face_pos = faces of the chunk before it
+struct ObjChunk {
+    const char *begin = nullptr, *end = nullptr;
+    std::vector<float> pos, tex, nrm;
+    std::vector<RawElem> elems;
+    std::vector<RawFace> faces;
+    std::vector<ObjEvent> events;
+    int err = PTC_OK; std::string msg;
+};
+struct ObjGlobal { std::vector<float> pos, tex, nrm; std::vector<size_t> pos_base, tex_base, nrm_base; };   // *_base[c] = elements before chunk c
+
+inline bool is_ws(char c) { return std::isspace((unsigned char)c) != 0; }
+
+// f32 token: the fast path (std::from_chars, correctly rounded like strtof) covers plain decimals; anything else goes through parse_f32
+bool parse_f32_tok(const char* a, const char* b, float* out) {
+    const char* p = a;
+    if (p < b && *p == '+') ++p;
+    bool plain = p < b;
+    for (const char* q = p; q < b && plain; ++q) plain = (*q >= '0' && *q <= '9') || *q == '.' || *q == '-' || *q == '+' || *q == 'e' || *q == 'E';
+    if (plain && !(p < b && (*p == '+'))) {
+        auto r = std::from_chars(p, b, *out);
+        if (r.ec == std::errc() && r.ptr == b) return true;
+    }
+    return parse_f32(std::string(a, b), out);
+}
+bool parse_index_tok(const char* a, const char* b, long long* out) {
+    if (a == b) { *out = 0; return true; }
+    const char* p = a;
+    if (*p == '+') ++p;                                   // strtoll accepts a leading '+'
+    long long v = 0;
+    auto r = std::from_chars(p, b, v);
+    if (r.ec != std::errc() || r.ptr != b || p == b) return false;
+    *out = v; return true;                                // "0" reads as absent, as an empty field does
 }
 
-struct ObjState {
-    std::vector<float> pos, tex, nrm;
-    std::vector<std::vector<VertKey>> faces;
-};
+void scan_chunk(ObjChunk& c) {
+    const char* p = c.begin;
+    std::vector<std::pair<const char*, const char*>> w;
+    while (p < c.end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(c.end - p));
+        if (!eol) eol = c.end;
+        const char *a = p, *b = eol;
+        p = eol < c.end ? eol + 1 : c.end;
+        while (a < b && is_ws(*a)) ++a;
+        while (b > a && is_ws(b[-1])) --b;
+        if (a == b || *a == '#') continue;
+        w.clear();
+        for (const char* q = a; q < b;) {
+            while (q < b && is_ws(*q)) ++q;
+            const char* t = q;
+            while (q < b && !is_ws(*q)) ++q;
+            if (q > t) w.emplace_back(t, q);
+        }
+        const size_t klen = (size_t)(w[0].second - w[0].first);
+        const char* k = w[0].first;
+        auto is = [&](const char* s) { return strlen(s) == klen && memcmp(k, s, klen) == 0; };
+        auto floats = [&](size_t n, std::vector<float>& dst) {
+            if (w.size() < 1 + n) return false;
+            float v[4];
+            for (size_t i = 0; i < n; ++i) if (!parse_f32_tok(w[1 + i].first, w[1 + i].second, &v[i])) return false;
+            dst.insert(dst.end(), v, v + n); return true;
+        };
+        auto fail = [&](const std::string& m) { c.err = PTC_ERR_PARSE; c.msg = m; };
+        if (is("v")) { if (!floats(3, c.pos)) { fail("OBJ: bad v"); return; } }
+        else if (is("vt")) { if (!floats(2, c.tex)) { fail("OBJ: bad vt"); return; } }
+        else if (is("vn")) { if (!floats(3, c.nrm)) { fail("OBJ: bad vn"); return; } }
+        else if (is("f") || is("l")) {
+            RawFace f; f.first = (uint32_t)c.elems.size(); f.count = 0;
+            f.np = (uint32_t)(c.pos.size() / 3); f.nt = (uint32_t)(c.tex.size() / 2); f.nn = (uint32_t)(c.nrm.size() / 3);
+            for (size_t i = 1; i < w.size(); ++i) {
+                const char *t = w[i].first, *te = w[i].second;
+                const char* part[3][2]; int np = 0;
+                for (const char* q = t;;) {
+                    const char* sl = (const char*)memchr(q, '/', (size_t)(te - q));
+                    part[np][0] = q; part[np][1] = sl ? sl : te; ++np;
+                    if (!sl || np == 3) break;
+                    q = sl + 1;
+                }
+                RawElem e{0, 0, 0};
+                bool ok = parse_index_tok(part[0][0], part[0][1], &e.v);
+                if (np > 1) ok = ok && parse_index_tok(part[1][0], part[1][1], &e.vt);
+                if (np > 2) ok = ok && parse_index_tok(part[2][0], part[2][1], &e.vn);
+                if (!ok || e.v == 0) { fail("OBJ: bad face element '" + std::string(t, te) + "'"); return; }
+                c.elems.push_back(e); f.count++;
+            }
+            if (f.count == 0) { fail("OBJ: empty face"); return; }
+            c.faces.push_back(f);
+        } else if (is("o") || is("g") || is("usemtl") || is("mtllib")) {
+            ObjEvent ev; ev.kind = (is("o") || is("g")) ? 0 : is("usemtl") ? 1 : 2;
+            ev.face_pos = (uint32_t)c.faces.size();
+            const char* r = k + klen;                      // rest of the (trimmed) line after the keyword, trimmed
+            while (r < b && is_ws(*r)) ++r;
+            ev.arg.assign(r, b);
+            c.events.push_back(std::move(ev));
+        }
+    }
+}
 
-int export_faces(const ObjState& st, bool has_mat, size_t mat_id, const std::string& name, std::vector<TobjModel>& models) {
-    TobjModel m; m.name = name; m.has_material = has_mat; m.material_id = mat_id;
+struct FaceSpan { uint32_t chunk, first, last; };        // faces [first, last) of a chunk
+struct ModelJob { std::string name; bool has_mat; size_t mat_id; std::vector<FaceSpan> spans; };
+
+int export_model(const std::vector<ObjChunk>& chunks, const ObjGlobal& g, const ModelJob& job, TobjModel& m, std::string& msg) {
+    m.name = job.name; m.has_material = job.has_mat; m.material_id = job.mat_id;
+    size_t nelem = 0;
+    for (const FaceSpan& sp : job.spans) for (uint32_t f = sp.first; f < sp.last; ++f) nelem += chunks[sp.chunk].faces[f].count;
     std::unordered_map<VertKey, uint32_t, VertKeyHash> index_map;
+    index_map.reserve(nelem / 2 + 16);
+    m.indices.reserve(nelem);
     int err = PTC_OK;
     auto add = [&](const VertKey& k) {
         auto it = index_map.find(k);
         if (it != index_map.end()) { m.indices.push_back(it->second); return; }
-        if (k.v == kMissing || k.v * 3 + 2 >= st.pos.size()) { err = PTC_ERR_PARSE; return; }
-        m.positions.insert(m.positions.end(), {st.pos[k.v * 3], st.pos[k.v * 3 + 1], st.pos[k.v * 3 + 2]});
-        if (!st.tex.empty() && k.vt != kMissing) {
-            if (k.vt * 2 + 1 >= st.tex.size()) { err = PTC_ERR_PARSE; return; }
-            m.texcoords.insert(m.texcoords.end(), {st.tex[k.vt * 2], st.tex[k.vt * 2 + 1]});
+        if (k.v == kMissing || k.v * 3 + 2 >= g.pos.size()) { err = PTC_ERR_PARSE; return; }
+        m.positions.insert(m.positions.end(), {g.pos[k.v * 3], g.pos[k.v * 3 + 1], g.pos[k.v * 3 + 2]});
+        if (!g.tex.empty() && k.vt != kMissing) {
+            if (k.vt * 2 + 1 >= g.tex.size()) { err = PTC_ERR_PARSE; return; }
+            m.texcoords.insert(m.texcoords.end(), {g.tex[k.vt * 2], g.tex[k.vt * 2 + 1]});
         }
-        if (!st.nrm.empty() && k.vn != kMissing) {
-            if (k.vn * 3 + 2 >= st.nrm.size()) { err = PTC_ERR_PARSE; return; }
-            m.normals.insert(m.normals.end(), {st.nrm[k.vn * 3], st.nrm[k.vn * 3 + 1], st.nrm[k.vn * 3 + 2]});
+        if (!g.nrm.empty() && k.vn != kMissing) {
+            if (k.vn * 3 + 2 >= g.nrm.size()) { err = PTC_ERR_PARSE; return; }
+            m.normals.insert(m.normals.end(), {g.nrm[k.vn * 3], g.nrm[k.vn * 3 + 1], g.nrm[k.vn * 3 + 2]});
         }
         uint32_t next = (uint32_t)index_map.size();
         m.indices.push_back(next); index_map.emplace(k, next);
     };
-    for (const auto& f : st.faces) {
-        if (f.size() < 3) continue;                                   // ignore_points, ignore_lines
-        if (f.size() == 3) { add(f[0]); add(f[1]); add(f[2]); }
-        else if (f.size() == 4) { add(f[0]); add(f[1]); add(f[2]); add(f[0]); add(f[2]); add(f[3]); }
-        else { const VertKey& a = f[0]; VertKey b = f[1]; for (size_t i = 2; i < f.size(); ++i) { add(a); add(b); add(f[i]); b = f[i]; } }
-        if (err != PTC_OK) { set_error("OBJ: face references a vertex out of bounds"); return err; }
+    std::vector<VertKey> face;
+    for (const FaceSpan& sp : job.spans) {
+        const ObjChunk& c = chunks[sp.chunk];
+        for (uint32_t fi = sp.first; fi < sp.last; ++fi) {
+            const RawFace& rf = c.faces[fi];
+            if (rf.count < 3) continue;                               // ignore_points, ignore_lines
+            face.clear();
+            auto resolve = [](long long raw, size_t count) -> size_t {  // 1-based, or relative to the elements seen so far
+                if (raw == 0) return kMissing;
+                return raw < 0 ? (size_t)((long long)count + raw) : (size_t)(raw - 1);
+            };
+            for (uint32_t e = 0; e < rf.count; ++e) {
+                const RawElem& re = c.elems[rf.first + e];
+                face.push_back(VertKey{resolve(re.v, g.pos_base[sp.chunk] + rf.np), resolve(re.vt, g.tex_base[sp.chunk] + rf.nt),
+                                       resolve(re.vn, g.nrm_base[sp.chunk] + rf.nn)});
+            }
+            if (face.size() == 3) { add(face[0]); add(face[1]); add(face[2]); }
+            else if (face.size() == 4) { add(face[0]); add(face[1]); add(face[2]); add(face[0]); add(face[2]); add(face[3]); }
+            else { const VertKey a = face[0]; VertKey b = face[1]; for (size_t i = 2; i < face.size(); ++i) { add(a); add(b); add(face[i]); b = face[i]; } }
+            if (err != PTC_OK) { msg = "OBJ: face references a vertex out of bounds"; return err; }
+        }
     }
-    models.push_back(std::move(m));
     return PTC_OK;
+}
+
+template <class F>
+void run_parallel(size_t n, F f) {                        // f(i) for i in [0, n), work-stealing over the host threads
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    nt = (unsigned)std::min<size_t>(std::min<size_t>(nt, 32), n);
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&] { for (;;) { size_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+    for (auto& x : th) x.join();
 }
 
 int parse_obj(const std::string& text, const std::string& mtl_override, bool use_override, const std::string& obj_dir,
               std::vector<TobjModel>& models, std::vector<TobjMaterial>& mats) {
-    std::unordered_map<std::string, size_t> mat_map;
-    ObjState st; std::string name = "unnamed_object";
-    bool has_mat = false; size_t mat_id = 0;
-    std::istringstream is(text); std::string raw;
-    bool saw_mtllib = false;
-    while (std::getline(is, raw)) {
-        std::string line = trim(raw);
-        std::vector<std::string> w = split_ws(line);
-        if (w.empty() || w[0][0] == '#') continue;
-        const std::string& k = w[0];
-        auto floats = [&](size_t n, std::vector<float>& dst) {
-            if (w.size() < 1 + n) return false;
-            float v[4];
-            for (size_t i = 0; i < n; ++i) if (!parse_f32(w[1 + i], &v[i])) return false;
-            dst.insert(dst.end(), v, v + n); return true;
-        };
-        if (k == "v") { if (!floats(3, st.pos)) { set_error("OBJ: bad v"); return PTC_ERR_PARSE; } }
-        else if (k == "vt") { if (!floats(2, st.tex)) { set_error("OBJ: bad vt"); return PTC_ERR_PARSE; } }
-        else if (k == "vn") { if (!floats(3, st.nrm)) { set_error("OBJ: bad vn"); return PTC_ERR_PARSE; } }
-        else if (k == "f" || k == "l") {
-            std::vector<VertKey> face;
-            for (size_t i = 1; i < w.size(); ++i) {
-                VertKey key{kMissing, kMissing, kMissing};
-                std::string parts[3]; int np = 0; size_t a = 0;
-                for (;;) { size_t b = w[i].find('/', a); parts[np++] = w[i].substr(a, b == std::string::npos ? std::string::npos : b - a); if (b == std::string::npos || np == 3) break; a = b + 1; }
-                bool ok = parse_index(parts[0], st.pos.size() / 3, &key.v);
-                if (np > 1) ok = ok && parse_index(parts[1], st.tex.size() / 2, &key.vt);
-                if (np > 2) ok = ok && parse_index(parts[2], st.nrm.size() / 3, &key.vn);
-                if (!ok || key.v == kMissing) { set_error("OBJ: bad face element '" + w[i] + "'"); return PTC_ERR_PARSE; }
-                face.push_back(key);
-            }
-            if (face.empty()) { set_error("OBJ: empty face"); return PTC_ERR_PARSE; }
-            st.faces.push_back(std::move(face));
-        } else if (k == "o" || k == "g") {
-            if (!st.faces.empty()) { int rc = export_faces(st, has_mat, mat_id, name, models); if (rc) return rc; st.faces.clear(); }
-            std::string rest = line.size() > k.size() ? trim(line.substr(k.size())) : std::string();
-            name = rest.empty() ? std::string("unnamed_object") : rest;
-        } else if (k == "mtllib") {
-            saw_mtllib = true;
-            std::string mtl_text;
-            if (use_override) mtl_text = mtl_override;
-            else {
-                std::string p = join_path(obj_dir, trim(line.substr(6)));
-                std::ifstream f(p, std::ios::binary);
-                if (!f) { set_error("Failed to load MTL " + p); return PTC_ERR_IO; }
-                std::stringstream ss; ss << f.rdbuf(); mtl_text = ss.str();
-            }
-            std::vector<TobjMaterial> loaded; std::unordered_map<std::string, size_t> lm;
-            int rc = parse_mtl(mtl_text, loaded, lm); if (rc) return rc;
-            size_t base = mats.size();
-            for (auto& kv : lm) mat_map[kv.first] = kv.second + base;
-            mats.insert(mats.end(), loaded.begin(), loaded.end());
-        } else if (k == "usemtl") {
-            std::string mname = trim(line.substr(6));
-            if (mname.empty()) { set_error("OBJ: usemtl without a name"); return PTC_ERR_PARSE; }
-            auto it = mat_map.find(mname);
-            bool new_has = it != mat_map.end(); size_t new_id = new_has ? it->second : 0;
-            bool differs = (new_has != has_mat) || (new_has && new_id != mat_id);
-            if (differs && !st.faces.empty()) { int rc = export_faces(st, has_mat, mat_id, name, models); if (rc) return rc; st.faces.clear(); }
-            has_mat = new_has; mat_id = new_id;
+    // pass 1: chunks cut at line ends, scanned in parallel
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    size_t chunk_bytes = 1u << 20;
+    if (const char* e = getenv("PTC_OBJ_CHUNK_BYTES")) { long v = atol(e); if (v >= 1) chunk_bytes = (size_t)v; }   // tests cut small files into many chunks
+    size_t nchunks = std::max<size_t>(1, std::min<size_t>(chunk_bytes < (1u << 20) ? 4096 : std::min<unsigned>(nt, 32) * 4, text.size() / chunk_bytes));
+    std::vector<ObjChunk> chunks(nchunks);
+    {
+        const char *base = text.data(), *endp = text.data() + text.size();
+        const char* cur = base;
+        for (size_t c = 0; c < nchunks; ++c) {
+            const char* want = c + 1 == nchunks ? endp : base + (text.size() / nchunks) * (c + 1);
+            if (want < cur) want = cur;
+            if (c + 1 < nchunks) { const char* nl = (const char*)memchr(want, '\n', (size_t)(endp - want)); want = nl ? nl + 1 : endp; }
+            chunks[c].begin = cur; chunks[c].end = want; cur = want;
         }
     }
-    int rc = export_faces(st, has_mat, mat_id, name, models);      // the last object is pushed unconditionally
-    if (rc) return rc;
-    (void)saw_mtllib;
+    run_parallel(nchunks, [&](size_t c) { scan_chunk(chunks[c]); });
+    for (const ObjChunk& c : chunks) if (c.err != PTC_OK) { set_error(c.msg); return c.err; }
+    ObjGlobal g;
+    g.pos_base.resize(nchunks); g.tex_base.resize(nchunks); g.nrm_base.resize(nchunks);
+    size_t np = 0, ntx = 0, nn = 0;
+    for (size_t c = 0; c < nchunks; ++c) {
+        g.pos_base[c] = np / 3; g.tex_base[c] = ntx / 2; g.nrm_base[c] = nn / 3;
+        np += chunks[c].pos.size(); ntx += chunks[c].tex.size(); nn += chunks[c].nrm.size();
+    }
+    g.pos.resize(np); g.tex.resize(ntx); g.nrm.resize(nn);
+    run_parallel(nchunks, [&](size_t c) {
+        if (!chunks[c].pos.empty()) std::memcpy(&g.pos[g.pos_base[c] * 3], chunks[c].pos.data(), chunks[c].pos.size() * 4);
+        if (!chunks[c].tex.empty()) std::memcpy(&g.tex[g.tex_base[c] * 2], chunks[c].tex.data(), chunks[c].tex.size() * 4);
+        if (!chunks[c].nrm.empty()) std::memcpy(&g.nrm[g.nrm_base[c] * 3], chunks[c].nrm.data(), chunks[c].nrm.size() * 4);
+    });
+
+    // pass 2: events -> models (tobj: a new model on o / g with pending faces and on a usemtl that changes the material with
+    // pending faces; the last model is pushed unconditionally)
+    std::unordered_map<std::string, size_t> mat_map;
+    std::vector<ModelJob> jobs;
+    ModelJob cur; cur.name = "unnamed_object"; cur.has_mat = false; cur.mat_id = 0;
+    size_t pending = 0;
+    auto flush = [&](bool always) {
+        if (!always && pending == 0) return;
+        jobs.push_back(cur);
+        cur.spans.clear(); pending = 0;
+    };
+    for (size_t c = 0; c < nchunks; ++c) {
+        uint32_t at = 0;
+        auto take = [&](uint32_t upto) { if (upto > at) { cur.spans.push_back(FaceSpan{(uint32_t)c, at, upto}); pending += upto - at; at = upto; } };
+        for (const ObjEvent& ev : chunks[c].events) {
+            take(ev.face_pos);
+            if (ev.kind == 0) {
+                flush(false);
+                cur.name = ev.arg.empty() ? std::string("unnamed_object") : ev.arg;
+            } else if (ev.kind == 2) {
+                std::string mtl_text;
+                if (use_override) mtl_text = mtl_override;
+                else {
+                    std::string p = join_path(obj_dir, ev.arg);
+                    std::ifstream f(p, std::ios::binary);
+                    if (!f) { set_error("Failed to load MTL " + p); return PTC_ERR_IO; }
+                    std::stringstream ss; ss << f.rdbuf(); mtl_text = ss.str();
+                }
+                std::vector<TobjMaterial> loaded; std::unordered_map<std::string, size_t> lm;
+                int rc = parse_mtl(mtl_text, loaded, lm); if (rc) return rc;
+                size_t base = mats.size();
+                for (auto& kv : lm) mat_map[kv.first] = kv.second + base;
+                mats.insert(mats.end(), loaded.begin(), loaded.end());
+            } else {
+                if (ev.arg.empty()) { set_error("OBJ: usemtl without a name"); return PTC_ERR_PARSE; }
+                auto it = mat_map.find(ev.arg);
+                bool new_has = it != mat_map.end(); size_t new_id = new_has ? it->second : 0;
+                bool differs = (new_has != cur.has_mat) || (new_has && new_id != cur.mat_id);
+                if (differs) flush(false);
+                cur.has_mat = new_has; cur.mat_id = new_id;
+            }
+        }
+        take((uint32_t)chunks[c].faces.size());
+    }
+    flush(true);
+
+    // pass 3: models exported in parallel, in order
+    const size_t m0 = models.size();
+    models.resize(m0 + jobs.size());
+    std::vector<int> errs(jobs.size(), PTC_OK); std::vector<std::string> msgs(jobs.size());
+    run_parallel(jobs.size(), [&](size_t j) { errs[j] = export_model(chunks, g, jobs[j], models[m0 + j], msgs[j]); });
+    for (size_t j = 0; j < jobs.size(); ++j) if (errs[j] != PTC_OK) { set_error(msgs[j]); return errs[j]; }
     return PTC_OK;
 }
 
