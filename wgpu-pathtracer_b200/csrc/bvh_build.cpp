@@ -19,7 +19,8 @@ namespace {
 
 constexpr int kBins = 16;
 constexpr float kTraversalCost = 1.2f;   // relative to one triangle test
-constexpr uint32_t kTaskGrain = 8192;    // subtrees below this many triangles are built inline by one thread
+constexpr uint32_t kTaskGrain = 8192;
+constexpr size_t kTopNodes = 128;        // inner nodes numbered breadth-first at the top of the tree    // subtrees below this many triangles are built inline by one thread
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t id; };
 
@@ -224,13 +225,22 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
         // single-leaf tree: synthesise a root whose second child is absent
         out.nodes.resize(1);
     } else {
-        stack.push_back(0);
+        // numbering: the first kTopNodes inner nodes in breadth-first order (the top of the tree is contiguous: every ray
+        // starts there; used by the shared-memory staging experiment PTC_SMEM_TOP), the rest depth-first below them
+        std::vector<uint32_t> bfs; bfs.push_back(0);
+        for (size_t h = 0; h < bfs.size() && bfs.size() < kTopNodes; ++h) {
+            uint32_t l = bvh.nodes[bfs[h]].left;
+            if (!is_leaf(l) && bfs.size() < kTopNodes) bfs.push_back(l);
+            if (!is_leaf(l + 1) && bfs.size() < kTopNodes) bfs.push_back(l + 1);
+        }
+        for (uint32_t n : bfs) dev_id[n] = (int32_t)n_inner++;
+        for (size_t h = bfs.size(); h-- > 0;) stack.push_back(bfs[h]);
         while (!stack.empty()) {
             uint32_t n = stack.back(); stack.pop_back();
-            dev_id[n] = (int32_t)n_inner++;
+            if (dev_id[n] < 0) dev_id[n] = (int32_t)n_inner++;
             uint32_t l = bvh.nodes[n].left;
-            if (!is_leaf(l + 1)) stack.push_back(l + 1);
-            if (!is_leaf(l)) stack.push_back(l);
+            if (!is_leaf(l + 1) && dev_id[l + 1] < 0) stack.push_back(l + 1);
+            if (!is_leaf(l) && dev_id[l] < 0) stack.push_back(l);
         }
         out.nodes.resize(n_inner);
     }

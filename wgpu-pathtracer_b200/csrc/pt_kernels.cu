@@ -132,6 +132,18 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
     const uint32_t n = *count_ptr;
     if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
 
+#ifdef PTC_SMEM_TOP
+    // experiment (north_star: "top BVH levels staged in shared memory"): the first PTC_SMEM_TOP nodes — the breadth-first top of
+    // the SAH tree (bvh_build.cpp) — are copied into shared memory by every CTA.  Measured: see DESIGN.md section 5.
+    __shared__ NodeQ top_nodes[PTC_SMEM_TOP];
+    {
+        const uint32_t ntop = min((uint32_t)PTC_SMEM_TOP, s.num_nodes);
+        const uint4* src = reinterpret_cast<const uint4*>(s.nodes);
+        uint4* dst = reinterpret_cast<uint4*>(top_nodes);
+        for (uint32_t i = threadIdx.x; i < ntop * 2u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+#endif
     int stack[PTC_STACK_SIZE];
     int node = PTC_SENTINEL, sp = 0;
     uint32_t ray = kNoRay, tri_i = 0, tri_end = 0;
@@ -207,7 +219,12 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
 #pragma unroll 1
             for (;;) {
                 if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
+#ifdef PTC_SMEM_TOP
+                    NodeQ nq;
+                    if (node < PTC_SMEM_TOP) nq = top_nodes[node]; else nq = ld_node(s.nodes + node);
+#else
                     const NodeQ nq = ld_node(s.nodes + node);
+#endif
                     bool h0, h1; float tn0, tn1;
                     node_test(r, nq, best.t, h0, h1, tn0, tn1);
                     const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
