@@ -184,6 +184,17 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE line, the JSON: whatever libraries print on fd 1 while the job runs (NCCL's version banner
+    # at NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE) is sent to stderr, and fd 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj, allow_nan=False), flush=True)
+        os.dup2(2, 1)                                      # and anything printed while tearing down goes to stderr again
 
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -380,7 +391,7 @@ def main():
                              "so each launch covers a whole segment and its CUDA-event duration is exclusive; the timed region itself runs %d concurrent parts" % step.stats()["frame_parts"]},
         "cpu_baseline": ({k: base[k] for k in ("value", "unit", "cores", "kind", "sample")} if (base and world == 1) else None),
     }
-    print(json.dumps(line, allow_nan=False))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
