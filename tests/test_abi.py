@@ -80,3 +80,23 @@ def test_scene_view_roundtrip(ptc, standins):
     assert v.num_vertices == len(scene.vertices) and v.num_indices == 36 * 3 and v.num_textures == len(scene.textures)
     raw = np.frombuffer(C.string_at(v.vertices, 48 * 3), dtype=ptc.types.VERTEX_DT)
     np.testing.assert_array_equal(raw["position"], scene.vertices["position"][:3])
+
+
+def test_cpp_harness_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """harness/render_main.cpp + include/ptcore.hpp: the compiled-code host over the C ABI builds, and on a box without a
+    CUDA device it reports the library's error instead of rendering anything (exit code 3 = PTC_ERR_NO_DEVICE)."""
+    import subprocess
+    csrc = os.path.join(ROOT, "wgpu-pathtracer_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "ptrender"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(csrc, "ptrender")
+    assert subprocess.run([exe, "--help"], capture_output=True).returncode == 0
+    obj = tmp_path / "tri.obj"
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 1 1 1\n")
+    obj.write_text("mtllib m.mtl\nusemtl a\nv 2 -1 -1\nv 2 1 -1\nv 2 0 1\nf 1 2 3\n")
+    r = subprocess.run([exe, "--obj", str(obj), "--size", "32x32", "--frames", "1", "--out", str(tmp_path / "o")], capture_output=True, text=True)
+    import ctypes
+    has_gpu = ctypes.CDLL(os.path.join(csrc, "libptcore.so")).ptc_device_count() > 0
+    if has_gpu:
+        assert r.returncode == 0 and (tmp_path / "o.pfm").exists()
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr

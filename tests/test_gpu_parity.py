@@ -550,3 +550,45 @@ def test_checkpoint_resume_bit_exact(ptc, standins):
         with pytest.raises(ptc.PtcError):
             second.write(saved, plane=T.PLANE_DEPTH)
         whole.destroy(); second.destroy()
+
+
+def test_cpp_harness_matches_python_mirror(ptc, standins, tmp_path):
+    """The compiled host (harness/render_main.cpp over include/ptcore.hpp: Scene::load_obj from a file, Camera::new, the
+    Raytracer::render loop, blit) produces the same accumulation image, bit for bit, as the ctypes mirror the tests use."""
+    import os
+    import subprocess
+    T = ptc.types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "wgpu-pathtracer_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "ptrender"], stdout=subprocess.DEVNULL)
+    # the Cornell stand-in as OBJ + MTL files, and its environment map as raw float32 RGBA
+    env = standins.make_envmap(128, 64)
+    room = [
+        ("floor", "white", standins.grid((0, 0, -1), (0, 0, 2), (2, 0, 0), 1, 1)),
+        ("back", "white", standins.grid((2, 0, -1), (0, 2, 0), (0, 0, 2), 1, 1)),
+        ("left", "red", standins.grid((0, 0, -1), (2, 0, 0), (0, 2, 0), 1, 1)),
+        ("box", "blue", standins.transform(standins.box((-0.3, 0, -0.3), (0.3, 1.2, 0.3)), rot_y=-0.35, translate=(1.35, 0, -0.35))),
+    ]
+    obj_text = standins._obj_text(room).replace("mtllib standin.mtl", "mtllib room.mtl")
+    (tmp_path / "room.obj").write_text(obj_text)
+    (tmp_path / "room.mtl").write_text(standins.CORNELL_MTL)
+    env.texels.astype(np.float32).tofile(tmp_path / "sky.f32")
+    W, H, frames = 200, 120, 3
+    pos, look = (-2.6, 1.0, 0.0), (1.0, 1.0, 0.0)
+    r = subprocess.run([os.path.join(csrc, "ptrender"), "--obj", str(tmp_path / "room.obj"), "--env-raw", str(tmp_path / "sky.f32"), "128", "64",
+                        "--size", f"{W}x{H}", "--frames", str(frames), "--pos", *map(str, pos), "--look", *map(str, look), "--fov", "60",
+                        "--out", str(tmp_path / "cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(tmp_path / "cpp.rgba32f", np.float32).reshape(H, W, 4)
+    scene = ptc.Scene(env)
+    scene.load_obj(obj_text=obj_text, mtl_text=standins.CORNELL_MTL, obj_dir=str(tmp_path))
+    camera = standins.make_camera({"position": pos, "fov": 60.0, "target": look}, W, H)
+    step = ptc.RTStep.create(scene, ptc.make_config(W, H))
+    for f in range(1, frames + 1):
+        step.update(camera.uniforms(frame=f)); step.render()
+    ref = step.read(T.PLANE_COLOR)
+    assert (ref[..., 3] == frames).all() and np.array_equal(got, ref)
+    step.blit()
+    ppm = (tmp_path / "cpp.ppm").read_bytes()
+    assert np.array_equal(np.frombuffer(ppm[-W * H * 3:], np.uint8).reshape(H, W, 3), step.read(T.PLANE_DISPLAY)[..., :3])
+    step.destroy()
