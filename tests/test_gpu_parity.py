@@ -592,3 +592,14 @@ def test_cpp_harness_matches_python_mirror(ptc, standins, tmp_path):
     ppm = (tmp_path / "cpp.ppm").read_bytes()
     assert np.array_equal(np.frombuffer(ppm[-W * H * 3:], np.uint8).reshape(H, W, 3), step.read(T.PLANE_DISPLAY)[..., :3])
     step.destroy()
+
+
+@pytest.mark.parametrize("build", [0, 1])
+def test_degenerate_and_tied_geometry_gpu(ptc, standins, oracle, build):
+    """Coincident duplicates (equal t: smaller triangle id wins), zero-area and sliver triangles, coplanar overlaps and a
+    far-away triangle that stretches the quantisation grid: kernels == oracle on every plane, for both tree builders."""
+    from test_hostemu_parity import _degenerate_scene
+    scene, cam = _degenerate_scene(ptc, standins)
+    step, ref = render_both(ptc, standins, oracle, scene, cam, 320, 240, 2, max_bounces=5, bvh_build=build)
+    check_all_planes(ptc, step, ref)
+    step.destroy()

@@ -165,3 +165,33 @@ def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which):
     assert_identical(ro, re)
     info = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=ptc.types.BVH_LBVH_DEVICE)).bvh_info()
     assert info["max_depth"] < 64 and info["triangles"] == len(scene.indices) // 3
+
+
+def _degenerate_scene(ptc, standins):
+    """Cornell plus geometry that stresses ties and degeneracy: exact duplicates (equal t: the smaller triangle id must win),
+    zero-area triangles, a sliver, coplanar overlapping quads, and a far-away huge triangle that stretches the scene box
+    (coarser quantisation grid for everything else)."""
+    scene, cam = standins.cornell()
+    tri = np.array([[1.2, 0.4, -0.4], [1.2, 1.3, 0.0], [1.2, 0.4, 0.4]], np.float32)
+    nrm = np.tile([-1, 0, 0], (3, 1))
+    for _ in range(3):
+        scene.add_mesh(tri, nrm, None, [0, 1, 2], 1)                                       # three coincident copies
+    scene.add_mesh(np.array([[1, 1, 0], [1, 1, 0], [1, 1, 0]], np.float32), nrm, None, [0, 1, 2], 2)          # point
+    scene.add_mesh(np.array([[0.5, 0.2, -0.5], [0.5, 0.7, 0.0], [0.5, 1.2, 0.5]], np.float32), nrm, None, [0, 1, 2], 2)   # collinear
+    scene.add_mesh(np.array([[0.8, 0.1, -0.9], [0.8, 1.9, -0.9], [0.8, 1.0, -0.9 + 1e-6]], np.float32), nrm, None, [0, 1, 2], 3)  # sliver
+    quad = np.array([[1.6, 0.2, -0.6], [1.6, 1.0, -0.6], [1.6, 1.0, 0.6], [1.6, 0.2, 0.6]], np.float32)
+    scene.add_mesh(quad, np.tile([-1, 0, 0], (4, 1)), None, [0, 1, 2, 0, 2, 3], 2)
+    scene.add_mesh(quad + np.array([0, 0.3, 0.2], np.float32), np.tile([-1, 0, 0], (4, 1)), None, [0, 1, 2, 0, 2, 3], 4)   # coplanar overlap
+    scene.add_mesh(np.array([[4000, -3000, -3000], [4000, 3000, -3000], [4000, 0, 5000]], np.float32), nrm, None, [0, 1, 2], 1)
+    return scene, cam
+
+
+@pytest.mark.parametrize("build", [0, 1])
+def test_degenerate_and_tied_geometry(ptc, standins, oracle, hostemu, build):
+    scene, cam = _degenerate_scene(ptc, standins)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 200, 150, 2, max_bounces=5, bvh_build=build)
+    assert_identical(ro, re)
+    # the duplicates resolve to the first copy (smaller global triangle id) at every pixel that sees them
+    first_dup = len(scene.meshes) - 9
+    seen = set(np.unique(ro["hit_id"][..., 0]).tolist())
+    assert first_dup in seen and first_dup + 1 not in seen and first_dup + 2 not in seen
