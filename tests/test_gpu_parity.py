@@ -603,3 +603,26 @@ def test_degenerate_and_tied_geometry_gpu(ptc, standins, oracle, build):
     step, ref = render_both(ptc, standins, oracle, scene, cam, 320, 240, 2, max_bounces=5, bvh_build=build)
     check_all_planes(ptc, step, ref)
     step.destroy()
+
+
+def test_many_frames_in_flight(ptc, standins, oracle):
+    """150 frames enqueued back to back without a poll (more than the ring of per-frame device counters holds), two frame
+    parts: the running mean after the last one is the oracle's, bit for bit."""
+    T = ptc.types
+    scene, cam = standins.cornell()
+    W, H, frames = 160, 120, 150
+    cfg = ptc.make_config(W, H, max_bounces=3)
+    camera = standins.make_camera(cam, W, H)
+    step = ptc.RTStep.create(scene, cfg)
+    us = [camera.uniforms(frame=f) for f in range(1, frames + 1)]
+    for u in us:
+        step.update(u); step.render()
+    orc = oracle.OracleScene(scene, cfg)
+    ref = None
+    for u in us:
+        ref = orc.render_frame(u, None if ref is None else ref["color"], want_aux=False)
+    step.poll(True)
+    got = step.read(T.PLANE_COLOR)
+    assert step.stats()["frame_parts"] == 2 and (got[..., 3] == frames).all()
+    assert np.array_equal(got, ref["color"])
+    step.destroy()
