@@ -177,7 +177,9 @@ typedef struct ptc_stats {
     uint64_t frames_rendered;
     uint64_t kernel_launches;  /* CUDA kernels this library launched */
     uint64_t frame_parts;      /* independent wavefronts a frame is split into (each runs raygen + (trace, shade) x segments) */
-    uint64_t reserved[4];
+    uint64_t packet_node_visits;  /* primary-ray packet traversal: node visits of all packets ... */
+    uint64_t packet_lane_visits;  /* ... and lanes (rays) that entered a child at them: coherence = lane / (32 x node) */
+    uint64_t reserved[2];
 } ptc_stats;
 
 /* status codes */

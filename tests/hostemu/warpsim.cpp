@@ -224,3 +224,63 @@ uint64_t emu_collect_rays(const void* scene, const ptc_uniforms* un_in, uint32_t
     }
     return n;
 }
+
+// Host model of k_trace_packet (pt_kernels.cu): 32 consecutive rays walk the tree together with one uniform node and stack,
+// descending where ANY ray needs to, the near child chosen by the vote of the rays that enter both.  hits_out as
+// emu_warpsim; stats: [0] node visits, [1] triangle tests (per packet), [2] hits differing from trace_closest_bvh2.
+extern "C" __attribute__((visibility("default")))
+int emu_packet_trace(const void* scene, const float* rays, uint64_t n, uint32_t* hits_out, uint64_t stats[3]) {
+    const DevScene& s = *emu_dev_scene(scene);
+    stats[0] = stats[1] = stats[2] = 0;
+    for (uint64_t base = 0; base < n; base += 32) {
+        pt_v3 o[32], d[32]; RaySlab r[32]; HitRec best[32]; bool live[32];
+        bool any = false;
+        for (int l = 0; l < 32; ++l) {
+            const uint64_t i = base + l;
+            o[l] = pt_mk3(0.0f, 0.0f, 0.0f); d[l] = pt_mk3(1.0f, 0.0f, 0.0f);
+            if (i < n) { const float* q = rays + i * 8; o[l] = pt_mk3(q[0], q[1], q[2]); d[l] = pt_mk3(q[4], q[5], q[6]); }
+            live[l] = i < n && s.num_nodes != 0 && ray_is_finite(o[l], d[l]);
+            r[l] = make_ray_slab(s, o[l], d[l]);
+            best[l].t = PT_RAY_TMAX; best[l].b1 = best[l].b2 = 0.0f; best[l].tri = 0xFFFFFFFFu;
+            any = any || live[l];
+        }
+        int stack[PTC_STACK_SIZE]; int sp = 0; stack[sp++] = PTC_SENTINEL;
+        int node = any ? 0 : PTC_SENTINEL;
+        while (node != PTC_SENTINEL) {
+            if (node >= 0) {
+                const NodeQ nq = ld_node(s.nodes + node); stats[0]++;
+                int m0 = 0, m1 = 0, both = 0, far_first = 0;
+                for (int l = 0; l < 32; ++l) {
+                    bool h0, h1; float a, b; node_test(r[l], nq, best[l].t, h0, h1, a, b);
+                    h0 = h0 && live[l]; h1 = h1 && live[l];
+                    m0 += h0; m1 += h1; both += h0 && h1; far_first += h0 && h1 && b < a;
+                }
+                const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+                if (m0 && m1) { const bool swap = 2 * far_first > both; stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }
+                else if (m0 || m1) node = m0 ? c0 : c1;
+                else node = stack[--sp];
+            } else {
+                const uint32_t enc = ~(uint32_t)node, first = enc >> 3, cnt = (enc & 7u) + 1u;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const F4* tp = s.tris + (size_t)(first + k) * 4;
+                    F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2); stats[1]++;
+                    for (int l = 0; l < 32; ++l) {
+                        float t, b1, b2;
+                        if (live[l] && pt_ray_tri(o[l], d[l], pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                            const uint32_t id = f2u(a.w);
+                            if (t < best[l].t || (t == best[l].t && id < best[l].tri)) { best[l].t = t; best[l].b1 = b1; best[l].b2 = b2; best[l].tri = id; }
+                        }
+                    }
+                }
+                node = stack[--sp];
+            }
+        }
+        for (int l = 0; l < 32 && base + l < n; ++l) {
+            const uint64_t i = base + l;
+            if (hits_out) { std::memcpy(&hits_out[i * 4], &best[l].t, 4); std::memcpy(&hits_out[i * 4 + 1], &best[l].b1, 4); std::memcpy(&hits_out[i * 4 + 2], &best[l].b2, 4); hits_out[i * 4 + 3] = best[l].tri; }
+            HitRec h = trace_closest_bvh2(s, o[l], d[l], nullptr);
+            if (h.tri != best[l].tri || std::memcmp(&h.t, &best[l].t, 4) != 0 || std::memcmp(&h.b1, &best[l].b1, 4) != 0) stats[2]++;
+        }
+    }
+    return 0;
+}

@@ -195,3 +195,45 @@ def test_degenerate_and_tied_geometry(ptc, standins, oracle, hostemu, build):
     first_dup = len(scene.meshes) - 9
     seen = set(np.unique(ro["hit_id"][..., 0]).tolist())
     assert first_dup in seen and first_dup + 1 not in seen and first_dup + 2 not in seen
+
+
+@pytest.mark.parametrize("which", ["sponza_tiles", "soup_random", "degenerate"])
+def test_packet_traversal_same_hits(ptc, standins, oracle, hostemu, which):
+    """Host model of k_trace_packet (32 rays walking the tree together with one uniform node and stack): whatever the
+    packet contains — a coherent 8x4 tile of primary rays, 32 unrelated rays, NaN rays, ties — every ray's hit equals
+    the per-ray traversal's and the oracle's."""
+    import ctypes as C
+    from conftest import random_rays
+    L = hostemu.L
+    L.emu_packet_trace.restype = C.c_int
+    L.emu_packet_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.emu_collect_rays.restype = C.c_uint64
+    L.emu_collect_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+    if which == "sponza_tiles":
+        scene, cam = standins.sponza(tex_size=16)
+        W, H = 240, 136
+        es = hostemu.scene(scene, ptc.make_config(W, H))
+        un = standins.make_camera(cam, W, H).uniforms(frame=1)
+        buf = np.zeros((W * H, 8), np.float32)
+        n = int(L.emu_collect_rays(es._h, C.byref(un), 0, buf.ctypes.data_as(C.c_void_p), W * H))
+        ys, xs = np.mgrid[0:H, 0:W]
+        key = ((ys // 4) * (W // 8) + xs // 8) * 32 + (ys % 4) * 8 + xs % 8
+        rays = np.ascontiguousarray(buf[:n][np.argsort(key.ravel(), kind="stable")])
+    elif which == "soup_random":
+        scene, _ = standins.random_soup(20000, seed=5, textured=False)
+        es = hostemu.scene(scene, ptc.make_config(8, 8))
+        rays = random_rays(20011, 17)                                    # not a multiple of 32: a partial last packet
+        rays[5::97, 4] = np.nan; rays[11::89, 1] = np.inf
+    else:
+        scene, _ = _degenerate_scene(ptc, standins)
+        es = hostemu.scene(scene, ptc.make_config(8, 8))
+        rays = random_rays(6000, 23, extent=1.5)
+        rays[:, 0:3] = rays[:, 0:3] * 0.3 + np.array([0.6, 1.0, 0.0], np.float32)
+    hits = np.zeros((len(rays), 4), np.uint32)
+    stats = (C.c_uint64 * 3)()
+    L.emu_packet_trace(es._h, rays.ctypes.data_as(C.c_void_p), len(rays), hits.ctypes.data_as(C.c_void_p), stats)
+    assert stats[2] == 0
+    ref, _, _ = oracle.OracleScene(scene, ptc.make_config(8, 8)).trace_rays(rays)
+    assert np.array_equal(hits, ref)
+    if which == "sponza_tiles":
+        assert stats[0] / (len(rays) / 32) < 90                          # even at this low resolution a tile visits ~2x what one ray does (1.2x at 1080p)

@@ -34,7 +34,7 @@ class Config(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("rays_traced", u64), ("frames_rendered", u64), ("kernel_launches", u64), ("frame_parts", u64), ("reserved", u64 * 4)]
+    _fields_ = [("rays_traced", u64), ("frames_rendered", u64), ("kernel_launches", u64), ("frame_parts", u64), ("packet_node_visits", u64), ("packet_lane_visits", u64), ("reserved", u64 * 2)]
 
 
 class HostCamera(C.Structure):  # include/ptcore.h ptc_host_camera (camera.rs:5-28)

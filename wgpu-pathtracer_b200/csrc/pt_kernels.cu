@@ -239,6 +239,72 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
     }
 }
 
+// Primary rays: PACKET traversal.  Queue slots are dealt to warps by 8x4-pixel tile (k_raygen), so the 32 rays of a warp
+// share an origin and differ by a few pixels: the warp walks the tree ONCE with a warp-uniform node and stack, every lane
+// testing its own ray against the same node (one broadcast load), and descends where ANY lane needs to.  No lane ever waits
+// for a phase and there is nothing to vote on but the two hit masks: ~55 warp instructions per node visit at 32 active
+// lanes, against ~61 at 18/32 in k_trace.  The union of the nodes 32 neighbouring rays need is only ~1.2x what one of them
+// needs (tests/hostemu: 38.9 vs 32.2 on Sponza, 43.7 vs 32.1 classroom), so a packet costs 30-40 % fewer instructions than
+// its rays cost one by one.  The visiting order differs from the per-ray loop's; the closest hit (ties to the smaller
+// triangle id) does not.  Incoherent segments stay with k_trace: a packet of unrelated rays would visit the union of 32
+// different paths.
+__global__ void __launch_bounds__(kTraceThreads, PTC_TRACE_MIN_BLOCKS) k_trace_packet(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+                                                                                     U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
+                                                                                     uint32_t* cursor, unsigned long long* total_rays,
+                                                                                     unsigned long long* packet_stats) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t n = *count_ptr;
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
+    const uint32_t lane = threadIdx.x & 31;
+    int stack[PTC_STACK_SIZE];                      // every lane keeps the same (warp-uniform) stack
+    uint32_t visits = 0, lane_visits = 0;           // coherence feedback: node visits, and lanes that entered a child at them
+    for (;;) {
+        const uint32_t base = warp_fetch(cursor);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        pt_v3 o = pt_mk3(0.0f, 0.0f, 0.0f), d = pt_mk3(1.0f, 0.0f, 0.0f);
+        if (i < n) { const F4 ro = ld4_stream(ray_o + i), rd = ld4_stream(ray_d + i); o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z); }
+        const bool live = i < n && s.num_nodes != 0 && ray_is_finite(o, d);
+        const RaySlab r = make_ray_slab(s, o, d);
+        HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
+        int sp = 0; stack[sp++] = PTC_SENTINEL;
+        int node = __ballot_sync(FULL, live) ? 0 : PTC_SENTINEL;
+        while (node != PTC_SENTINEL) {
+            if (node >= 0) {
+                const NodeQ nq = ld_node(s.nodes + node);
+                bool h0, h1; float tn0, tn1;
+                node_test(r, nq, best.t, h0, h1, tn0, tn1);
+                h0 = h0 && live; h1 = h1 && live;
+                const uint32_t m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+                const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+                visits++; lane_visits += __popc(m0 | m1);
+                if (m0 && m1) {
+                    // near child first by the vote of the lanes that enter both
+                    const uint32_t both = m0 & m1, far_first = __ballot_sync(FULL, h0 && h1 && tn1 < tn0);
+                    const bool swap = 2 * __popc(far_first) > __popc(both);
+                    stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0;
+                } else if (m0 | m1) node = m0 ? c0 : c1;
+                else node = stack[--sp];
+            } else {
+                const uint32_t enc = ~(uint32_t)node;
+                const uint32_t first = enc >> 3, cnt = (enc & 7u) + 1u;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const F4* tp = s.tris + (size_t)(first + k) * 4;
+                    F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
+                    float t, b1, b2;
+                    if (live && pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                        const uint32_t id = f2u(a.w);
+                        if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+                    }
+                }
+                node = stack[--sp];
+            }
+        }
+        if (i < n) reinterpret_cast<uint4*>(hits)[i] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+    }
+    if (packet_stats && lane == 0 && visits) { atomicAdd(packet_stats, (unsigned long long)visits); atomicAdd(packet_stats + 1, (unsigned long long)lane_visits); }
+}
+
 __global__ void __launch_bounds__(kTraceThreads) k_trace_any(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
                                                               uint8_t* __restrict__ occluded, uint32_t n, uint32_t* cursor) {
     const uint32_t lane = threadIdx.x & 31;
@@ -341,9 +407,10 @@ void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounte
     k_raygen<<<(n + 255) / 256, 256, 0, st>>>(un, q, fc, n, num_parts, part);
 }
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
-                  unsigned long long* total_rays) {
+                  unsigned long long* total_rays, unsigned long long* packet_stats) {
     if (impl == 0) k_trace<false, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
     else if (impl == 2) k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
+    else if (impl == 3) k_trace_packet<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, packet_stats);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,

@@ -48,8 +48,9 @@ struct Planes {
 
 // part `part` of `num_parts`: its n queue slots are the warps t = part, part + num_parts, ... of the frame's slot order
 void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part);
+// impl 3 = packet traversal (primary rays in tile order); packet_stats (optional): [0] += node visits, [1] += lanes entering a child
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
-                  unsigned long long* total_rays);
+                  unsigned long long* total_rays, unsigned long long* packet_stats = nullptr);
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
                   FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh);
 // PTC_LIGHTS_MIS: any-hit traversal of the shadow rays shade(segment) queued; unoccluded ones add into acc_next

@@ -83,6 +83,17 @@ struct ptc_step {
     void* d_display = nullptr; F4* d_reprojected = nullptr; uint32_t* d_owner = nullptr;
     uint32_t npix = 0;
     int trace_grid = 0, shade_grid = 0;
+    // Primary rays: packet traversal (k_trace_packet) pays off when the 32 rays of a tile stay together — 1.3-1.45x on
+    // Sponza / San Miguel, where ~24 of 32 lanes enter a child at the average node visit, 0.7-0.86x on classroom / dragon
+    // (~20 lanes: triangles smaller than a tile).  The kernel counts exactly that; the step samples the counters with an
+    // asynchronous read-back every kPacketSample frames and keeps packets on while the coherence stays above kPacketMinLanes,
+    // probing with one packet frame per sample period while they are off.  Either kernel produces the same hits.
+    int packets_mode = -1;                         // PTC_PRIMARY_PACKETS: 0 never, 1 always, unset (-1) adaptive
+    bool primary_packets = true;
+    unsigned long long* h_packet_stats = nullptr;  // pinned: [0] node visits, [1] lane visits at the last sample
+    unsigned long long packet_prev[2] = {0, 0};
+    cudaEvent_t packet_ev = nullptr; bool packet_pending = false;
+    uint64_t packet_frame = 0;
     int trace_impl = 0;                            // 0 = k_trace, 1 = k_trace_simple (PTC_TRACE_IMPL=simple, A/B timing only)
     uint64_t frames = 0, launches = 0;
     // optional per-stage timing (CUDA events on the render stream)
@@ -379,6 +390,8 @@ static void destroy_step(ptc_step* s) {
     for (auto a : s->pages) if (a) cudaFreeArray(a);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_shade); cudaFree(s->d_mats); cudaFree(s->d_texs); cudaFree(s->d_lights); cudaFree(s->d_light_of_tri);
     cudaFree(s->d_fc); cudaFree(s->d_total_rays);
+    if (s->h_packet_stats) cudaFreeHost(s->h_packet_stats);
+    if (s->packet_ev) cudaEventDestroy(s->packet_ev);
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->snap_ready) cudaEventDestroy(s->snap_ready);
     if (s->copy_done) cudaEventDestroy(s->copy_done);
@@ -441,8 +454,8 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
             cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
         if ((rc = upload_scene(s, scene)) != PTC_OK) break;
         if ((rc = alloc_frame_buffers(s, config->width, config->height)) != PTC_OK) break;
-        if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing * ptc_step::kMaxParts) != cudaSuccess || cudaMalloc(&s->d_total_rays, 8) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
-        cudaMemsetAsync(s->d_total_rays, 0, 8, s->stream);
+        if (cudaMalloc(&s->d_fc, sizeof(FrameCounters) * kFcRing * ptc_step::kMaxParts) != cudaSuccess || cudaMalloc(&s->d_total_rays, 24) != cudaSuccess) { set_error("counter allocation failed"); rc = PTC_ERR_OOM; break; }
+        cudaMemsetAsync(s->d_total_rays, 0, 24, s->stream);     // [0] rays traced, [1] packet node visits, [2] lanes entering a child at them
         {   // traversal kernel variant: by BVH size (pt_kernels.cu), PTC_TRACE_IMPL = simple | std | dense overrides (A/B timing)
             const char* e = getenv("PTC_TRACE_IMPL");
             s->trace_impl = (s->bvh_info[2] + s->bvh_info[3]) > (96ull << 20) ? 2 : 0;
@@ -450,6 +463,8 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
             if (e && std::strcmp(e, "std") == 0) s->trace_impl = 0;
             if (e && std::strcmp(e, "dense") == 0) s->trace_impl = 2;
         }
+        { const char* e = getenv("PTC_PRIMARY_PACKETS"); s->packets_mode = e ? (std::strcmp(e, "0") == 0 ? 0 : 1) : -1; s->primary_packets = s->packets_mode != 0; }
+        if (cudaMallocHost(&s->h_packet_stats, 16) != cudaSuccess || cudaEventCreateWithFlags(&s->packet_ev, cudaEventDisableTiming) != cudaSuccess) { set_error("packet statistics allocation failed"); rc = PTC_ERR_OOM; break; }
         s->trace_grid = trace_grid_size(cuda_device, s->trace_impl);
         s->shade_grid = shade_grid_size(cuda_device);
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
@@ -477,6 +492,19 @@ PTC_API int ptc_render(ptc_step* s) {
     pc.light_sampling = s->cfg.light_sampling;
     const bool mis = pc.light_sampling == PTC_LIGHTS_MIS && s->scene.num_real_lights != 0;
     if (s->profiling && s->ev_used > 60000) prof_collect(s);
+    // primary rays: packets or per-ray traversal, by the measured coherence (see ptc_step::packets_mode)
+    bool use_packets = s->primary_packets && s->trace_impl != 1;
+    if (s->packets_mode < 0 && s->trace_impl != 1) {
+        static const uint64_t kPacketSample = 32; static const double kPacketMinLanes = 21.5;
+        if (s->packet_pending && cudaEventQuery(s->packet_ev) == cudaSuccess) {
+            s->packet_pending = false;
+            const unsigned long long dn = s->h_packet_stats[0] - s->packet_prev[0], dl = s->h_packet_stats[1] - s->packet_prev[1];
+            s->packet_prev[0] = s->h_packet_stats[0]; s->packet_prev[1] = s->h_packet_stats[1];
+            if (dn) s->primary_packets = (double)dl / (double)dn >= kPacketMinLanes;
+        }
+        const bool probe = s->packet_frame % kPacketSample == 0;             // frame 0, 32, 64, ...: always a packet frame, then sampled
+        use_packets = s->primary_packets || probe;
+    }
     // work enqueued on the ordering stream since the last frame (blit, reduce, reset, an asynchronous read's snapshot) must
     // be over before this frame touches the planes; raygen and the primary-ray traversal do not, and are not held back
     const bool wait_main = s->main_dirty && !s->profiling;
@@ -497,7 +525,8 @@ PTC_API int ptc_render(ptc_step* s) {
         prof_mark(s, 0);
         launch_raygen(st0, s->uniforms, P.qp, fc, P.n, nparts, p);
         prof_mark(s, 1);
-        launch_trace(st0, s->trace_grid, s->trace_impl, s->scene, P.qp, P.d_hits_p, fc, 0, s->d_total_rays);
+        // primary rays arrive in 8x4-pixel tiles, one per warp: packet traversal (pt_kernels.cu); PTC_PRIMARY_PACKETS=0 uses k_trace
+        launch_trace(st0, s->trace_grid, use_packets ? 3 : s->trace_impl, s->scene, P.qp, P.d_hits_p, fc, 0, s->d_total_rays, s->d_total_rays + 1);
         if (prefetch) { CK(cudaEventRecord(P.primary_done, st0)); CK(cudaStreamWaitEvent(st, P.primary_done, 0)); }
         if (wait_main) CK(cudaStreamWaitEvent(st, s->ev_main, 0));
         s->launches += 1;
@@ -511,6 +540,15 @@ PTC_API int ptc_render(ptc_step* s) {
             if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(st, s->trace_grid, s->scene, P.shq, P.q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
         }
         if (!s->profiling) { CK(cudaEventRecord(P.done, st)); CK(cudaStreamWaitEvent(s->stream, P.done, 0)); }
+    }
+    if (s->packets_mode < 0 && s->trace_impl != 1) {
+        // sample the coherence counters after a probing frame: an asynchronous read-back behind this frame on the ordering stream
+        if (s->packet_frame % 32 == 0 && !s->packet_pending) {
+            CK(cudaMemcpyAsync(s->h_packet_stats, s->d_total_rays + 1, 16, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaEventRecord(s->packet_ev, s->stream));
+            s->packet_pending = true;
+        }
+        s->packet_frame++;
     }
     prof_mark(s, -1);
     if (s->profiling) s->main_dirty = true;           // the next unprofiled frame's parts must wait for this one
@@ -683,9 +721,11 @@ PTC_API int ptc_get_stats(ptc_step* s, ptc_stats* out) {
     if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     std::memset(out, 0, sizeof(*out));
-    unsigned long long rays = 0;
-    CK(cudaMemcpyAsync(&rays, s->d_total_rays, 8, cudaMemcpyDeviceToHost, s->stream));
+    unsigned long long c[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(c, s->d_total_rays, 24, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    const unsigned long long rays = c[0];
+    out->packet_node_visits = c[1]; out->packet_lane_visits = c[2];
     out->rays_traced = rays; out->frames_rendered = s->frames; out->kernel_launches = s->launches; out->frame_parts = s->num_parts;
     return PTC_OK;
 }

@@ -108,7 +108,7 @@ class RTStep:
         s = T.Stats()
         check(lib().ptc_get_stats(self._h, C.byref(s)))
         return {"rays_traced": s.rays_traced, "frames_rendered": s.frames_rendered, "kernel_launches": s.kernel_launches,
-                "frame_parts": s.frame_parts}
+                "frame_parts": s.frame_parts, "packet_node_visits": s.packet_node_visits, "packet_lane_visits": s.packet_lane_visits}
 
     def set_profiling(self, enable=True):
         check(lib().ptc_set_profiling(self._h, 1 if enable else 0))
