@@ -277,7 +277,11 @@ int emu_packet_trace(const void* scene, const float* rays, uint64_t n, uint32_t*
         }
         for (int l = 0; l < 32 && base + l < n; ++l) {
             const uint64_t i = base + l;
-            if (hits_out) { std::memcpy(&hits_out[i * 4], &best[l].t, 4); std::memcpy(&hits_out[i * 4 + 1], &best[l].b1, 4); std::memcpy(&hits_out[i * 4 + 2], &best[l].b2, 4); hits_out[i * 4 + 3] = best[l].tri; }
+            if (hits_out) {                                    // a miss is reported as (0, 0, 0, 0xFFFFFFFF), as emu_trace_rays / orc_trace_rays do
+                const bool hit = best[l].tri != 0xFFFFFFFFu; const float z = 0.0f;
+                std::memcpy(&hits_out[i * 4], hit ? &best[l].t : &z, 4); std::memcpy(&hits_out[i * 4 + 1], hit ? &best[l].b1 : &z, 4);
+                std::memcpy(&hits_out[i * 4 + 2], hit ? &best[l].b2 : &z, 4); hits_out[i * 4 + 3] = best[l].tri;
+            }
             HitRec h = trace_closest_bvh2(s, o[l], d[l], nullptr);
             if (h.tri != best[l].tri || std::memcmp(&h.t, &best[l].t, 4) != 0 || std::memcmp(&h.b1, &best[l].b1, 4) != 0) stats[2]++;
         }
