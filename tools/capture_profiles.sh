@@ -15,6 +15,6 @@ python bench.py --workload san_miguel_4k --bvh-build lbvh --steps 16 --warmup 4 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/ncu_launches_bench_steps4.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $out/ncu_launches.log 2>&1
 # full capture of the hot kernels, whole-frame launches (PTC_PARTS=1: what the stage-timing pass and the roofline figure use)
-PTC_PARTS=1 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade" -s 24 -c 6 -o $out/ncu_full -f \
+PTC_PARTS=1 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade" -s 20 -c 10 -o $out/ncu_full -f \
     python bench.py --steps 2 --warmup 4 --no-cpu-baseline > $out/ncu_full.log 2>&1
 ls -la $out
