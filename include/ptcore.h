@@ -116,7 +116,8 @@ PTC_API void* ptc_stream(ptc_step* step);
  * rank of `nccl_comm` into rank `root` — one ncclReduce(ncclFloat32, ncclSum), after the frames already enqueued.  The
  * reference has no counterpart (single GPU).  `nccl_comm` is the caller's ncclComm_t; the library binds to the NCCL the
  * process has already loaded (dlopen RTLD_NOLOAD "libnccl.so.2"), else loads the system one, so the communicator and the
- * call always come from the same NCCL.  Returns PTC_ERR_INVALID when no NCCL can be found. */
+ * call always come from the same NCCL.  root < 0: ncclAllReduce instead (every rank ends up with the sum, e.g. to display it).
+ * Returns PTC_ERR_INVALID when no NCCL can be found. */
 PTC_API int ptc_reduce(ptc_step* step, void* nccl_comm, int root);
 
 PTC_API int ptc_get_stats(ptc_step* step, ptc_stats* out);

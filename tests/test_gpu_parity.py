@@ -468,6 +468,8 @@ def test_ptc_reduce_binds_process_nccl(ptc, standins):
         before = step.read(T.PLANE_COLOR)
         step.reduce(comm, 0); step.poll(True)
         assert np.array_equal(step.read(T.PLANE_COLOR), before) and (before[..., 3] == 2).all()
+        step.reduce(comm, -1); step.poll(True)                            # root < 0: ncclAllReduce
+        assert np.array_equal(step.read(T.PLANE_COLOR), before)
         with pytest.raises(ptc.PtcError):
             step.reduce(0, 0)
         step.destroy()

@@ -867,8 +867,10 @@ PTC_API int ptc_debug_sample(ptc_step* s, int texture_index, const float* in, ui
 
 // ---- ptc_reduce: NCCL bound at run time (no link dependency; the communicator's own library is the one called) ---------
 typedef int (*nccl_reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);   // ncclReduce(send, recv, count, dtype, op, root, comm, stream)
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);     // ncclAllReduce(send, recv, count, dtype, op, comm, stream)
 typedef const char* (*nccl_errstr_fn)(int);
 static nccl_reduce_fn g_nccl_reduce = nullptr;
+static nccl_allreduce_fn g_nccl_allreduce = nullptr;
 static nccl_errstr_fn g_nccl_errstr = nullptr;
 static bool bind_nccl() {
     if (g_nccl_reduce) return true;
@@ -876,6 +878,7 @@ static bool bind_nccl() {
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return false;
     g_nccl_reduce = (nccl_reduce_fn)dlsym(h, "ncclReduce");
+    g_nccl_allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
     g_nccl_errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
     return g_nccl_reduce != nullptr;
 }
@@ -885,7 +888,11 @@ PTC_API int ptc_reduce(ptc_step* s, void* nccl_comm, int root) {
     CK(cudaSetDevice(s->device));
     const int kNcclFloat32 = 7, kNcclSum = 0;                     // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
     s->main_dirty = true;
-    int r = g_nccl_reduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
+    int r;
+    if (root < 0) {                                               // every rank wants the image (each one displays): all-reduce
+        if (!g_nccl_allreduce) { set_error("ptc_reduce: ncclAllReduce not found"); return PTC_ERR_INVALID; }
+        r = g_nccl_allreduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, nccl_comm, s->stream);
+    } else r = g_nccl_reduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
     if (r != 0) { set_error(std::string("ncclReduce: ") + (g_nccl_errstr ? g_nccl_errstr(r) : "error")); return PTC_ERR_CUDA; }
     return PTC_OK;
 }
