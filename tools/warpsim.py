@@ -47,7 +47,7 @@ def main():
     cfg = ptc.make_config(W, H)
     es = emu.scene(scene, cfg)
     un = st.make_camera(cam, W, H).uniforms(frame=1)
-    policies = [("fixed vote", dict(policy=0, tri_vote=8, refill_vote=16, node_inner=12, tri_inner=8))]
+    policies = [("rv%d" % rv, dict(policy=0, tri_vote=8, refill_vote=rv, node_inner=12, tri_inner=8)) for rv in (4, 8, 12, 16, 20)]
     for seg in segs:
         buf = np.zeros((W * H, 8), np.float32)
         n = int(L.emu_collect_rays(es._h, C.byref(un), seg, buf.ctypes.data_as(C.c_void_p), W * H))
@@ -76,9 +76,10 @@ def main():
                 O = SimOut()
                 L.emu_warpsim(es._h, r.ctypes.data_as(C.c_void_p), n, C.byref(P), C.byref(O), None)
                 cost = O.it_outer * C_OUTER + O.it_node * C_NODE + O.it_tri * C_TRI + O.it_refill * C_REFILL + O.it_inner_vote * C_INNER
+                cost60 = cost - O.it_refill * (C_REFILL - 60)
                 base = base or cost
                 print(f"  {pname:22s} cost/ray {cost / n:7.1f} ({cost / base:5.3f})  outer {O.it_outer / n * 32:6.1f} node it {O.it_node / n * 32:6.1f} util {O.ln_node / max(1, O.it_node) / 32:4.2f}"
-                      f"  tri it {O.it_tri / n * 32:5.1f} util {O.ln_tri / max(1, O.it_tri) / 32:4.2f}  refill {O.it_refill / n * 32:4.1f}  nodes/ray {O.node_visits / n:5.1f} tris/ray {O.tri_tests / n:4.2f} mism {O.mismatches}")
+                      f" | refill=60: {cost60 / n:6.1f} |  tri it {O.it_tri / n * 32:5.1f} util {O.ln_tri / max(1, O.it_tri) / 32:4.2f}  refill {O.it_refill / n * 32:4.1f}  nodes/ray {O.node_visits / n:5.1f} tris/ray {O.tri_tests / n:4.2f} mism {O.mismatches}")
 
 
 if __name__ == "__main__":
