@@ -59,7 +59,11 @@ PTC_API int ptc_poll(ptc_step* step, int wait);
 
 /* replaces RTStep::resize (pt.rs:732-745) + the accumulation-texture
  * re-creation in Raytracer::resize (raytracer.rs:344): reallocates and zeroes
- * every plane. */
+ * every plane.  Buffers injected with ptc_set_output / ptc_set_reduce_output are
+ * dropped (their size is the old one): the step renders into its own planes
+ * until the caller injects new ones.  A bad size fails without touching the
+ * step; if allocation fails the previous size is restored (accumulation
+ * cleared), and if even that fails every later call reports the step invalid. */
 PTC_API int ptc_resize(ptc_step* step, uint32_t width, uint32_t height);
 
 /* the analogue of `step.output_texture_view = ...` (raytracer.rs:86): the
@@ -74,7 +78,9 @@ PTC_API int ptc_reset_accumulation(ptc_step* step);
 
 /* replaces BlitStep::render (src/render_steps/blit.rs:176-205, shaders/blit/blit.wgsl:35-40, shaders/common/color.wgsl:4-27):
  * Khronos PBR-neutral tonemap of an rgba32f image + the surface's sRGB encode (wgpu_util.rs:235-238) into the 8-bit
- * DISPLAY plane.  src = device pointer to width*height float4, NULL = the COLOR plane.  Enqueued on the step's stream. */
+ * DISPLAY plane.  src = device pointer to width*height float4, NULL = the COLOR plane.  Ordered after the frames already
+ * enqueued.  With src = NULL right after ptc_render the tonemap runs per frame part on the parts' own streams, so it
+ * does not hold the next frame back (the reference blits on its second queue while the RT queue renders on). */
 PTC_API int ptc_blit(ptc_step* step, const void* src_device_rgba32f);
 
 /* replaces RayprojectStep::render (src/render_steps/rayproject.rs:205-249, shaders/rayproject/rayproject.wgsl:45-74):
@@ -104,6 +110,13 @@ PTC_API int ptc_write(ptc_step* step, int plane, const void* src, size_t src_pit
 PTC_API int ptc_read_async(ptc_step* step, int plane, void* dst_pinned);
 PTC_API int ptc_read_wait(ptc_step* step);
 
+/* device-to-device copy of a plane into a caller-owned buffer with the caller's row pitch, enqueued on the step's stream —
+ * what DenoiseStep does before OIDN (src/render_steps/denoise.rs:84-100 copy_texture_to_buffer into a buffer whose rows
+ * are rounded up to 256 bytes, pt.rs:470-472).  dst_pitch_bytes = 0 means tightly packed.  The NORMAL / ALBEDO planes
+ * themselves are tightly packed float4 rows, exactly as the reference's shader writes them (index y*W + x,
+ * pathtracer/pathtracer.wgsl:272-273) and as OIDN reads them there (pixel stride 16, row stride 0, denoise.rs:137-160). */
+PTC_API int ptc_copy_plane(ptc_step* step, int plane, void* dst_device, size_t dst_pitch_bytes);
+
 /* zero-copy interop: device address of a plane (valid until resize/destroy) */
 PTC_API void* ptc_device_ptr(ptc_step* step, int plane);
 
@@ -111,14 +124,22 @@ PTC_API void* ptc_device_ptr(ptc_step* step, int plane);
  * order their own work after it */
 PTC_API void* ptc_stream(ptc_step* step);
 
-/* Multi-GPU: frames are sharded over one step per GPU, each accumulating with PTC_ACCUM_SUM; this enqueues,
- * on the step's stream, the in-place sum of the COLOR planes (rgb sums + sample counts, width*height*4 floats) of every
- * rank of `nccl_comm` into rank `root` — one ncclReduce(ncclFloat32, ncclSum), after the frames already enqueued.  The
- * reference has no counterpart (single GPU).  `nccl_comm` is the caller's ncclComm_t; the library binds to the NCCL the
- * process has already loaded (dlopen RTLD_NOLOAD "libnccl.so.2"), else loads the system one, so the communicator and the
- * call always come from the same NCCL.  root < 0: ncclAllReduce instead (every rank ends up with the sum, e.g. to display it).
- * Returns PTC_ERR_INVALID when no NCCL can be found. */
+/* Multi-GPU: frames are sharded over one step per GPU, each accumulating with PTC_ACCUM_SUM (any other mode
+ * is refused with PTC_ERR_INVALID: running means cannot be summed).  This enqueues, on the step's stream and after the
+ * frames already enqueued, ONE ncclReduce(ncclFloat32, ncclSum) of the COLOR planes (rgb sums + sample counts,
+ * width*height*4 floats) of every rank of `nccl_comm` into the REDUCED plane of rank `root` (PTC_PLANE_REDUCED: read it
+ * with ptc_read / ptc_device_ptr, or inject the receive buffer with ptc_set_reduce_output).  The COLOR plane — each
+ * rank's own accumulation — is left untouched, so the call may be repeated: a reduce after more frames receives every
+ * rank's whole history exactly once (an in-place reduce would add the earlier ranks' sums again).  On ranks other than
+ * the root the REDUCED plane's content is unspecified.  root < 0: ncclAllReduce instead (every rank receives the sum,
+ * e.g. to display it).  The reference has no counterpart (single GPU).
+ * `nccl_comm` is the caller's ncclComm_t.  The call binds to the NCCL that is ALREADY in the process — the loaded
+ * libnccl.so.2 (dlopen RTLD_NOLOAD), else a global ncclReduce symbol (static NCCL) — and never loads another copy, so
+ * communicator and call always come from the same NCCL; PTC_ERR_INVALID when there is none. */
 PTC_API int ptc_reduce(ptc_step* step, void* nccl_comm, int root);
+/* inject the receive buffer of ptc_reduce: a device pointer to width*height float4 (NULL restores the step-owned plane,
+ * allocated by the first ptc_reduce).  Dropped by ptc_resize, like the buffer of ptc_set_output. */
+PTC_API int ptc_set_reduce_output(ptc_step* step, void* device_rgba32f);
 
 PTC_API int ptc_get_stats(ptc_step* step, ptc_stats* out);
 

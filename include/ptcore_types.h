@@ -168,7 +168,8 @@ enum ptc_plane {
     PTC_PLANE_ALBEDO = 3,  /* float4 per pixel: first-hit albedo, w=1 (albedo_output) */
     PTC_PLANE_HIT_ID = 4,  /* uint32x2 per pixel: primary (instance_index, geometry_index); 0xFFFFFFFF,0xFFFFFFFF = miss */
     PTC_PLANE_DISPLAY = 5,     /* uint8x4 per pixel: tonemapped, sRGB-encoded RGBA (what ptc_blit produced; the swap-chain image) */
-    PTC_PLANE_REPROJECTED = 6  /* float4 per pixel: what ptc_rayproject produced (blit_storage_texture) */
+    PTC_PLANE_REPROJECTED = 6, /* float4 per pixel: what ptc_rayproject produced (blit_storage_texture) */
+    PTC_PLANE_REDUCED = 7      /* float4 per pixel: what ptc_reduce received (sum over ranks of rgb sums + sample counts) */
 };
 
 /* Per-step statistics (device counters, read at poll time). */

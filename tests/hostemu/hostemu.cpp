@@ -67,7 +67,7 @@ void emu_path_cfg(const void* ev, const ptc_uniforms* un_in, PathCfg* pc, ptc_un
     *out_un = *un_in; out_un->num_lights = e->ds.num_lights;
     pc->width = e->cfg.width; pc->height = e->cfg.height; pc->max_bounces = e->cfg.max_bounces;
     pc->send_to_light_probability = e->cfg.send_to_light_probability; pc->accum_mode = e->cfg.accum_mode; pc->is_grabbed = un_in->is_grabbed;
-    pc->light_sampling = e->cfg.light_sampling;
+    pc->light_sampling = e->cfg.light_sampling; pc->spp = 1; pc->sample = 0;
 }
 
 __attribute__((visibility("default")))
@@ -95,7 +95,7 @@ int emu_render_frame(const emu_scene* e, const ptc_uniforms* un_in, float* color
     const uint32_t W = e->cfg.width, H = e->cfg.height;
     PathCfg pc; pc.width = W; pc.height = H; pc.max_bounces = e->cfg.max_bounces;
     pc.send_to_light_probability = e->cfg.send_to_light_probability; pc.accum_mode = e->cfg.accum_mode; pc.is_grabbed = un.is_grabbed;
-    pc.light_sampling = e->cfg.light_sampling;
+    pc.light_sampling = e->cfg.light_sampling; pc.spp = 1; pc.sample = 0;
     if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
     if (nthreads <= 0) nthreads = 1;
     std::atomic<uint32_t> next_row(0);

@@ -100,3 +100,27 @@ def test_cpp_harness_builds_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 0 and (tmp_path / "o.pfm").exists()
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr
+
+
+def test_config_fields_without_meaning_are_refused(ptc, standins):
+    """ptc_create validates the whole ptc_config before it looks for a device: options this build gives no meaning to
+    (unknown compat flags, non-zero reserved words, an unsupported bvh_width, samples_per_pixel 0) are errors, never ignored."""
+    scene, _ = standins.cornell()
+    import ctypes as C
+    L, T = ptc.lib(), ptc.types
+    view = scene.view()
+    def create(**kw):
+        cfg = ptc.make_config(16, 16)
+        for k, v in kw.items():
+            if k == "reserved":
+                cfg.reserved[v] = 1
+            else:
+                setattr(cfg, k, v)
+        h = C.c_void_p()
+        rc = L.ptc_create(C.byref(view), C.byref(cfg), 0, C.byref(h))
+        if rc == 0:
+            L.ptc_destroy(h)
+        return rc, L.ptc_last_error().decode()
+    for kw in (dict(compat_flags=1), dict(reserved=0), dict(reserved=4), dict(bvh_width=3), dict(samples_per_pixel=0), dict(accum_mode=7)):
+        rc, msg = create(**kw)
+        assert rc == T.ERR_INVALID, (kw, rc, msg)

@@ -467,9 +467,21 @@ def test_ptc_reduce_binds_process_nccl(ptc, standins):
         step.poll(True)
         before = step.read(T.PLANE_COLOR)
         step.reduce(comm, 0); step.poll(True)
-        assert np.array_equal(step.read(T.PLANE_COLOR), before) and (before[..., 3] == 2).all()
-        step.reduce(comm, -1); step.poll(True)                            # root < 0: ncclAllReduce
+        # the sum arrives in the REDUCED plane; the rank's own accumulation is untouched, so a reduce can be repeated
+        assert np.array_equal(step.read(T.PLANE_REDUCED), before) and (before[..., 3] == 2).all()
         assert np.array_equal(step.read(T.PLANE_COLOR), before)
+        step.update(camera.uniforms(frame=3)); step.render()
+        step.reduce(comm, -1); step.poll(True)                            # root < 0: ncclAllReduce; after one more frame
+        after = step.read(T.PLANE_COLOR)
+        assert (after[..., 3] == 3).all() and np.array_equal(step.read(T.PLANE_REDUCED), after)
+        recv = torch.zeros(64, 96, 4, device="cuda:0")                    # caller-injected receive buffer
+        step.set_reduce_output(recv.data_ptr()); step.reduce(comm, 0); step.poll(True)
+        assert np.array_equal(recv.cpu().numpy(), after)
+        step.set_reduce_output(0)
+        mean_step = ptc.RTStep.create(scene, ptc.make_config(96, 64))     # PTC_ACCUM_MEAN: running means cannot be summed
+        with pytest.raises(ptc.PtcError, match="PTC_ACCUM_SUM"):
+            mean_step.reduce(comm, 0)
+        mean_step.destroy()
         with pytest.raises(ptc.PtcError):
             step.reduce(0, 0)
         step.destroy()
@@ -627,4 +639,77 @@ def test_many_frames_in_flight(ptc, standins, oracle):
     got = step.read(T.PLANE_COLOR)
     assert step.stats()["frame_parts"] == 2 and (got[..., 3] == frames).all()
     assert np.array_equal(got, ref["color"])
+    step.destroy()
+
+
+def test_samples_per_pixel_loop(ptc, standins, oracle):
+    """SAMPLES_PER_PIXEL > 1 (pathtracer/pathtracer.wgsl:258-266): the samples of a pixel re-trace the same primary ray with
+    the RNG stream running on, their mean enters the accumulation once per frame, aux planes come from the last sample."""
+    scene, cam = standins.random_soup(3000, seed=3)
+    for spp in (2, 3):
+        step, ref = render_both(ptc, standins, oracle, scene, cam, 96, 72, 2, samples_per_pixel=spp, max_bounces=3)
+        check_all_planes(ptc, step, ref)
+        assert (ref["color"][..., 3] == 2).all()
+        step.destroy()
+
+
+def test_blit_by_parts_equals_whole_frame_blit(ptc, standins):
+    """ptc_blit right after ptc_render tonemaps per frame part on the parts' streams; the DISPLAY plane must equal the one
+    the single whole-frame kernel produces (explicit src pointer = ordering-stream path), also while read_async snapshots
+    are in flight and on an odd frame size (right / bottom strips outside the 8x4 tiles)."""
+    import torch
+    T = ptc.types
+    scene, cam = standins.cornell()
+    W, H = 203, 131
+    step = ptc.RTStep.create(scene, ptc.make_config(W, H))
+    camera = standins.make_camera(cam, W, H)
+    pinned = torch.empty(H, W, 4, dtype=torch.uint8).pin_memory()
+    shots = []
+    for f in range(1, 6):
+        step.update(camera.uniforms(frame=f)); step.render(); step.blit()
+        step.read_async(T.PLANE_DISPLAY, pinned.data_ptr()); step.read_wait()
+        shots.append(pinned.numpy().copy())
+    step.poll(True)
+    by_parts = step.read(T.PLANE_DISPLAY)
+    assert np.array_equal(by_parts, shots[-1])
+    step.blit(step.device_ptr(T.PLANE_COLOR)); step.poll(True)
+    assert np.array_equal(step.read(T.PLANE_DISPLAY), by_parts)
+    assert step.stats()["frame_parts"] >= 2 and any(not np.array_equal(shots[0], x) for x in shots[1:])
+    step.destroy()
+
+
+def test_copy_plane_with_row_pitch(ptc, standins):
+    """ptc_copy_plane: device-to-device copy into a caller buffer whose rows are rounded up to 256 bytes (pt.rs:470-472)."""
+    import torch
+    T = ptc.types
+    scene, cam = standins.cornell()
+    W, H = 100, 40                                   # 1600-byte rows -> 1792-byte pitch
+    step = ptc.RTStep.create(scene, ptc.make_config(W, H))
+    camera = standins.make_camera(cam, W, H)
+    step.update(camera.uniforms(frame=1)); step.render()
+    pitch = (W * 16 + 255) // 256 * 256
+    for plane in (T.PLANE_NORMAL, T.PLANE_ALBEDO, T.PLANE_COLOR):
+        buf = torch.full((H, pitch // 4), -7.0, device="cuda:0")
+        step.copy_plane(plane, buf.data_ptr(), pitch); step.poll(True)
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[:, :W * 4].reshape(H, W, 4), step.read(plane)) and (got[:, W * 4:] == -7.0).all()
+    with pytest.raises(ptc.PtcError):
+        step.copy_plane(T.PLANE_COLOR, buf.data_ptr(), 64)
+    step.destroy()
+
+
+def test_resize_failure_keeps_the_step_usable(ptc, standins, oracle):
+    """A bad size is refused before anything is freed; the step renders on at its old size."""
+    T = ptc.types
+    scene, cam = standins.cornell()
+    step = ptc.RTStep.create(scene, ptc.make_config(64, 48))
+    camera = standins.make_camera(cam, 64, 48)
+    step.update(camera.uniforms(frame=1)); step.render(); step.poll(True)
+    before = step.read(T.PLANE_COLOR)
+    for w, h in ((0, 10), (70000, 70000)):
+        with pytest.raises(ptc.PtcError):
+            step.resize(w, h)
+    assert np.array_equal(step.read(T.PLANE_COLOR), before)
+    step.update(camera.uniforms(frame=2)); step.render(); step.poll(True)
+    assert (step.read(T.PLANE_COLOR)[..., 3] == 2).all()
     step.destroy()

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, steps, W, H, out_path):
+def _worker(rank, world, port, steps, extra, W, H, out_path):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -26,11 +26,17 @@ def _worker(rank, world, port, steps, W, H, out_path):
     img = np.zeros((H, W, 4), np.float32)
     for f in sh.frames_for_rank(rank, world, steps):
         orc.render_frame(camera.uniforms(frame=f), img, nthreads=1, want_aux=False)
-    t = torch.from_numpy(img)
-    sh.reduce_sum(t, dist, dst=0)
+    mine, recv = torch.from_numpy(img), torch.zeros(H, W, 4)
+    sh.reduce_into(recv, mine, dist, dst=0)                 # the semantics of ptc_reduce: COLOR -> REDUCED, COLOR untouched
+    first = recv.numpy().copy()
+    # a second report interval: more frames on every rank, then ANOTHER reduce of the whole accumulation — an in-place
+    # reduce would count the first interval of the other ranks twice here
+    for f in sh.frames_for_rank(rank, world, extra, first_frame=1 + world * steps):
+        orc.render_frame(camera.uniforms(frame=f), img, nthreads=1, want_aux=False)
+    sh.reduce_into(recv, mine, dist, dst=0)
     dist.barrier()
     if rank == 0:
-        np.save(out_path, t.numpy())
+        np.savez(out_path, first=first, second=recv.numpy())
     dist.destroy_process_group()
 
 
@@ -45,17 +51,30 @@ def test_frame_sharding_partition():
 
 def test_two_rank_gloo_reduce_equals_single_run(tmp_path, ptc, standins, oracle):
     import torch.multiprocessing as mp
-    world, steps, W, H = 2, 3, 40, 32
-    out = str(tmp_path / "sum.npy")
+    world, steps, extra, W, H = 2, 3, 2, 40, 32
+    out = str(tmp_path / "sum.npz")
     port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, steps, W, H, out), nprocs=world, join=True)
-    summed = np.load(out)
+    mp.spawn(_worker, args=(world, port, steps, extra, W, H, out), nprocs=world, join=True)
+    z = np.load(out)
     sh = importlib.import_module("wgpu-pathtracer_b200.sharding")
-    assert (summed[..., 3] == world * steps).all()
     scene, cam = standins.cornell()
     camera = standins.make_camera(cam, W, H)
     orc = oracle.OracleScene(scene, ptc.make_config(W, H))
     ref = np.zeros((H, W, 4), np.float32)
-    for f in sh.all_frames(world, steps):
-        orc.render_frame(camera.uniforms(frame=f), ref, want_aux=False)
-    np.testing.assert_allclose(sh.mean_from_sum(summed)[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6)
+    band = sh.band_rows(H, W, world * (steps + extra))
+    for n_frames, key in ((world * steps, "first"), (world * (steps + extra), "second")):
+        first_new = 1 if key == "first" else 1 + world * steps
+        for f in range(first_new, n_frames + 1):             # the single-process render of the same frame set, continued
+            orc.render_frame(camera.uniforms(frame=f), ref, want_aux=False)
+        chk = sh.reduce_check(z[key], n_frames, band, ref[band[0]:band[1]])      # the function bench.py reports with
+        assert chk["alpha_ok"] and chk["band_ok"], chk
+        np.testing.assert_allclose(sh.mean_from_sum(z[key])[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6)
+    assert not sh.reduce_check(z["second"], world * steps)["alpha_ok"]
+
+
+def test_band_rows_budget():
+    sh = importlib.import_module("wgpu-pathtracer_b200.sharding")
+    assert sh.band_rows(1080, 1920, 20) == (532, 548)          # 16 rows around the centre
+    y0, y1 = sh.band_rows(2160, 3840, 2048)
+    assert y1 - y0 == 2 and 0 <= y0 < y1 <= 2160               # never fewer than two rows
+    assert sh.band_rows(8, 16, 1) == (0, 8)

@@ -217,3 +217,56 @@ def test_obj_zero_and_plus_indices(ptc, standins):
     assert len(sc.indices) == 3
     with pytest.raises(ptc.PtcError, match="bad face element"):
         ptc.Scene(standins.make_envmap(8, 4)).load_obj(obj_text=base + "f 0 1 2\n", mtl_text=MTL, obj_dir="standin", decode=tiny_decode(ptc))
+
+
+def test_failed_load_rolls_the_scene_back(ptc, standins):
+    """A load that fails late (here: a mesh without material in an OBJ that loads no MTL, detected after materials,
+    vertices and indices were appended) must leave the scene exactly as it was: the reference panics, so no half-loaded
+    Scene exists there either."""
+    import ctypes as C
+    L, T = ptc.lib(), ptc.types
+    h = C.c_void_p()
+    assert L.ptc_scene_new(b"<envmap>", C.byref(h)) == 0
+    try:
+        good = b"mtllib m.mtl\nusemtl a\nv 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n"
+        assert L.ptc_scene_load_obj_text(h, good, b"newmtl a\nKd 0.25 0.5 0.75\n", b"") == 0
+        ntex = L.ptc_scene_num_textures(h)
+        texel = np.zeros((1, 1, 4), np.float32)
+        assert L.ptc_scene_set_texels(h, 9, 1, 1, T.TEXEL_RGBA32F, texel.ctypes.data_as(C.c_void_p)) == 0
+        v0 = T.SceneView(); assert L.ptc_scene_get_view(h, C.byref(v0)) == 0
+        before = (v0.num_vertices, v0.num_indices, v0.num_meshes, v0.num_materials, v0.num_textures)
+        # second load: first mesh fine (new material + constant texture are pushed), second mesh mixes normals -> PTC_ERR_PARSE
+        bad = b"mtllib n.mtl\nusemtl b\nv 0 0 1\nv 1 0 1\nv 0 1 1\nf 1 2 3\no two\nvn 0 0 1\nv 0 0 2\nv 1 0 2\nv 0 1 2\nf 4//1 5//1 6\n"
+        rc = L.ptc_scene_load_obj_text(h, bad, b"newmtl b\nKd 0.1 0.2 0.3\nKe 3 3 3\n", b"")
+        assert rc == T.ERR_PARSE, L.ptc_last_error()
+        assert L.ptc_scene_num_textures(h) == ntex
+        v1 = T.SceneView(); assert L.ptc_scene_get_view(h, C.byref(v1)) == 0
+        assert (v1.num_vertices, v1.num_indices, v1.num_meshes, v1.num_materials, v1.num_textures) == before
+        assert v1.num_meshes == 1 and v1.num_indices == 3
+    finally:
+        L.ptc_scene_free(h)
+
+
+def test_mtl_floats_do_not_depend_on_the_locale(ptc, standins):
+    """MTL scalars are parsed like Rust's f32::from_str (locale-free): a process running under a comma-decimal LC_NUMERIC
+    reads `Pr 0.25` as 0.25, not 0."""
+    import locale
+    mtl = "newmtl a\nKd 0.5 0.25 0.125\nPr 0.25\nNi 1.5\nPm +0.5\nPs 1e-1\n"
+    obj = "mtllib m.mtl\nusemtl a\nv 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n"
+    def load():
+        sc = ptc.Scene(standins.make_envmap(8, 4)).load_obj(obj_text=obj, mtl_text=mtl)
+        m = sc.materials[1]
+        return [sc.textures[int(m[k])].texels.reshape(-1)[:3].tolist() for k in ("albedo_texture_idx", "roughness_texture_idx", "ior_texture_idx", "metallic_texture_idx", "sheen_texture_idx")]
+    want = load()
+    assert want[0] == [0.5, 0.25, 0.125] and want[1][0] == 0.25 and want[2][0] == 1.5 and want[3][0] == 0.5 and want[4][0] == np.float32(0.1)
+    old = locale.setlocale(locale.LC_NUMERIC)
+    switched = False
+    for name in ("de_DE.UTF-8", "fr_FR.UTF-8", "de_DE", "fr_FR"):
+        try:
+            locale.setlocale(locale.LC_NUMERIC, name); switched = True; break
+        except locale.Error:
+            continue
+    try:
+        assert load() == want          # (when no comma locale is installed this still checks from_chars == the old result)
+    finally:
+        locale.setlocale(locale.LC_NUMERIC, old)

@@ -46,6 +46,7 @@ def lib():
         "ptc_read": (i32, [vp, i32, vp, sz]),
         "ptc_read_async": (i32, [vp, i32, vp]),
         "ptc_read_wait": (i32, [vp]),
+        "ptc_copy_plane": (i32, [vp, i32, vp, sz]),
         "ptc_device_ptr": (vp, [vp, i32]),
         "ptc_stream": (vp, [vp]),
         "ptc_get_stats": (i32, [vp, P(T.Stats)]),
@@ -54,6 +55,7 @@ def lib():
         "ptc_num_lights": (i32, [vp, P(u32)]),
         "ptc_bvh_info": (i32, [vp, P(u64)]),
         "ptc_reduce": (i32, [vp, vp, i32]),
+        "ptc_set_reduce_output": (i32, [vp, vp]),
         "ptc_write": (i32, [vp, i32, vp, C.c_size_t]),
         "ptc_debug_bvh_hash": (i32, [vp, P(u64)]),
         "ptc_trace_rays": (i32, [vp, vp, u64, vp, vp]),

@@ -133,6 +133,7 @@ struct PathCfg {
     float send_to_light_probability;
     uint32_t accum_mode, is_grabbed;
     uint32_t light_sampling;      // ptc_light_sampling
+    uint32_t spp, sample;         // SAMPLES_PER_PIXEL and the index of the sample this pass renders (pathtracer/pathtracer.wgsl:258-266)
 };
 
 // ---- RNG: src/shaders/common/random.wgsl:7-36 ---------------------------------

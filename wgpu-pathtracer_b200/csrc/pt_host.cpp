@@ -128,10 +128,23 @@ struct TobjModel {
 // Rust's f32::from_str accepts decimal / exponent / inf / nan with optional sign and nothing else.
 bool parse_f32(const std::string& s, float* out) {
     if (s.empty()) return false;
-    for (char ch : s) if (ch == 'x' || ch == 'X' || ch == ' ' || ch == '\t') return false;
-    char* end = nullptr;
-    float v = std::strtof(s.c_str(), &end);
-    if (end == s.c_str() || *end != '\0') return false;
+    // std::from_chars is locale-independent (strtof follows LC_NUMERIC: "0.8" would stop at the '.' under a comma locale)
+    // and correctly rounded.  It takes no leading '+', Rust does; "inf" / "nan" / "infinity" in any case are accepted by both.
+    const char* a = s.data(); const char* b = a + s.size();
+    if (*a == '+') { ++a; if (a == b || *a == '+' || *a == '-') return false; }
+    for (const char* c = a; c < b; ++c) if (*c == 'x' || *c == 'X' || *c == ' ' || *c == '\t' || *c == '(') return false;
+    float v = 0.0f;
+    const std::from_chars_result r = std::from_chars(a, b, v);
+    if (r.ptr != b) return false;
+    if (r.ec == std::errc::result_out_of_range) {
+        // Rust (and strtof) round overflow to infinity and underflow to zero / a subnormal instead of failing: take the value
+        // through double, whose range covers every f32 overflow / underflow a file could plausibly hold
+        double dv = 0.0;
+        const std::from_chars_result rd = std::from_chars(a, b, dv);
+        if (rd.ptr != b) return false;
+        if (rd.ec == std::errc()) v = (float)dv;
+        else { const bool neg = *a == '-'; bool tiny = false; for (const char* c = a; c < b; ++c) if ((*c == 'e' || *c == 'E') && c + 1 < b && c[1] == '-') tiny = true; v = tiny ? 0.0f : HUGE_VALF; if (neg) v = -v; }
+    } else if (r.ec != std::errc()) return false;
     *out = v; return true;
 }
 
@@ -539,7 +552,18 @@ int parse_obj(const std::string& text, const std::string& mtl_override, bool use
     return PTC_OK;
 }
 
+int ingest_unchecked(ptc_scene* s, const std::vector<TobjModel>& models, const std::vector<TobjMaterial>& mats, const std::string& dir);
+// The reference panics on a bad OBJ/MTL, so no half-loaded Scene ever exists there; here a failing load rolls the scene
+// back to the sizes it had before the call (the arrays only ever grow inside one load), so the caller keeps a usable scene.
 int ingest(ptc_scene* s, const std::vector<TobjModel>& models, const std::vector<TobjMaterial>& mats, const std::string& dir) {
+    const size_t n_mat = s->materials.size(), n_tex = s->textures.size(), n_vtx = s->vertices.size(), n_idx = s->indices.size(), n_mesh = s->meshes.size();
+    const int rc = ingest_unchecked(s, models, mats, dir);
+    if (rc != PTC_OK) {
+        s->materials.resize(n_mat); s->textures.resize(n_tex); s->vertices.resize(n_vtx); s->indices.resize(n_idx); s->meshes.resize(n_mesh);
+    }
+    return rc;
+}
+int ingest_unchecked(ptc_scene* s, const std::vector<TobjModel>& models, const std::vector<TobjMaterial>& mats, const std::string& dir) {
     const size_t prev_num_materials = s->materials.size();
     for (const TobjMaterial& m : mats) {                                                  // scene.rs:134-167
         ptc_material out; std::memset(&out, 0, sizeof(out));

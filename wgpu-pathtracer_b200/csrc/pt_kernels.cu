@@ -16,36 +16,44 @@ constexpr int kShadeThreads = PTC_SHADE_THREADS;
 #endif
 
 // ---- raygen: rand_init + primary ray (pathtracer.wgsl:27, pathtracer/pathtracer.wgsl:240-250) ----
-__global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;       // slot in this part's queue
-    if (j == 0) fc->count[0] = n;
-    if (j >= n) return;
-    const uint32_t i = (((j >> 5) * num_parts + part) << 5) | (j & 31u);   // slot in the frame's order: warps are dealt round-robin to the parts
-    // Queue slot i -> pixel: 8x4 pixel tiles, one tile per warp, so the 32 primary rays of a warp (and the paths that
-    // descend from them, which k_shade compacts in queue order) share BVH nodes and texture lines; a scanline run of 32
-    // pixels diverges sooner.  Pixels outside the tile-aligned part (right strip, then bottom strip) follow in row
-    // order.  The reference's thread -> pixel map (pathtracer.wgsl:22-24) is not observable: every pixel's result
-    // depends only on (x, y, frame).
-    const uint32_t W = un.camera.width, H = un.camera.height, W8 = W & ~7u, H4 = H & ~3u;
-    uint32_t x, y;
+// Queue slot i -> pixel: 8x4 pixel tiles, one tile per warp, so the 32 primary rays of a warp (and the paths that
+// descend from them, which k_shade compacts in queue order) share BVH nodes and texture lines; a scanline run of 32
+// pixels diverges sooner.  Pixels outside the tile-aligned part (right strip, then bottom strip) follow in row
+// order.  The reference's thread -> pixel map (pathtracer.wgsl:22-24) is not observable: every pixel's result
+// depends only on (x, y, frame).
+__device__ __forceinline__ void slot_to_pixel(uint32_t i, uint32_t W, uint32_t H, uint32_t& x, uint32_t& y) {
+    const uint32_t W8 = W & ~7u, H4 = H & ~3u;
 #ifdef PTC_RAYGEN_LINEAR
-    if (false) {
+    x = i % W; y = i / W; (void)W8; (void)H4;
 #else
     if (i < W8 * H4) {
-#endif
         const uint32_t tile = i >> 5, in = i & 31u, tpr = W8 >> 3;
         x = (tile % tpr) * 8u + (in & 7u); y = (tile / tpr) * 4u + (in >> 3);
-#ifdef PTC_RAYGEN_LINEAR
-    } else if (true) { x = i % W; y = i / W;
-#endif
     } else {
         uint32_t j = i - W8 * H4;
         const uint32_t rw = W - W8;
         if (j < rw * H4) { x = W8 + j % rw; y = j / rw; }
         else { j -= rw * H4; x = j % W; y = H4 + j / W; }
     }
+#endif
+}
+// slot j of part `part` -> slot in the frame's order: warps are dealt round-robin to the parts
+__device__ __forceinline__ uint32_t part_slot(uint32_t j, uint32_t num_parts, uint32_t part) { return (((j >> 5) * num_parts + part) << 5) | (j & 31u); }
+
+// spp_rng: null for the first sample of a frame; for sample s > 0 of SAMPLES_PER_PIXEL > 1 the pixel's RNG state where its
+// previous sample's path ended — pixel_color's loop re-traces the SAME rd with the stream simply running on
+// (pathtracer/pathtracer.wgsl:258-266)
+__global__ void __launch_bounds__(256) k_raygen(ptc_uniforms un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part,
+                                                const uint32_t* __restrict__ spp_rng) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;       // slot in this part's queue
+    if (j == 0) fc->count[0] = n;
+    if (j >= n) return;
+    const uint32_t W = un.camera.width, H = un.camera.height;
+    uint32_t x, y;
+    slot_to_pixel(part_slot(j, num_parts, part), W, H, x, y);
     uint32_t rng; pt_v3 ro, rd;
     gen_primary(un.camera, x, y, rng, ro, rd);
+    if (spp_rng) rng = spp_rng[y * W + x];
     st4_stream(q.ray_o + j, ro.x, ro.y, ro.z, __uint_as_float(y * W + x));
     st4_stream(q.ray_d + j, rd.x, rd.y, rd.z, __uint_as_float(rng));
     // color_mask = 1 and accumulated_color = 0 at segment 0 are constants of k_shade<true>: not stored
@@ -368,7 +376,21 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             pt_v3 radiance;
             alive = combine_path(so, mask, acc, radiance, pdf_prev);
             no = so.next_o; nd = so.next_d; rng = so.rng;
-            if (!alive) accumulate_pixel(planes.color + pixel, radiance, cfg.accum_mode, cfg.is_grabbed);   // pathtracer.wgsl:32-42
+            if (!alive) {
+                if (cfg.spp > 1u) {
+                    // SAMPLES_PER_PIXEL > 1 (pathtracer/pathtracer.wgsl:258-266): the samples of a pixel run one after the other
+                    // on one RNG stream; their sum lives in spp_sum, the stream's state in spp_rng, and the last sample hands
+                    // sum / SPP to the accumulation
+                    F4* sp = planes.spp_sum + pixel;
+                    pt_v3 sum = radiance;
+                    if (cfg.sample != 0u) { const F4 p = *sp; sum = pt_mk3(p.x + radiance.x, p.y + radiance.y, p.z + radiance.z); }
+                    if (cfg.sample + 1u < cfg.spp) { sp->x = sum.x; sp->y = sum.y; sp->z = sum.z; sp->w = 0.0f; planes.spp_rng[pixel] = rng; }
+                    else {
+                        const float nspp = (float)cfg.spp;
+                        accumulate_pixel(planes.color + pixel, pt_mk3(pt_div(sum.x, nspp), pt_div(sum.y, nspp), pt_div(sum.z, nspp)), cfg.accum_mode, cfg.is_grabbed);
+                    }
+                } else accumulate_pixel(planes.color + pixel, radiance, cfg.accum_mode, cfg.is_grabbed);   // pathtracer.wgsl:32-42
+            }
         }
         // warp-aggregated slot allocation in the next queue
         const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
@@ -403,8 +425,8 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
-void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part) {
-    k_raygen<<<(n + 255) / 256, 256, 0, st>>>(un, q, fc, n, num_parts, part);
+void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part, const uint32_t* spp_rng) {
+    k_raygen<<<(n + 255) / 256, 256, 0, st>>>(un, q, fc, n, num_parts, part, spp_rng);
 }
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays, unsigned long long* packet_stats) {
@@ -494,6 +516,21 @@ __global__ void k_blit(const F4* __restrict__ src, uchar4* __restrict__ dst, uin
     const F4 c = ld4(src + i);
     const pt_v3 t = tonemap_khronos_pbr_neutral(pt_mk3(c.x, c.y, c.z));
     dst[i] = make_uchar4((unsigned char)encode_srgb8(t.x), (unsigned char)encode_srgb8(t.y), (unsigned char)encode_srgb8(t.z), (unsigned char)encode_unorm8(c.w));
+}
+// the same for the pixels of ONE frame part (slot order of k_raygen): runs on the part's own stream right behind the part's
+// last shade, so presenting a frame does not make the parts wait for each other (the reference blits on its second queue)
+__global__ void k_blit_part(const F4* __restrict__ src, uchar4* __restrict__ dst, uint32_t n, uint32_t num_parts, uint32_t part, uint32_t W, uint32_t H) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t x, y;
+    slot_to_pixel(part_slot(j, num_parts, part), W, H, x, y);
+    const uint32_t i = y * W + x;
+    const F4 c = ld4(src + i);
+    const pt_v3 t = tonemap_khronos_pbr_neutral(pt_mk3(c.x, c.y, c.z));
+    dst[i] = make_uchar4((unsigned char)encode_srgb8(t.x), (unsigned char)encode_srgb8(t.y), (unsigned char)encode_srgb8(t.z), (unsigned char)encode_unorm8(c.w));
+}
+void launch_blit_part(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n, uint32_t num_parts, uint32_t part, uint32_t W, uint32_t H) {
+    if (n) k_blit_part<<<(n + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<uchar4*>(dst_rgba8), n, num_parts, part, W, H);
 }
 void launch_reproject(cudaStream_t st, const ptc_camera& cam, const ptc_camera& prev, const float* depth, uint32_t* owner, const F4* src, F4* dst) {
     const uint32_t ns = prev.width * prev.height, nd = cam.width * cam.height;

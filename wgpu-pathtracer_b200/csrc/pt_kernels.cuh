@@ -44,10 +44,12 @@ struct Planes {
     F4* normal;           // normals_output
     F4* albedo;           // albedo_output
     uint32_t* hit_tri;    // primary-hit global triangle id (0xFFFFFFFF = miss)
+    F4* spp_sum;          // SAMPLES_PER_PIXEL > 1 only: radiance summed over the samples of the frame so far ...
+    uint32_t* spp_rng;    // ... and the pixel's RNG state after its latest sample
 };
 
 // part `part` of `num_parts`: its n queue slots are the warps t = part, part + num_parts, ... of the frame's slot order
-void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part);
+void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounters* fc, uint32_t n, uint32_t num_parts, uint32_t part, const uint32_t* spp_rng = nullptr);
 // impl 3 = packet traversal (primary rays in tile order); packet_stats (optional): [0] += node visits, [1] += lanes entering a child
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays, unsigned long long* packet_stats = nullptr);
@@ -63,6 +65,7 @@ void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* 
 // display path: rayproject.wgsl (forward reprojection of the last real frame) and blit.wgsl (tonemap to the 8-bit surface)
 void launch_reproject(cudaStream_t st, const ptc_camera& cam, const ptc_camera& prev, const float* depth, uint32_t* owner, const F4* src, F4* dst);
 void launch_blit(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n);
+void launch_blit_part(cudaStream_t st, const F4* src, void* dst_rgba8, uint32_t n, uint32_t num_parts, uint32_t part, uint32_t W, uint32_t H);
 void launch_unorm_probe(cudaStream_t st, unsigned long long tex_obj, float* out512);   // x and w channels of a 256x1 RGBA8 ramp
 void launch_sample(cudaStream_t st, const DevScene& s, uint32_t tex, int sky, const float* in, float* out, uint32_t n, uint32_t tex_mod);
 void launch_l2_read(cudaStream_t st, int device, const void* buf, uint64_t bytes, uint32_t iters, float* sink);   // L2 bandwidth probe

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -81,6 +83,12 @@ struct ptc_step {
     Planes planes{}; F4* owned_color = nullptr; F4* d_snapshot = nullptr; size_t snapshot_bytes = 0;
     // display path (allocated on first use): tonemapped RGBA8 image, reprojected rgba32f image, splat ownership
     void* d_display = nullptr; F4* d_reprojected = nullptr; uint32_t* d_owner = nullptr;
+    // ptc_reduce receives into its own plane (REDUCED), so the per-rank accumulation is never overwritten and a later
+    // reduce — after more frames — sums each rank's whole history exactly once.  Caller-injectable like COLOR.
+    F4* owned_reduced = nullptr; F4* reduced = nullptr;
+    bool invalid = false;                          // a failed ptc_resize left the step without frame buffers
+    cudaEvent_t ev_display_free = nullptr; bool display_busy = false;   // a read_async snapshot of DISPLAY is pending on the ordering stream
+    bool blit_by_parts = true;                     // PTC_BLIT_PARTS=0: always tonemap on the ordering stream (A/B timing)
     uint32_t npix = 0;
     int trace_grid = 0, shade_grid = 0;
     // Primary rays: packet traversal (k_trace_packet) pays off when the 32 rays of a tile stay together — 1.3-1.45x on
@@ -102,6 +110,21 @@ struct ptc_step {
     std::vector<int> ev_tag;                       // tag of the stage that STARTS at event i (-1 = end of frame)
     double prof_ms[3] = {0, 0, 0}; uint64_t prof_n[3] = {0, 0, 0};   // 0 raygen, 1 trace, 2 shade
 };
+
+static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
+    if (s->invalid) return false;
+    switch (plane) {
+        case PTC_PLANE_COLOR: *p = s->planes.color; *px_bytes = 16; return true;
+        case PTC_PLANE_DEPTH: *p = s->planes.depth; *px_bytes = 4; return true;
+        case PTC_PLANE_NORMAL: *p = s->planes.normal; *px_bytes = 16; return true;
+        case PTC_PLANE_ALBEDO: *p = s->planes.albedo; *px_bytes = 16; return true;
+        case PTC_PLANE_HIT_ID: *p = s->planes.hit_tri; *px_bytes = 4; return true;
+        case PTC_PLANE_DISPLAY: *p = s->d_display; *px_bytes = 4; return s->d_display != nullptr;
+        case PTC_PLANE_REPROJECTED: *p = s->d_reprojected; *px_bytes = 16; return s->d_reprojected != nullptr;
+        case PTC_PLANE_REDUCED: *p = s->reduced; *px_bytes = 16; return s->reduced != nullptr;
+    }
+    return false;
+}
 
 static void prof_mark(ptc_step* s, int tag) {
     if (!s->profiling) return;
@@ -132,7 +155,7 @@ static int unorm8_probe(float out[512]) {
     for (int i = 0; i < 256; ++i) ramp[i] = make_uchar4((unsigned char)i, 0, 0, (unsigned char)(255 - i));
     cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
     cudaArray_t arr = nullptr; cudaTextureObject_t obj = 0; float* d_out = nullptr;
-    int rc = PTC_OK;
+    int rc = PTC_OK; cudaError_t launch_err = cudaSuccess;
     do {
         if (cudaMallocArray(&arr, &cd, 256, 1) != cudaSuccess || cudaMalloc(&d_out, 512 * sizeof(float)) != cudaSuccess) { rc = PTC_ERR_OOM; break; }
         if (cudaMemcpy2DToArray(arr, 0, 0, ramp, 256 * 4, 256 * 4, 1, cudaMemcpyHostToDevice) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
@@ -142,9 +165,10 @@ static int unorm8_probe(float out[512]) {
         td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 0;
         if (cudaCreateTextureObject(&obj, &rd, &td, nullptr) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
         launch_unorm_probe(nullptr, (unsigned long long)obj, d_out);
+        if ((launch_err = cudaGetLastError()) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }   // e.g. cudaErrorNoKernelImageForDevice on a non-sm_100a GPU
         if (cudaMemcpy(out, d_out, 512 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = PTC_ERR_CUDA; break; }
     } while (0);
-    if (rc != PTC_OK) { set_error(std::string("unorm8 probe: ") + cudaGetErrorString(cudaGetLastError())); }
+    if (rc != PTC_OK) { set_error(std::string("unorm8 probe: ") + cudaGetErrorString(launch_err != cudaSuccess ? launch_err : cudaGetLastError())); }
     if (obj) cudaDestroyTextureObject(obj);
     if (arr) cudaFreeArray(arr);
     cudaFree(d_out);
@@ -154,17 +178,23 @@ static int unorm8_probe(float out[512]) {
 // 1 iff the texture unit converts every u8 value to exactly rn(v / 255.0f) — the value texture.rs:241 (`to_rgba32f`)
 // produces and the oracle uses.  Evaluated once per process on the device being created; decides the device
 // encoding of 8-bit textures (PTC_DEVTEX_UNORM8 vs read-bytes-and-divide).  PTC_UNORM8=div forces the latter.
-static int unorm8_hw_exact() {
-    static int cached = -1;
-    if (cached >= 0) return cached;
+// Returns 1 / 0, or a negative ptc_status when the probe itself could not run (e.g. no kernel image for this GPU: the
+// library is built for sm_100a only) — ptc_create reports that instead of failing at the first ptc_render.
+static int unorm8_hw_exact(int device) {
+    static std::mutex mu;
+    static std::map<int, int> cached;              // per device: steps on different GPUs are created from different threads
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cached.find(device);
+    if (it != cached.end()) return it->second;
     const char* e = getenv("PTC_UNORM8");
-    if (e && std::strcmp(e, "div") == 0) { cached = 0; return 0; }
+    if (e && std::strcmp(e, "div") == 0) { cached[device] = 0; return 0; }
     float out[512];
-    if (unorm8_probe(out) != PTC_OK) { cached = 0; return 0; }
+    int rc = unorm8_probe(out);
+    if (rc != PTC_OK) return rc;                   // not cached: the error is reported, a later create may retry
     int ok = 1;
     for (int i = 0; i < 256; ++i)
         if (out[i] != pt_div((float)i, 255.0f) || out[256 + i] != pt_div((float)(255 - i), 255.0f)) { ok = 0; break; }
-    cached = ok;
+    cached[device] = ok;
     return ok;
 }
 
@@ -182,8 +212,10 @@ static void free_frame_buffers(ptc_step* s) {
     }
     cudaFree(s->owned_color); s->owned_color = nullptr;
     cudaFree(s->planes.depth); cudaFree(s->planes.normal); cudaFree(s->planes.albedo); cudaFree(s->planes.hit_tri);
+    cudaFree(s->planes.spp_sum); cudaFree(s->planes.spp_rng);
     cudaFree(s->d_snapshot); s->d_snapshot = nullptr; s->snapshot_bytes = 0;
     cudaFree(s->d_display); s->d_display = nullptr; cudaFree(s->d_reprojected); s->d_reprojected = nullptr; cudaFree(s->d_owner); s->d_owner = nullptr;
+    cudaFree(s->owned_reduced); s->owned_reduced = nullptr; s->reduced = nullptr;
     s->planes = Planes{};
 }
 
@@ -222,6 +254,7 @@ static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
     CK(cudaMalloc(&s->planes.normal, (size_t)n * 16));
     CK(cudaMalloc(&s->planes.albedo, (size_t)n * 16));
     CK(cudaMalloc(&s->planes.hit_tri, (size_t)n * 4));
+    if (s->cfg.samples_per_pixel > 1) { CK(cudaMalloc(&s->planes.spp_sum, (size_t)n * 16)); CK(cudaMalloc(&s->planes.spp_rng, (size_t)n * 4)); }
     s->planes.color = s->owned_color;
     CK(cudaMemsetAsync(s->owned_color, 0, (size_t)n * 16, s->stream));
     CK(cudaMemsetAsync(s->planes.depth, 0, (size_t)n * 4, s->stream));
@@ -284,7 +317,8 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
     // textures (texture.rs:232-336): shelf-packed into atlas pages, one cudaArray + texture object per page
     std::vector<TexDev> texs(v->num_textures);
     {
-        const int hw_unorm = unorm8_hw_exact();
+        const int hw_unorm = unorm8_hw_exact(s->device);
+        if (hw_unorm < 0) return hw_unorm;
         int max_w = 0, max_h = 0;
         CK(cudaDeviceGetAttribute(&max_w, cudaDevAttrMaxTexture2DWidth, s->device));
         CK(cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DHeight, s->device));
@@ -396,6 +430,7 @@ static void destroy_step(ptc_step* s) {
     if (s->snap_ready) cudaEventDestroy(s->snap_ready);
     if (s->copy_done) cudaEventDestroy(s->copy_done);
     if (s->ev_main) cudaEventDestroy(s->ev_main);
+    if (s->ev_display_free) cudaEventDestroy(s->ev_display_free);
     for (auto& P : s->parts) {
         if (P.done) cudaEventDestroy(P.done);
         if (P.primary_done) cudaEventDestroy(P.primary_done);
@@ -419,11 +454,15 @@ PTC_API int ptc_device_count(void) {
 PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, int cuda_device, ptc_step** out) {
     if (!scene || !config || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
     *out = nullptr;
-    if (config->samples_per_pixel != 1) { set_error("samples_per_pixel must be 1 (SAMPLES_PER_PIXEL, shader_definitions.rs:17); call ptc_render once per sample"); return PTC_ERR_INVALID; }
+    if (config->samples_per_pixel == 0 || config->samples_per_pixel > 1024) { set_error("samples_per_pixel must be in 1..1024 (SAMPLES_PER_PIXEL, shader_definitions.rs:17)"); return PTC_ERR_INVALID; }
     if (config->max_bounces + 1 > PTC_MAX_SEGMENTS) { set_error("max_bounces too large"); return PTC_ERR_INVALID; }
     if (config->accum_mode > PTC_ACCUM_SUM) { set_error("bad accum_mode"); return PTC_ERR_INVALID; }
     if (config->light_sampling > PTC_LIGHTS_MIS) { set_error("bad light_sampling"); return PTC_ERR_INVALID; }
     if (config->bvh_build > PTC_BVH_LBVH_DEVICE) { set_error("bad bvh_build"); return PTC_ERR_INVALID; }
+    // fields this build gives no meaning to must be zero, so a caller never believes an option took effect
+    if (config->bvh_width != 0 && config->bvh_width != 2) { set_error("bad bvh_width (0 = library default, 2 = BVH2)"); return PTC_ERR_INVALID; }
+    if (config->compat_flags != PTC_COMPAT_NONE) { set_error("unknown compat_flags (none are defined)"); return PTC_ERR_INVALID; }
+    for (uint32_t r : config->reserved) if (r != 0) { set_error("ptc_config.reserved must be zero"); return PTC_ERR_INVALID; }
     if (config->light_sampling == PTC_LIGHTS_MIS && config->send_to_light_probability != 0.0f) { set_error("PTC_LIGHTS_MIS requires send_to_light_probability == 0"); return PTC_ERR_INVALID; }
     int ndev = ptc_device_count();
     if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
@@ -446,9 +485,11 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
                        cudaEventCreateWithFlags(&P.primary_free, cudaEventDisableTiming) == cudaSuccess;
         }
         { const char* e = getenv("PTC_OVERLAP"); s->overlap = !(e && std::strcmp(e, "0") == 0); }
+        { const char* e = getenv("PTC_BLIT_PARTS"); s->blit_by_parts = !(e && std::strcmp(e, "0") == 0); }
         if (!parts_ok) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
         if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_display_free, cudaEventDisableTiming) != cudaSuccess ||
             cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming) != cudaSuccess) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
@@ -484,6 +525,7 @@ PTC_API int ptc_update(ptc_step* s, const ptc_uniforms* u) {
 
 PTC_API int ptc_render(ptc_step* s) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     if (!s->have_uniforms) { set_error("ptc_render before ptc_update"); return PTC_ERR_INVALID; }
     if (s->uniforms.camera.width != s->cfg.width || s->uniforms.camera.height != s->cfg.height) { set_error("uniform size differs from step size; call ptc_resize"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
@@ -510,34 +552,41 @@ PTC_API int ptc_render(ptc_step* s) {
     const bool wait_main = s->main_dirty && !s->profiling;
     if (wait_main) CK(cudaEventRecord(s->ev_main, s->stream));
     s->main_dirty = false;
-    const uint32_t ring = s->fc_next++ % kFcRing;
     // stage timing renders the frame as ONE part on the ordering stream, so that the per-stage CUDA-event times are exclusive
     // and each launch covers a whole segment of the frame (same image: pixels do not care which part they are in)
     const uint32_t nparts = s->profiling ? 1u : s->num_parts;
+    const uint32_t spp = s->cfg.samples_per_pixel;
+    pc.spp = spp;
     for (uint32_t p = 0; p < nparts; ++p) {
         ptc_step::FramePart& P = s->parts[s->profiling ? ptc_step::kMaxParts : p];
         cudaStream_t st = s->profiling ? s->stream : P.stream;
-        const bool prefetch = s->overlap && !s->profiling;
+        // SAMPLES_PER_PIXEL > 1: sample k of a pixel starts from the RNG state sample k-1 ended with, so the samples of a part
+        // run back to back on the part's stream (no primary-ray prefetch: its queue is reused by every sample)
+        const bool prefetch = s->overlap && !s->profiling && spp == 1;
         cudaStream_t st0 = prefetch ? P.prefetch_stream : st;
-        FrameCounters* fc = s->d_fc + ((size_t)ring * ptc_step::kMaxParts + p);
         if (prefetch) CK(cudaStreamWaitEvent(st0, P.primary_free, 0));      // the previous frame's shade(0) has consumed qp / d_hits_p
-        CK(cudaMemsetAsync(fc, 0, sizeof(FrameCounters), st0));
-        prof_mark(s, 0);
-        launch_raygen(st0, s->uniforms, P.qp, fc, P.n, nparts, p);
-        prof_mark(s, 1);
-        // primary rays arrive in 8x4-pixel tiles, one per warp: packet traversal (pt_kernels.cu); PTC_PRIMARY_PACKETS=0 uses k_trace
-        launch_trace(st0, s->trace_grid, use_packets ? 3 : s->trace_impl, s->scene, P.qp, P.d_hits_p, fc, 0, s->d_total_rays, s->d_total_rays + 1);
-        if (prefetch) { CK(cudaEventRecord(P.primary_done, st0)); CK(cudaStreamWaitEvent(st, P.primary_done, 0)); }
-        if (wait_main) CK(cudaStreamWaitEvent(st, s->ev_main, 0));
-        s->launches += 1;
-        for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
-            if (seg) { prof_mark(s, 1); launch_trace(st, s->trace_grid, s->trace_impl, s->scene, P.q[seg & 1], P.d_hits, fc, seg, s->d_total_rays); }
-            prof_mark(s, 2);
-            launch_shade(st, s->shade_grid, s->scene, pc, seg ? P.q[seg & 1] : P.qp, P.q[(seg + 1) & 1], seg ? P.d_hits : P.d_hits_p, fc, seg, s->planes, P.shq);
-            if (seg == 0 && prefetch) CK(cudaEventRecord(P.primary_free, st));
+        for (uint32_t sample = 0; sample < spp; ++sample) {
+            pc.sample = sample;
+            const uint32_t ring = s->fc_next++ % kFcRing;
+            FrameCounters* fc = s->d_fc + ((size_t)ring * ptc_step::kMaxParts + p);
+            CK(cudaMemsetAsync(fc, 0, sizeof(FrameCounters), st0));
+            prof_mark(s, 0);
+            launch_raygen(st0, s->uniforms, P.qp, fc, P.n, nparts, p, sample ? s->planes.spp_rng : nullptr);
+            prof_mark(s, 1);
+            // primary rays arrive in 8x4-pixel tiles, one per warp: packet traversal (pt_kernels.cu); PTC_PRIMARY_PACKETS=0 uses k_trace
+            launch_trace(st0, s->trace_grid, use_packets ? 3 : s->trace_impl, s->scene, P.qp, P.d_hits_p, fc, 0, s->d_total_rays, s->d_total_rays + 1);
+            if (prefetch) { CK(cudaEventRecord(P.primary_done, st0)); CK(cudaStreamWaitEvent(st, P.primary_done, 0)); }
+            if (wait_main && sample == 0) CK(cudaStreamWaitEvent(st, s->ev_main, 0));
             s->launches += 2;
-            // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
-            if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(st, s->trace_grid, s->scene, P.shq, P.q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
+            for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
+                if (seg) { prof_mark(s, 1); launch_trace(st, s->trace_grid, s->trace_impl, s->scene, P.q[seg & 1], P.d_hits, fc, seg, s->d_total_rays); s->launches++; }
+                prof_mark(s, 2);
+                launch_shade(st, s->shade_grid, s->scene, pc, seg ? P.q[seg & 1] : P.qp, P.q[(seg + 1) & 1], seg ? P.d_hits : P.d_hits_p, fc, seg, s->planes, P.shq);
+                if (seg == 0 && prefetch) CK(cudaEventRecord(P.primary_free, st));
+                s->launches++;
+                // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
+                if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(st, s->trace_grid, s->scene, P.shq, P.q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
+            }
         }
         if (!s->profiling) { CK(cudaEventRecord(P.done, st)); CK(cudaStreamWaitEvent(s->stream, P.done, 0)); }
     }
@@ -572,17 +621,32 @@ PTC_API int ptc_poll(ptc_step* s, int wait) {
 
 PTC_API int ptc_resize(ptc_step* s, uint32_t w, uint32_t h) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    // validate BEFORE anything is freed: a bad size leaves the step exactly as it was
+    if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull) { set_error("bad frame size"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
+    for (auto& P : s->parts) { if (P.prefetch_stream) CK(cudaStreamSynchronize(P.prefetch_stream)); if (P.stream) CK(cudaStreamSynchronize(P.stream)); }
     CK(cudaStreamSynchronize(s->stream)); CK(cudaStreamSynchronize(s->copy_stream));
-    free_frame_buffers(s);
+    const uint32_t old_w = s->cfg.width, old_h = s->cfg.height;
+    free_frame_buffers(s);                       // drops buffers injected with ptc_set_output / ptc_set_reduce_output too (their size is the old one)
     int rc = alloc_frame_buffers(s, w, h);
-    if (rc != PTC_OK) return rc;
+    if (rc != PTC_OK) {
+        // out of memory midway: go back to the old size (which fitted a moment ago); if even that fails the step is marked
+        // invalid and every entry point that touches the planes reports it instead of dereferencing null buffers
+        const std::string why = g_last_error;
+        free_frame_buffers(s);
+        if (alloc_frame_buffers(s, old_w, old_h) != PTC_OK) { free_frame_buffers(s); s->invalid = true; s->npix = 0; }
+        cudaStreamSynchronize(s->stream);
+        set_error("ptc_resize: " + why + (s->invalid ? " (and the previous size could not be restored: step invalid)" : " (previous size restored, accumulation cleared)"));
+        return rc;
+    }
+    s->invalid = false;
     CK(cudaStreamSynchronize(s->stream));
     return PTC_OK;
 }
 
 PTC_API int ptc_set_output(ptc_step* s, void* device_rgba32f) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     s->planes.color = device_rgba32f ? (F4*)device_rgba32f : s->owned_color;
@@ -591,6 +655,7 @@ PTC_API int ptc_set_output(ptc_step* s, void* device_rgba32f) {
 
 PTC_API int ptc_reset_accumulation(ptc_step* s) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     CK(cudaMemsetAsync(s->planes.color, 0, (size_t)s->npix * 16, s->stream));
     s->main_dirty = true;
@@ -599,8 +664,25 @@ PTC_API int ptc_reset_accumulation(ptc_step* s) {
 
 PTC_API int ptc_blit(ptc_step* s, const void* src_device_rgba32f) {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     if (!s->d_display) CK(cudaMalloc(&s->d_display, (size_t)s->npix * 4));
+    if (!src_device_rgba32f && !s->main_dirty && !s->profiling && s->frames > 0 && s->blit_by_parts) {
+        // Presenting the accumulated image right after a frame: every frame part tonemaps ITS pixels on its own stream, behind
+        // its own last shade — the parts never wait for each other and the next frame is not held back (the reference runs
+        // BlitStep on its second queue while the RT queue renders on, wgpu_util.rs:111-114).  The DISPLAY plane may still be
+        // feeding the previous ptc_read_async snapshot: that copy (ordering stream) is awaited first.
+        if (s->display_busy) for (uint32_t p = 0; p < s->num_parts; ++p) CK(cudaStreamWaitEvent(s->parts[p].stream, s->ev_display_free, 0));
+        s->display_busy = false;
+        for (uint32_t p = 0; p < s->num_parts; ++p) {
+            ptc_step::FramePart& P = s->parts[p];
+            launch_blit_part(P.stream, s->planes.color, s->d_display, P.n, s->num_parts, p, s->cfg.width, s->cfg.height);
+            CK(cudaEventRecord(P.done, P.stream)); CK(cudaStreamWaitEvent(s->stream, P.done, 0));
+            s->launches += P.n ? 1 : 0;
+        }
+        CK(cudaGetLastError());
+        return PTC_OK;
+    }
     s->main_dirty = true;
     launch_blit(s->stream, src_device_rgba32f ? (const F4*)src_device_rgba32f : s->planes.color, s->d_display, s->npix);
     s->launches += 1;
@@ -608,8 +690,24 @@ PTC_API int ptc_blit(ptc_step* s, const void* src_device_rgba32f) {
     return PTC_OK;
 }
 
+// The analogue of denoise.rs's copy_texture_to_buffer (src/render_steps/denoise.rs:84-100): a device-to-device copy of one
+// plane into a caller-owned buffer with the caller's row pitch (wgpu needs 256-byte-aligned rows there, pt.rs:470-472), after
+// the frames already enqueued.
+PTC_API int ptc_copy_plane(ptc_step* s, int plane, void* dst_device, size_t dst_pitch_bytes) {
+    if (!s || !dst_device) { set_error("null argument"); return PTC_ERR_INVALID; }
+    void* src; size_t pb;
+    if (plane == PTC_PLANE_HIT_ID || !plane_ptr(s, plane, &src, &pb)) { set_error("plane not copyable (or not produced yet)"); return PTC_ERR_INVALID; }
+    const size_t row = (size_t)s->cfg.width * pb;
+    if (dst_pitch_bytes && dst_pitch_bytes < row) { set_error("ptc_copy_plane: pitch smaller than a row"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    if (plane != PTC_PLANE_DISPLAY && plane != PTC_PLANE_REPROJECTED && plane != PTC_PLANE_REDUCED) s->main_dirty = true;   // the next frame writes these planes
+    CK(cudaMemcpy2DAsync(dst_device, dst_pitch_bytes ? dst_pitch_bytes : row, src, row, row, s->cfg.height, cudaMemcpyDeviceToDevice, s->stream));
+    return PTC_OK;
+}
+
 PTC_API int ptc_rayproject(ptc_step* s, const ptc_uniforms* prev, const ptc_uniforms* cur, const void* src_device_rgba32f) {
     if (!s || !prev || !cur) { set_error("null argument"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     if (prev->camera.width != s->cfg.width || prev->camera.height != s->cfg.height || cur->camera.width != s->cfg.width || cur->camera.height != s->cfg.height) {
         set_error("rayproject: camera size differs from step size"); return PTC_ERR_INVALID;
     }
@@ -627,22 +725,10 @@ PTC_API int ptc_rayproject(ptc_step* s, const ptc_uniforms* prev, const ptc_unif
 
 PTC_API void ptc_destroy(ptc_step* s) { destroy_step(s); }
 
-static bool plane_ptr(ptc_step* s, int plane, void** p, size_t* px_bytes) {
-    switch (plane) {
-        case PTC_PLANE_COLOR: *p = s->planes.color; *px_bytes = 16; return true;
-        case PTC_PLANE_DEPTH: *p = s->planes.depth; *px_bytes = 4; return true;
-        case PTC_PLANE_NORMAL: *p = s->planes.normal; *px_bytes = 16; return true;
-        case PTC_PLANE_ALBEDO: *p = s->planes.albedo; *px_bytes = 16; return true;
-        case PTC_PLANE_HIT_ID: *p = s->planes.hit_tri; *px_bytes = 4; return true;
-        case PTC_PLANE_DISPLAY: *p = s->d_display; *px_bytes = 4; return s->d_display != nullptr;
-        case PTC_PLANE_REPROJECTED: *p = s->d_reprojected; *px_bytes = 16; return s->d_reprojected != nullptr;
-    }
-    return false;
-}
-
 PTC_API int ptc_write(ptc_step* s, int plane, const void* src, size_t pitch) {
     if (!s || !src) { set_error("null argument"); return PTC_ERR_INVALID; }
     if (plane != PTC_PLANE_COLOR) { set_error("ptc_write: only the accumulation plane (PTC_PLANE_COLOR) can be loaded"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     const size_t row = (size_t)s->cfg.width * 16;
     s->main_dirty = true;
@@ -692,10 +778,12 @@ PTC_API int ptc_read_async(ptc_step* s, int plane, void* dst_pinned) {
         CK(cudaMalloc(&s->d_snapshot, bytes)); s->snapshot_bytes = bytes;
     }
     // the previous host copy must have drained the snapshot before it is overwritten
-    s->main_dirty = true;
+    const bool frame_plane = plane != PTC_PLANE_DISPLAY && plane != PTC_PLANE_REPROJECTED && plane != PTC_PLANE_REDUCED;
+    if (frame_plane) s->main_dirty = true;         // the next frame writes this plane: it must wait for the snapshot copy
     CK(cudaStreamWaitEvent(s->stream, s->copy_done, 0));
     CK(cudaMemcpyAsync(s->d_snapshot, src, bytes, cudaMemcpyDeviceToDevice, s->stream));
     CK(cudaEventRecord(s->snap_ready, s->stream));
+    if (plane == PTC_PLANE_DISPLAY) { CK(cudaEventRecord(s->ev_display_free, s->stream)); s->display_busy = true; }   // the next per-part blit waits for this
     CK(cudaStreamWaitEvent(s->copy_stream, s->snap_ready, 0));
     CK(cudaMemcpyAsync(dst_pinned, s->d_snapshot, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
     CK(cudaEventRecord(s->copy_done, s->copy_stream));
@@ -874,25 +962,45 @@ static nccl_allreduce_fn g_nccl_allreduce = nullptr;
 static nccl_errstr_fn g_nccl_errstr = nullptr;
 static bool bind_nccl() {
     if (g_nccl_reduce) return true;
+    // Only an NCCL that is ALREADY part of this process can own the caller's ncclComm_t: look the shared object up without
+    // loading it (RTLD_NOLOAD), then the global symbol scope (an NCCL linked statically into the host program or into
+    // torch).  Loading another copy — e.g. the system libnccl next to torch's bundled one — would hand the communicator
+    // to a different NCCL instance, so there is no such fallback.
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) return false;
-    g_nccl_reduce = (nccl_reduce_fn)dlsym(h, "ncclReduce");
+    if (!h) h = RTLD_DEFAULT;
+    nccl_reduce_fn red = (nccl_reduce_fn)dlsym(h, "ncclReduce");
+    if (!red) return false;
     g_nccl_allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
     g_nccl_errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
-    return g_nccl_reduce != nullptr;
+    g_nccl_reduce = red;
+    return true;
+}
+PTC_API int ptc_set_reduce_output(ptc_step* s, void* device_rgba32f) {
+    if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    if (device_rgba32f) s->reduced = (F4*)device_rgba32f;
+    else s->reduced = s->owned_reduced;          // may be null: allocated by the next ptc_reduce
+    return PTC_OK;
 }
 PTC_API int ptc_reduce(ptc_step* s, void* nccl_comm, int root) {
     if (!s || !nccl_comm) { set_error("null argument"); return PTC_ERR_INVALID; }
-    if (!bind_nccl()) { set_error("ptc_reduce: no NCCL (libnccl.so.2) loaded or loadable in this process"); return PTC_ERR_INVALID; }
+    if (s->invalid) { set_error("step has no frame buffers (a ptc_resize failed)"); return PTC_ERR_INVALID; }
+    // running means do not add: rank images are only summable as (sum of radiance, sample count)
+    if (s->cfg.accum_mode != PTC_ACCUM_SUM) { set_error("ptc_reduce needs ptc_config.accum_mode == PTC_ACCUM_SUM (per-rank running means cannot be summed)"); return PTC_ERR_INVALID; }
+    if (!bind_nccl()) { set_error("ptc_reduce: no NCCL in this process (neither a loaded libnccl.so.2 nor a global ncclReduce symbol); the caller's communicator must come from the NCCL the call goes to"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
+    if (!s->reduced) {
+        if (!s->owned_reduced) CK(cudaMalloc(&s->owned_reduced, (size_t)s->npix * 16));
+        s->reduced = s->owned_reduced;
+    }
     const int kNcclFloat32 = 7, kNcclSum = 0;                     // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
-    s->main_dirty = true;
+    s->main_dirty = true;                                         // the next frame must not write COLOR while NCCL reads it
     int r;
     if (root < 0) {                                               // every rank wants the image (each one displays): all-reduce
         if (!g_nccl_allreduce) { set_error("ptc_reduce: ncclAllReduce not found"); return PTC_ERR_INVALID; }
-        r = g_nccl_allreduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, nccl_comm, s->stream);
-    } else r = g_nccl_reduce(s->planes.color, s->planes.color, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
+        r = g_nccl_allreduce(s->planes.color, s->reduced, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, nccl_comm, s->stream);
+    } else r = g_nccl_reduce(s->planes.color, s->reduced, (size_t)s->npix * 4, kNcclFloat32, kNcclSum, root, nccl_comm, s->stream);
     if (r != 0) { set_error(std::string("ncclReduce: ") + (g_nccl_errstr ? g_nccl_errstr(r) : "error")); return PTC_ERR_CUDA; }
     return PTC_OK;
 }
@@ -941,7 +1049,9 @@ PTC_API int ptc_debug_unorm8(int cuda_device, float* out512) {
     if (ptc_device_count() <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
     CK(cudaSetDevice(cuda_device));
     int rc = unorm8_probe(out512);
-    return rc != PTC_OK ? rc : (unorm8_hw_exact() ? 1 : 0);
+    if (rc != PTC_OK) return rc;
+    const int hw = unorm8_hw_exact(cuda_device);
+    return hw < 0 ? hw : (hw ? 1 : 0);
 }
 
 PTC_API const char* ptc_last_error(void) { return g_last_error.c_str(); }

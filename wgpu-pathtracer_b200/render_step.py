@@ -66,9 +66,13 @@ class RTStep:
         check(lib().ptc_write(self._h, int(plane), image.ctypes.data_as(C.c_void_p), 0))
 
     def reduce(self, nccl_comm, root=0):
-        """Sum the per-rank SUM-mode accumulation buffers into `root` with one ncclReduce on the step's stream (ptc_reduce).
-        nccl_comm: the ncclComm_t as an integer (e.g. torch's ProcessGroupNCCL._comm_ptr())."""
+        """Sum the per-rank SUM-mode accumulation planes into the REDUCED plane of `root` with one ncclReduce on the step's
+        stream (ptc_reduce); the accumulation itself is untouched, so the call can be repeated after more frames.
+        nccl_comm: the ncclComm_t as an integer (e.g. torch's ProcessGroupNCCL._comm_ptr()); root < 0 = all-reduce."""
         check(lib().ptc_reduce(self._h, C.c_void_p(int(nccl_comm)), int(root)))
+
+    def set_reduce_output(self, device_ptr):
+        check(lib().ptc_set_reduce_output(self._h, C.c_void_p(device_ptr) if device_ptr else None))
 
     def reset_accumulation(self):
         check(lib().ptc_reset_accumulation(self._h))
@@ -78,7 +82,7 @@ class RTStep:
         shape, dt = {T.PLANE_COLOR: ((h, w, 4), np.float32), T.PLANE_DEPTH: ((h, w), np.float32),
                      T.PLANE_NORMAL: ((h, w, 4), np.float32), T.PLANE_ALBEDO: ((h, w, 4), np.float32),
                      T.PLANE_HIT_ID: ((h, w, 2), np.uint32), T.PLANE_DISPLAY: ((h, w, 4), np.uint8),
-                     T.PLANE_REPROJECTED: ((h, w, 4), np.float32)}[plane]
+                     T.PLANE_REPROJECTED: ((h, w, 4), np.float32), T.PLANE_REDUCED: ((h, w, 4), np.float32)}[plane]
         out = np.empty(shape, dtype=dt)
         check(lib().ptc_read(self._h, plane, out.ctypes.data_as(C.c_void_p), 0))
         return out
@@ -93,6 +97,10 @@ class RTStep:
 
     def read_async(self, plane, pinned_ptr):
         check(lib().ptc_read_async(self._h, plane, C.c_void_p(pinned_ptr)))
+
+    def copy_plane(self, plane, dst_device_ptr, pitch=0):
+        """device-to-device copy of a plane into a caller buffer with `pitch` bytes per row (ptc_copy_plane)"""
+        check(lib().ptc_copy_plane(self._h, int(plane), C.c_void_p(dst_device_ptr), int(pitch)))
 
     def read_wait(self):
         check(lib().ptc_read_wait(self._h))
