@@ -37,6 +37,7 @@ def lib():
     L.orc_render_frame.restype = i32
     L.orc_render_frame.argtypes = [vp, P(T.Uniforms), vp, vp, vp, vp, vp, i32, i32, u32, u32, P(u64)]
     L.orc_trace_rays.restype, L.orc_trace_rays.argtypes = i32, [vp, vp, u64, i32, vp, vp, P(u64)]
+    L.orc_pixel.restype, L.orc_pixel.argtypes = i32, [vp, P(T.Uniforms), u32, u32, i32, P(C.c_float), P(u32), P(u64)]
     L.orc_trace_rays_any.restype, L.orc_trace_rays_any.argtypes = i32, [vp, vp, u64, vp]
     L.orc_jenkins_hash.restype, L.orc_jenkins_hash.argtypes = u32, [u32]
     L.orc_rand_stream.restype, L.orc_rand_stream.argtypes = None, [u32, u32, u32, u32, u32, P(u32), vp, vp]
@@ -85,6 +86,12 @@ class OracleScene:
         assert rc == 0
         return {"color": color, "depth": depth, "normal": normal, "albedo": albedo, "hit_id": hit,
                 "rays": cnt[0], "nodes": cnt[1], "tris": cnt[2]}
+
+    def pixel(self, uniforms, x, y, brute=False):
+        """pixel_color of one pixel: (rgba, RNG state after its path(s), rays traced)"""
+        col, st, rays = (C.c_float * 4)(), C.c_uint32(), C.c_uint64()
+        assert lib().orc_pixel(self._h, C.byref(uniforms), int(x), int(y), 1 if brute else 0, col, C.byref(st), C.byref(rays)) == 0
+        return np.array(list(col), dtype=np.float32), st.value, rays.value
 
     def trace_rays(self, rays, brute=False):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

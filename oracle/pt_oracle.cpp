@@ -713,6 +713,22 @@ int orc_render_frame(const orc_scene* o, const ptc_uniforms* un_in, float* color
 
 // closest hit for caller-supplied rays (n x 8 floats: ox,oy,oz,_,dx,dy,dz,_).
 // hits: n x 4 words (t,b1,b2 f32 bits, global triangle id); ids: n x 2 (instance, geometry)
+// one pixel of one frame, with the RNG state its path(s) ended in and the rays it traced: lets a test compare the number of
+// random draws per path with an independent restatement (tests/test_oracle_independent.py)
+__attribute__((visibility("default")))
+int orc_pixel(const orc_scene* o, const ptc_uniforms* un_in, uint32_t x, uint32_t y, int brute, float color[4], uint32_t* rng_state, uint64_t* rays) {
+    if (!o || !un_in || !color) return -1;
+    ptc_uniforms un = *un_in;
+    un.num_lights = (uint32_t)o->sc.lights.size();
+    Rng rng; rand_init(rng, x, y, 1u, o->sc.cfg.width, un.camera.frame);
+    TraceCounters c;
+    PixelOut po = pixel_color(o->sc, rng, un, x, y, brute != 0, c);
+    color[0] = po.color.x; color[1] = po.color.y; color[2] = po.color.z; color[3] = po.color.w;
+    if (rng_state) *rng_state = rng.state;
+    if (rays) *rays = c.rays;
+    return 0;
+}
+
 __attribute__((visibility("default")))
 int orc_trace_rays(const orc_scene* o, const float* rays, uint64_t n, int brute, uint32_t* hits, uint32_t* ids, uint64_t counters[3]) {
     const Scene& sc = o->sc;

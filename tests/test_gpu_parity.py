@@ -265,7 +265,7 @@ def test_errors_do_not_abort(ptc, standins):
     with pytest.raises(ptc.PtcError):
         ptc.RTStep.create(scene, ptc.make_config(0, 0))
     with pytest.raises(ptc.PtcError):
-        ptc.RTStep.create(scene, ptc.make_config(16, 16, samples_per_pixel=2))
+        ptc.RTStep.create(scene, ptc.make_config(16, 16, samples_per_pixel=0))
     with pytest.raises(ptc.PtcError):
         ptc.RTStep.create(scene, ptc.make_config(16, 16), device=99)
     step = ptc.RTStep.create(scene, ptc.make_config(16, 16))

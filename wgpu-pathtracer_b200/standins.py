@@ -18,6 +18,8 @@ counts, material parameters and texture counts of the named scenes:
 The environment map (texture 9; the reference uses ``res/knob/envmap.exr``, 4096x2048 rgba32f, values
 0.045..1.0) is a procedural sky of the same size and range.
 """
+import os
+
 import numpy as np
 
 from . import _types as T
@@ -330,10 +332,20 @@ def _sponza_mtl(n_mats=20, n_albedo=19, n_bump=18):
     return "\n".join(out) + "\n"
 
 
-def sponza(env=None, tex_size=512):
-    """C3: ~66 k-triangle atrium, 20 Sponza-parameter materials, 19 albedo + 18 bump textures."""
+# The reference's REAL Sponza material library and textures (byte copies of /root/reference/res/sponza, made by
+# tests/golden/fetch_ref_res.py).  The .obj beside them is a Git-LFS pointer, so the geometry below stays procedural.
+REF_RES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_res")
+
+
+def sponza(env=None, tex_size=512, real_materials=None):
+    """C3: ~78 k-triangle atrium with the reference's real sponza.mtl (20 materials, `Tf 1 1 1` on every one: SURVEY F10)
+    and its real 19 albedo + 18 bump JPGs on the objects round-robin; real_materials=False (or a checkout without
+    tests/golden/ref_res) uses a synthetic MTL of the same shape with procedural textures instead."""
     sc = Scene(env or make_envmap())
     base = [(0.745, 0.710, 0.675), (0.714, 0.706, 0.659), (0.784, 0.784, 0.784), (0.737, 0.710, 0.671), (0.647, 0.647, 0.604), (0.588, 0.557, 0.502)]
+    real_dir = os.path.join(REF_RES, "sponza")
+    if real_materials is None:
+        real_materials = os.path.exists(os.path.join(real_dir, "sponza.mtl"))
 
     def decode(path):
         name = path.rsplit("/", 1)[-1]
@@ -342,8 +354,14 @@ def sponza(env=None, tex_size=512):
             return make_albedo_texture(tex_size, tex_size, 100 + k, base[k % len(base)])
         return make_bump_texture(tex_size, tex_size, 500 + k)
 
-    mats = _materials_from_mtl(sc, _sponza_mtl(), decode=decode)
-    ids = [mats[f"sp_{i:02d}"] for i in range(20)]
+    if real_materials:
+        from .scene import decode_image
+        mtl_text = open(os.path.join(real_dir, "sponza.mtl"), encoding="utf-8", errors="replace").read()
+        mats = _materials_from_mtl(sc, mtl_text, decode=lambda p: decode_image(os.path.join(real_dir, os.path.basename(p))))
+        ids = list(mats.values())                     # the 20 materials in file order
+    else:
+        mats = _materials_from_mtl(sc, _sponza_mtl(), decode=decode)
+        ids = [mats[f"sp_{i:02d}"] for i in range(20)]
     L, Wd, Hh = 30.0, 12.0, 14.0          # atrium extents: x in [-15,15], z in [-6,6], y in [0,14]
     objs = []
     objs.append(grid((-L / 2, 0, -Wd / 2), (0, 0, Wd), (L, 0, 0), 96, 40, uv_scale=(4, 4)))                      # floor 7680
@@ -520,12 +538,39 @@ def _classroom_mtl(n_mats=79):
     return "\n".join(out) + "\n"
 
 
-def classroom(env=None, detail=1.32):
+def _ref_mtl(rel):
+    p = os.path.join(REF_RES, rel)
+    return open(p, encoding="utf-8", errors="replace").read() if os.path.exists(p) else None
+
+
+def _emitter_names(mtl_text):
+    """names of the materials whose `Ke` is not all zero (scene.rs:307-309: those are the lights)"""
+    out, cur = [], None
+    for ln in mtl_text.splitlines():
+        w = ln.split()
+        if w[:1] == ["newmtl"]:
+            cur = ln.split(None, 1)[1].strip()
+        elif w[:1] == ["Ke"] and any(float(x) != 0.0 for x in w[1:4]):
+            out.append(cur)
+    return out
+
+
+def classroom(env=None, detail=1.32, real_materials=None):
     """C4: a classroom of ~0.6 M triangles (detail=1): shell, 30 desks + chairs, shelves of books, blinds, a globe, ceiling
-    light panels (the emitters), 79 constant-colour materials, no transmission."""
+    light panels (the emitters), the 79 constant-colour materials of the reference's real res/classroom/classroom.mtl
+    (no Tf at all: no transmission, SURVEY F10; three emitters, Ke 5 / 7 / 15, which the light panels get);
+    real_materials=False (or no tests/golden/ref_res) uses a synthetic MTL of the same shape."""
     sc = Scene(env or make_envmap())
-    mats = _materials_from_mtl(sc, _classroom_mtl())
-    mid = [mats[f"cl_{i:02d}"] for i in range(79)]
+    real = _ref_mtl("classroom/classroom.mtl") if real_materials in (None, True) else None
+    if real is not None:
+        mats = _materials_from_mtl(sc, real)
+        emit = _emitter_names(real)
+        assert len(mats) == 79 and len(emit) == 3
+        rest = [i for n, i in mats.items() if n not in emit]
+        mid = rest[:10] + [mats[n] for n in emit] + rest[10:]       # slots 10..12 are what the light panels below use
+    else:
+        mats = _materials_from_mtl(sc, _classroom_mtl())
+        mid = [mats[f"cl_{i:02d}"] for i in range(79)]
     k = lambda n: max(1, int(round(n * np.sqrt(detail))))
     X, Y, Z = 12.0, 3.2, 9.0
     parts = []
@@ -599,11 +644,15 @@ def _san_miguel_mtl(n_mats=287, n_kd=200, n_bump=100, n_pr=23):
     return "\n".join(out) + "\n"
 
 
-def san_miguel(env=None, n_plants=2000, leaves_per_plant=2500, tex_size=256):
+def san_miguel(env=None, n_plants=2000, leaves_per_plant=2500, tex_size=256, real_materials=None):
     """C5: courtyard shell + n_plants procedural plants of leaves_per_plant leaf quads (2 triangles each; 10 M triangles
-    at the defaults), 287 materials, 323 textures, materials assigned by hash => divergent shading."""
+    at the defaults), the 287 materials of the reference's real res/san_miguel/san-miguel.mtl (264 map_Kd + 57 map_Bump +
+    3 map_Ks files, Pr / Pm / Ps scalars on every material, 5 with Tf) assigned by hash => divergent shading.  The 323 PNGs
+    themselves (134 MB) are not vendored: each file name gets a procedural texture (N_* = bump map).
+    real_materials=False (or no tests/golden/ref_res) uses a synthetic MTL of the same shape."""
     sc = Scene(env or make_envmap())
     rng = np.random.RandomState(0x5A17)
+    real = _ref_mtl("san_miguel/san-miguel.mtl") if real_materials in (None, True) else None
 
     def decode(path):
         name = path.rsplit("/", 1)[-1]
@@ -616,8 +665,22 @@ def san_miguel(env=None, n_plants=2000, leaves_per_plant=2500, tex_size=256):
         t = make_bump_texture(tex_size // 2, tex_size // 2, 3000 + kseed)
         return t
 
-    mats = _materials_from_mtl(sc, _san_miguel_mtl(), decode=decode)
-    mid = np.array([mats[f"sm_{i:03d}"] for i in range(287)], dtype=np.uint32)
+    def decode_real(path):
+        import zlib
+        name = path.rsplit("/", 1)[-1]
+        kseed = zlib.crc32(name.encode()) % 100000
+        if name.startswith("N_") or "bump" in name.lower():
+            return make_bump_texture(tex_size, tex_size, 2000 + kseed)
+        r = np.random.RandomState(kseed)
+        return make_albedo_texture(tex_size, tex_size, 1000 + kseed, tuple(0.3 + 0.7 * r.rand(3)))
+
+    if real is not None:
+        mats = _materials_from_mtl(sc, real, decode=decode_real)
+        assert len(mats) == 287
+        mid = np.array(list(mats.values()), dtype=np.uint32)
+    else:
+        mats = _materials_from_mtl(sc, _san_miguel_mtl(), decode=decode)
+        mid = np.array([mats[f"sm_{i:03d}"] for i in range(287)], dtype=np.uint32)
     Lx, Lz, Hy = 40.0, 30.0, 12.0
     parts = []
     sub = 400 if n_plants >= 500 else 120
