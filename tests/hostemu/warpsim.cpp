@@ -8,6 +8,8 @@
 #include "../../wgpu-pathtracer_b200/csrc/pt_device.cuh"
 #include "../../wgpu-pathtracer_b200/csrc/scene_prep.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -118,7 +120,54 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                 if (!any) { finished[w] = 1; --live; }
                 continue;
             }
-            if (P->policy == 0 || P->policy == 2) {
+            if (P->policy == 3) {
+                // policy 3: greedy — run the phase that serves the most lanes per instruction (node 40, triangle 62, refill 150
+                // instructions per iteration); a phase repeats while it keeps at least 3/4 of the lanes it started with
+                const uint32_t nnode = (uint32_t)__builtin_popcount(at_node), nleaf = (uint32_t)__builtin_popcount(at_leaf);
+                const double sn = nnode / 40.0, st = nleaf / 62.0, sr = exhausted[w] ? 0.0 : nidle / (double)(P->node_steps ? P->node_steps : 150);
+                if (sr > sn && sr > st) {
+                    out->it_refill++;
+                    for (int l = 0; l < 32; ++l) if ((idle >> l & 1) && L[l].ray != 0xFFFFFFFFu) { res[L[l].ray] = L[l].best; L[l].ray = 0xFFFFFFFFu; }
+                    uint64_t base = cursor; cursor += nidle;
+                    if (base + nidle >= n) exhausted[w] = 1;
+                    uint32_t k = 0;
+                    for (int l = 0; l < 32; ++l) if (idle >> l & 1) {
+                        uint64_t i = base + k++;
+                        if (i >= n) continue;
+                        Lane& X = L[l];
+                        X.ray = (uint32_t)i;
+                        X.o = pt_mk3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]); X.d = pt_mk3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]);
+                        X.r = make_ray_slab(s, X.o, X.d);
+                        X.best.t = PT_RAY_TMAX; X.best.b1 = X.best.b2 = 0.0f; X.best.tri = 0xFFFFFFFFu;
+                        X.stack[0] = PTC_SENTINEL; X.sp = 1; X.tri_i = X.tri_end = 0; X.pend = 0;
+                        if (s.num_nodes != 0 && ray_is_finite(X.o, X.d)) X.node = 0;
+                        out->ln_refill++; out->rays++;
+                    }
+                } else if (st >= sn) {
+                    const uint32_t start = nleaf;
+                    for (;;) {
+                        out->it_tri++;
+                        uint32_t still = 0;
+                        for (int l = 0; l < 32; ++l) if (L[l].node < 0) {
+                            Lane& X = L[l];
+                            tri_step(s, X, X.node, X.tri_i, X.tri_end); out->tri_tests++; out->ln_tri++;
+                            if (X.tri_i == X.tri_end) X.node = X.stack[--X.sp];
+                            if (X.node < 0) still++;
+                        }
+                        out->it_inner_vote++;
+                        if (still * 4 < start * 3 || still == 0) break;
+                    }
+                } else {
+                    const uint32_t start = nnode;
+                    for (;;) {
+                        uint32_t act = 0, still = 0;
+                        for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) { node_step(s, L[l]); out->node_visits++; act++; }
+                        for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) still++;
+                        out->it_node++; out->ln_node += act; out->it_inner_vote++;
+                        if (still * 4 < start * 3 || still == 0) break;
+                    }
+                }
+            } else if (P->policy == 0 || P->policy == 2) {
                 const uint32_t nleaf = (uint32_t)__builtin_popcount(at_leaf);
                 if (nleaf >= P->tri_vote || (at_leaf | idle) == 0xFFFFFFFFu) {
                     for (;;) {
@@ -141,6 +190,9 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                         for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) { node_step(s, L[l]); out->node_visits++; act++; }
                         if (!act) break;
                         out->it_node++; out->ln_node += act;
+                        if (getenv("WS_DIAG")) { static uint64_t a_leaf = 0, a_idle = 0, its = 0; uint32_t nl = 0, ni = 0;
+                            for (int l = 0; l < 32; ++l) { if (L[l].node == PTC_SENTINEL) ni++; else if (L[l].node < 0) nl++; }
+                            a_leaf += nl; a_idle += ni; its++; if (its % 200000 == 0) fprintf(stderr, "node its %llu: after-step at_leaf %.2f idle %.2f\n", (unsigned long long)its, (double)a_leaf / its, (double)a_idle / its); }
                         if (P->node_inner) {
                             uint32_t still = 0;
                             for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) still++;

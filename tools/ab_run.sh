@@ -3,7 +3,7 @@ for spec in "$@"; do
   v="${spec%%:*}"; envs=""; [ "$spec" != "$v" ] && envs="${spec#*:}"
   if [ "$v" != "cur" ]; then export PTC_LIB=$PWD/build/$v/pkg/csrc/libptcore.so; else unset PTC_LIB; fi
   echo "== variant '$spec'"
-  env $(echo "$envs" | tr ',' ' ') timeout 300 python bench.py --steps ${STEPS:-32} --warmup 4 --no-cpu-baseline ${BENCH_ARGS} 2>&1 | python -c "
+  env $(echo "$envs" | tr ',' ' ') timeout 300 python bench.py --steps ${STEPS:-32} --warmup 4 --no-cpu-baseline --no-others --reps 3 ${BENCH_ARGS} 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

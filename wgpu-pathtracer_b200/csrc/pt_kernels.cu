@@ -116,6 +116,9 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_simple(DevScene s, cons
 #ifndef PTC_REFILL_VOTE
 #define PTC_REFILL_VOTE 16
 #endif
+#ifndef PTC_NODE_UNROLL
+#define PTC_NODE_UNROLL 2                // node steps per repeat vote of the node phase (measured: 1 -> 2 +3.5 %, 3 and 4 -0.5 %)
+#endif
 #ifndef PTC_TRACE_MIN_BLOCKS
 #define PTC_TRACE_MIN_BLOCKS 20          // x 64 threads: 48 registers (8 bytes spilled), 40 resident warps per SM; 36 warps at 56 registers measured 0.6-2 % slower
 #endif
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
             // ---- node phase: both children of one node per lane ----
 #pragma unroll 1
             for (;;) {
+#ifdef PTC_NODE_LEGACY
                 if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
 #ifdef PTC_SMEM_TOP
                     NodeQ nq;
@@ -240,6 +244,120 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
                     if (h0 && h1) { stack[sp++] = swap ? c0 : c1; node = swap ? c1 : c0; }   // (an L1 prefetch of the pushed child measured -0.5 %)
                     else if (h0 || h1) node = h0 ? c0 : c1;
                     else node = stack[--sp];
+                }
+#else
+                // The step is written without control flow inside it: in a divergent warp the three outcomes of a node test (both
+                // children hit / one / none) ran as three serialised branches — every lane paid the issue slots of all of them plus
+                // the branch and reconvergence instructions (64 instructions per step in SASS, 35 of them box arithmetic).  Here the
+                // next node is chosen by selects, the far child is pushed by a predicated store and a miss pops by a predicated load.
+#pragma unroll
+                for (int rep = 0; rep < PTC_NODE_UNROLL; ++rep) {
+                    if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
+                        const NodeQ nq = ld_node(s.nodes + node);
+                        bool h0, h1; float tn0, tn1;
+                        node_test(r, nq, best.t, h0, h1, tn0, tn1);
+                        const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+                        // the child visited next is c1 when c0 is missed, or when both are hit and c1 is nearer (irrelevant when both are missed)
+                        const bool take1 = !h0 || (h1 && tn1 < tn0);
+                        const int next = take1 ? c1 : c0, other = take1 ? c0 : c1;
+                        stack[sp] = other;                                  // unconditional: the slot above the top is scratch
+                        if (h0 && h1) sp++;
+                        if (!(h0 || h1)) { sp--; node = stack[sp]; } else node = next;
+                    }
+                }
+#endif
+                if (PTC_NODE_INNER == 0 || __popc(__ballot_sync(FULL, (uint32_t)node < (uint32_t)PTC_SENTINEL)) < PTC_NODE_INNER) break;
+            }
+        }
+    }
+}
+
+// Closest hit with POSTPONED LEAVES (PTC_TRACE_IMPL=postpone; A/B against k_trace).  In k_trace a lane that reaches a leaf waits
+// until enough lanes want triangles — on average ~9 of 32 lanes sit at a leaf during a node step (lane-accurate model,
+// tests/hostemu/warpsim.cpp).  Here the lane parks the leaf in `pend` and keeps descending; it only waits when it reaches a
+// SECOND leaf.  The parked leaf's triangles are tested when the warp next votes for a triangle phase, so the ray's `best.t` may
+// shrink later than in the plain loop and a few more nodes are visited (+4-5 % in the model) — the closest hit (ties to the
+// smaller triangle id) does not depend on the visiting order.
+template <int MINB>
+__global__ void __launch_bounds__(kTraceThreads, MINB) k_trace_pp(DevScene s, const F4* __restrict__ ray_o, const F4* __restrict__ ray_d,
+                                                             U4* __restrict__ hits, const uint32_t* __restrict__ count_ptr,
+                                                             uint32_t* cursor, unsigned long long* total_rays) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const uint32_t n = *count_ptr;
+    if (total_rays && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total_rays, (unsigned long long)n);
+    int stack[PTC_STACK_SIZE];
+    int node = PTC_SENTINEL, sp = 0, pend = 0;                     // pend: parked leaf reference (negative), 0 = none
+    uint32_t ray = kNoRay, tri_i = 0, tri_end = 0;
+    pt_v3 o = pt_mk3(0.0f, 0.0f, 0.0f), d = o;
+    RaySlab r = {};
+    HitRec best; best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
+    bool exhausted = false;
+    for (;;) {
+        const bool done = node == PTC_SENTINEL && pend == 0;
+        const uint32_t idle = __ballot_sync(FULL, done);
+        if (idle == FULL || (!exhausted && __popc(idle) >= PTC_REFILL_VOTE)) {
+            if (done && ray != kNoRay) {
+                reinterpret_cast<uint4*>(hits)[ray] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+                ray = kNoRay;
+            }
+            if (!exhausted) {
+                const uint32_t k = __popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, k);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + k >= n) exhausted = true;
+                const uint32_t i = base + __popc(idle & lt);
+                if (done && i < n) {
+                    ray = i;
+                    const F4 ro = ld4(ray_o + i), rd = ld4(ray_d + i);
+                    o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z);
+                    r = make_ray_slab(s, o, d);
+                    best.t = PT_RAY_TMAX; best.b1 = 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
+                    stack[0] = PTC_SENTINEL; sp = 1;
+                    tri_i = tri_end = 0;
+                    if (s.num_nodes != 0 && ray_is_finite(o, d)) node = 0;
+                }
+            }
+            if (__ballot_sync(FULL, ray != kNoRay) == 0) break;
+            continue;
+        }
+        const uint32_t want_tri = __popc(__ballot_sync(FULL, pend != 0));
+        const uint32_t can_node = __ballot_sync(FULL, (uint32_t)node < (uint32_t)PTC_SENTINEL);
+        const uint32_t tri_vote = max(1u, min((uint32_t)PTC_TRI_VOTE, (32u - (uint32_t)__popc(idle)) >> 2));
+        if (want_tri >= tri_vote || can_node == 0u) {
+#pragma unroll 1
+            for (;;) {
+                if (pend != 0) {
+                    if (tri_i == tri_end) { const uint32_t enc = ~(uint32_t)pend; tri_i = enc >> 3; tri_end = tri_i + (enc & 7u) + 1u; }
+                    const F4* tp = s.tris + (size_t)tri_i * 4;
+                    F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
+                    float t, b1, b2;
+                    if (pt_ray_tri(o, d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+                        const uint32_t id = f2u(a.w);
+                        if (t < best.t || (t == best.t && id < best.tri)) { best.t = t; best.b1 = b1; best.b2 = b2; best.tri = id; }
+                    }
+                    if (++tri_i == tri_end) {
+                        pend = 0;
+                        if (node < 0) { pend = node; node = stack[--sp]; }      // the waiting leaf moves up, traversal resumes
+                    }
+                }
+                if (PTC_TRI_INNER == 0 || __popc(__ballot_sync(FULL, pend != 0)) < PTC_TRI_INNER) break;
+            }
+        } else {
+#pragma unroll 1
+            for (;;) {
+                if ((uint32_t)node < (uint32_t)PTC_SENTINEL) {
+                    const NodeQ nq = ld_node(s.nodes + node);
+                    bool h0, h1; float tn0, tn1;
+                    node_test(r, nq, best.t, h0, h1, tn0, tn1);
+                    const int c0 = (int)nq.w[3], c1 = (int)nq.w[7];
+                    const bool take1 = !h0 || (h1 && tn1 < tn0);
+                    const int next = take1 ? c1 : c0, other = take1 ? c0 : c1;
+                    stack[sp] = other;
+                    if (h0 && h1) sp++;
+                    if (!(h0 || h1)) { sp--; node = stack[sp]; } else node = next;
+                    if (node < 0 && pend == 0) { pend = node; node = stack[--sp]; }   // park the leaf, keep descending
                 }
                 if (PTC_NODE_INNER == 0 || __popc(__ballot_sync(FULL, (uint32_t)node < (uint32_t)PTC_SENTINEL)) < PTC_NODE_INNER) break;
             }
@@ -433,6 +551,7 @@ void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue 
     if (impl == 0) k_trace<false, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
     else if (impl == 2) k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, nullptr, nullptr);
     else if (impl == 3) k_trace_packet<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays, packet_stats);
+    else if (impl == 4) k_trace_pp<PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
@@ -459,6 +578,7 @@ void launch_trace_n(cudaStream_t st, int grid, int impl, const DevScene& s, cons
     k_set_u32<<<1, 1, 0, st>>>(cursor + 1, n);
     if (impl == 0) k_trace<false, PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
     else if (impl == 2) k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr, nullptr, nullptr);
+    else if (impl == 4) k_trace_pp<PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, ray_o, ray_d, hits, cursor + 1, cursor, nullptr);
 }
 void launch_trace_any_n(cudaStream_t st, int grid, const DevScene& s, const F4* ray_o, const F4* ray_d, uint8_t* occluded, uint32_t n, uint32_t* cursor) {
@@ -587,7 +707,8 @@ static int persistent_grid(const void* kernel, int threads, int device) {
     return sms * per_sm;          // a multiple of the SM count (148 on B200): every SM holds its full share of resident CTAs
 }
 int trace_grid_size(int device, int impl) {
-    const void* k = impl == 0 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS> : impl == 2 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE> : (const void*)k_trace_simple;
+    const void* k = impl == 0 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS> : impl == 2 ? (const void*)k_trace<false, PTC_TRACE_MIN_BLOCKS_DENSE>
+                  : impl == 4 ? (const void*)k_trace_pp<PTC_TRACE_MIN_BLOCKS> : (const void*)k_trace_simple;
     return persistent_grid(k, kTraceThreads, device);
 }
 int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false, false>, kShadeThreads, device); }

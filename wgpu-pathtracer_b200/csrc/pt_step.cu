@@ -503,11 +503,17 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
             if (e && std::strcmp(e, "simple") == 0) s->trace_impl = 1;
             if (e && std::strcmp(e, "std") == 0) s->trace_impl = 0;
             if (e && std::strcmp(e, "dense") == 0) s->trace_impl = 2;
+            if (e && std::strcmp(e, "postpone") == 0) s->trace_impl = 4;
         }
         { const char* e = getenv("PTC_PRIMARY_PACKETS"); s->packets_mode = e ? (std::strcmp(e, "0") == 0 ? 0 : 1) : -1; s->primary_packets = s->packets_mode != 0; }
         if (cudaMallocHost(&s->h_packet_stats, 16) != cudaSuccess || cudaEventCreateWithFlags(&s->packet_ev, cudaEventDisableTiming) != cudaSuccess) { set_error("packet statistics allocation failed"); rc = PTC_ERR_OOM; break; }
         s->trace_grid = trace_grid_size(cuda_device, s->trace_impl);
         s->shade_grid = shade_grid_size(cuda_device);
+        {   // persistent-grid sizes in CTAs per SM (A/B timing): smaller grids leave room for another part's kernel on the same SM
+            int sms = 1; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device);
+            const char* e = getenv("PTC_TRACE_CTAS"); if (e && atoi(e) >= 1) s->trace_grid = std::min(s->trace_grid, sms * atoi(e));
+            e = getenv("PTC_SHADE_CTAS"); if (e && atoi(e) >= 1) s->shade_grid = std::min(s->shade_grid, sms * atoi(e));
+        }
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
     } while (0);
     if (rc != PTC_OK) { destroy_step(s); return rc; }
