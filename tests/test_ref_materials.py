@@ -154,7 +154,7 @@ def load_through_product(ptc, standins, rel, decode=None):
         seen.append(path)
         return ptc.Texture(np.full((2, 2, 4), 128, np.uint8), path=path)
 
-    sc = ptc.Scene(standins.make_envmap(8, 4)).load_obj(obj_text="\n".join(obj) + "\n", mtl_text=text, obj_dir="DIR", decode=decode or dummy)
+    sc = ptc.Scene(standins.make_envmap(8, 4)).load_obj(obj_text="\n".join(obj) + "\n", mtl_text=text, obj_dir="DIR", decode=decode or dummy, decode_threads=1)
     return sc, text, seen
 
 

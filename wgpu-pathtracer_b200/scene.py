@@ -86,7 +86,7 @@ class Scene:
         self._keep = None
 
     # -- ingest ------------------------------------------------------------------------------------
-    def load_obj(self, path=None, obj_text=None, mtl_text=None, obj_dir="", fix_normals=False, decode=decode_image):
+    def load_obj(self, path=None, obj_text=None, mtl_text=None, obj_dir="", fix_normals=False, decode=decode_image, decode_threads=0):
         """``Scene::load_obj`` (scene.rs:124-257) through the C++ loader; appends to this scene.  Only valid on
         a scene that has not been modified since construction or a previous load_obj (the loader replays the
         same texture/material numbering)."""
@@ -104,13 +104,25 @@ class Scene:
                 check(L.ptc_scene_load_obj_text(h, obj_text.encode(), None if mtl_text is None else mtl_text.encode(), obj_dir.encode()))
             n = L.ptc_scene_num_textures(h)
             texs = list(self.textures)
+            files = []
             for i in range(10, n):
                 info = T.SceneTextureInfo()
                 check(L.ptc_scene_texture_info_at(h, i, C.byref(info)))
                 if info.source == T.TEX_FILE:
-                    texs.append(decode(info.path.decode()))
+                    files.append((len(texs), info.path.decode()))
+                    texs.append(None)
                 else:
                     texs.append(Texture(np.array(list(info.color), dtype=np.float32).reshape(1, 1, 4)))
+            # decode the files on a pool of threads, as the reference does (32 loader threads per chunk, scene.rs:239-254);
+            # OpenCV releases the GIL while decoding.  Results are stored by index, so the order of completion does not matter.
+            if len(files) > 1 and decode_threads != 1:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=min(decode_threads or 32, len(files))) as pool:
+                    for (slot, _), tex in zip(files, pool.map(decode, [p for _, p in files])):
+                        texs[slot] = tex
+            else:
+                for slot, path in files:
+                    texs[slot] = decode(path)
             # give the loader texels so get_view succeeds
             for i, t in enumerate(texs):
                 w, hh = t.size
