@@ -361,6 +361,7 @@ def measure(job, name, K, Wm, reps, e2e_reps, bvh_build, sampler=None, want_cpu_
     # K steps, repeated; the reported value is the MEDIAN repetition (all are listed in e2e.runs): a single wall-clock
     # pass is exposed to host-side noise (other tenants' PCIe traffic, nvidia-smi holding driver locks).
     e2e_runs = []
+    step.blit(); step.read_async(T.PLANE_DISPLAY, pinned.data_ptr()); step.read_wait()   # untimed: first use allocates the DISPLAY plane and the snapshot
     for rep in range(e2e_reps):
         step.reset_accumulation(); step.poll(True)
         rays0 = step.stats()["rays_traced"]

@@ -1,6 +1,6 @@
 """Traversal statistics of the PRODUCT's BVH on the CPU (tests/hostemu build of the device code): nodes visited and
 triangles tested per ray for one frame of a stand-in scene, next to the oracle's BVH2 counters on the same rays.
-usage: python tools/bvh_stats.py [scene=sponza] [width=480] [height=270]"""
+usage: python tools/bvh_stats.py [scene=sponza] [width=480] [height=270] [bvh_build=0]"""
 import importlib
 import os
 import sys
@@ -20,7 +20,8 @@ def main():
     import conftest
     import binding as oracle
     scene, cam = st.BUILDERS[scene_name]()
-    cfg = pkg.make_config(W, H, max_bounces=4)
+    build = int(sys.argv[4]) if len(sys.argv) > 4 else 0        # ptc_bvh_build: 0 SAH (host), 1 LBVH, 2 PLOC
+    cfg = pkg.make_config(W, H, max_bounces=4, bvh_build=build)
     camera = st.make_camera(cam, W, H)
     emu = conftest.HostEmu(pkg).scene(scene, cfg)
     u = camera.uniforms(frame=1)
