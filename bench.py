@@ -261,7 +261,7 @@ def measure(job, name, K, Wm, reps, e2e_reps, bvh_build, sampler=None, want_cpu_
     W, H, world, rank = w["width"], w["height"], job.world, job.rank
     accum = T.ACCUM_SUM if world > 1 else T.ACCUM_MEAN
     cfg = pkg.make_config(W, H, max_bounces=w["max_bounces"], accum_mode=accum, light_sampling=w.get("light_sampling", 0),
-                          bvh_build=T.BVH_LBVH_DEVICE if bvh_build == "lbvh" else T.BVH_SAH_HOST)
+                          bvh_build={"sah": T.BVH_SAH_HOST, "lbvh": T.BVH_LBVH_DEVICE, "ploc": T.BVH_PLOC_DEVICE}[bvh_build])
     t_create = time.perf_counter()
     step = pkg.RTStep.create(scene, cfg, device=job.local)
     t_create = time.perf_counter() - t_create
@@ -431,7 +431,7 @@ def measure(job, name, K, Wm, reps, e2e_reps, bvh_build, sampler=None, want_cpu_
             "value_runs": runs, "value_how": f"median of {reps} repetitions of the {K}-step device-timed region",
             "run_sm_mhz": run_clock, "gpu_launches": launches,
             "config": {"workload": workload_string(w, bvh["triangles"]),
-                       "bvh": {"build": "lbvh (CUDA kernels)" if bvh["built_on_device"] else "binned SAH (host threads)", "build_ms": bvh["build_us"] / 1e3,
+                       "bvh": {"build": f"{bvh_build} (CUDA kernels)" if bvh["built_on_device"] else "binned SAH (host threads)", "build_ms": bvh["build_us"] / 1e3,
                                "nodes": bvh["nodes"], "max_depth": bvh["max_depth"], "bytes": bvh_bytes, "ptc_create_s": t_create},
                        "baseline_config_index": w["config_index"],
                        "parallelism": f"frame-sharded x{world}, scene replicated; image reduce: {job.reduce_how}" if world > 1 else "single GPU",
@@ -479,7 +479,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads pass (A/B timing of the headline only)")
     ap.add_argument("--reps", type=int, default=REPS)
-    ap.add_argument("--bvh-build", default="sah", choices=["sah", "lbvh"], help="sah: binned SAH on the host (default); lbvh: linear BVH built by CUDA kernels")
+    ap.add_argument("--bvh-build", default="sah", choices=["sah", "lbvh", "ploc"],
+                    help="sah: binned SAH on the host (default); lbvh: Morton-order linear BVH, ploc: bottom-up clustering — both built by CUDA kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -137,7 +137,8 @@ enum ptc_light_sampling {
  * depend on the choice: hit identity is defined on triangles, never on the tree. */
 enum ptc_bvh_build {
     PTC_BVH_SAH_HOST    = 0,  /* binned SAH on the host cores: best trees, seconds for 10 M triangles (default) */
-    PTC_BVH_LBVH_DEVICE = 1   /* Morton-order linear BVH built by CUDA kernels: milliseconds, slower to trace */
+    PTC_BVH_LBVH_DEVICE = 1,  /* Morton-order linear BVH built by CUDA kernels: milliseconds, slower to trace */
+    PTC_BVH_PLOC_DEVICE = 2   /* bottom-up clustering of the Morton-sorted triangles (PLOC) by CUDA kernels: tens of milliseconds */
 };
 
 /* compat flags */

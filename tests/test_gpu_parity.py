@@ -412,11 +412,13 @@ def test_light_sampling_mis_rejects_reference_light_branch(ptc, standins):
         ptc.RTStep.create(scene, cfg)
 
 
+@pytest.mark.parametrize("build", [1, 2], ids=["lbvh", "ploc"])
 @pytest.mark.parametrize("which", ["soup", "sponza", "cornell", "coincident"])
-def test_linear_bvh_device_build(ptc, standins, oracle, hostemu, which):
-    """PTC_BVH_LBVH_DEVICE: the tree built by CUDA kernels (Morton keys, CUB radix sort, Karras radix tree,
-    atomic bottom-up fit, collapse, quantised emit) equals the host restatement of the same build WORD FOR WORD (FNV hash
-    of node and triangle arrays), and renders the same image as the oracle, which uses its own SAH tree."""
+def test_linear_bvh_device_build(ptc, standins, oracle, hostemu, which, build):
+    """PTC_BVH_LBVH_DEVICE / PTC_BVH_PLOC_DEVICE: the tree built by CUDA kernels (Morton keys, CUB radix sort,
+    then Karras' radix tree + atomic bottom-up fit, or rounds of nearest-partner search / mutual merge / compaction; collapse,
+    quantised emit) equals the host restatement of the same build WORD FOR WORD (FNV hash of node and triangle arrays), and
+    renders the same image as the oracle, which uses its own SAH tree."""
     from conftest import random_rays
     T = ptc.types
     if which == "soup":
@@ -430,10 +432,10 @@ def test_linear_bvh_device_build(ptc, standins, oracle, hostemu, which):
         tri = np.array([[1.0, 0.5, -0.3], [1.0, 1.2, 0.0], [1.0, 0.5, 0.3]], np.float32)
         for _ in range(6):
             scene.add_mesh(np.tile(tri, (100, 1)), np.tile([-1, 0, 0], (300, 1)), None, np.arange(300), 1)
-    step, ref = render_both(ptc, standins, oracle, scene, cam, 320, 200, 2, max_bounces=5, bvh_build=T.BVH_LBVH_DEVICE)
+    step, ref = render_both(ptc, standins, oracle, scene, cam, 320, 200, 2, max_bounces=5, bvh_build=build)
     info = step.bvh_info()
     assert info["built_on_device"] and info["max_depth"] < 64
-    emu = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_LBVH_DEVICE))
+    emu = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=build))
     assert emu.bvh_info()["nodes"] == info["nodes"] and emu.bvh_info()["max_depth"] == info["max_depth"]
     assert step.bvh_hash() == emu.bvh_hash(), "device-built BVH differs from the host restatement"
     check_all_planes(ptc, step, ref)
@@ -608,7 +610,7 @@ def test_cpp_harness_matches_python_mirror(ptc, standins, tmp_path):
     step.destroy()
 
 
-@pytest.mark.parametrize("build", [0, 1])
+@pytest.mark.parametrize("build", [0, 1, 2])
 def test_degenerate_and_tied_geometry_gpu(ptc, standins, oracle, build):
     """Coincident duplicates (equal t: smaller triangle id wins), zero-area and sliver triangles, coplanar overlaps and a
     far-away triangle that stretches the quantisation grid: kernels == oracle on every plane, for both tree builders."""

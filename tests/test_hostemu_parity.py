@@ -145,8 +145,9 @@ def test_light_sampling_mis_mode(ptc, standins, oracle, hostemu, which):
     assert np.array_equal(ro["hit_id"], r0["hit_id"])                           # primary visibility is untouched
 
 
+@pytest.mark.parametrize("build", [1, 2], ids=["lbvh", "ploc"])
 @pytest.mark.parametrize("which", ["soup", "sponza", "cornell", "coincident"])
-def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which):
+def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which, build):
     """PTC_BVH_LBVH_DEVICE, host restatement of the device build: a different tree, the same hits —
     every plane bit-identical to the oracle, which uses its own SAH tree."""
     if which == "soup":
@@ -161,9 +162,9 @@ def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which):
         tri = np.array([[1.0, 0.5, -0.3], [1.0, 1.2, 0.0], [1.0, 0.5, 0.3]], np.float32)
         for _ in range(6):
             scene.add_mesh(np.tile(tri, (100, 1)), np.tile([-1, 0, 0], (300, 1)), None, np.arange(300), 1)
-    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 160, 100, 2, max_bounces=5, bvh_build=ptc.types.BVH_LBVH_DEVICE)
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 160, 100, 2, max_bounces=5, bvh_build=build)
     assert_identical(ro, re)
-    info = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=ptc.types.BVH_LBVH_DEVICE)).bvh_info()
+    info = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=build)).bvh_info()
     assert info["max_depth"] < 64 and info["triangles"] == len(scene.indices) // 3
 
 
@@ -186,7 +187,7 @@ def _degenerate_scene(ptc, standins):
     return scene, cam
 
 
-@pytest.mark.parametrize("build", [0, 1])
+@pytest.mark.parametrize("build", [0, 1, 2])
 def test_degenerate_and_tied_geometry(ptc, standins, oracle, hostemu, build):
     scene, cam = _degenerate_scene(ptc, standins)
     ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 200, 150, 2, max_bounces=5, bvh_build=build)

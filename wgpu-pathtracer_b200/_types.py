@@ -64,7 +64,7 @@ assert VERTEX_DT.itemsize == 48 and MESH_DT.itemsize == 20 and MATERIAL_DT.items
 TEXEL_RGBA8, TEXEL_RGBA32F = 0, 1
 ACCUM_MEAN, ACCUM_SUM = 0, 1
 LIGHTS_REFERENCE, LIGHTS_MIS = 0, 1
-BVH_SAH_HOST, BVH_LBVH_DEVICE = 0, 1
+BVH_SAH_HOST, BVH_LBVH_DEVICE, BVH_PLOC_DEVICE = 0, 1, 2
 PLANE_COLOR, PLANE_DEPTH, PLANE_NORMAL, PLANE_ALBEDO, PLANE_HIT_ID, PLANE_DISPLAY, PLANE_REPROJECTED, PLANE_REDUCED = 0, 1, 2, 3, 4, 5, 6, 7
 TEX_CONSTANT, TEX_FILE, TEX_TEXELS = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_NOT_READY, ERR_IO, ERR_PARSE = 0, -1, -2, -3, -4, -5, -6, -7

@@ -362,4 +362,100 @@ void build_lbvh_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t
     for (uint32_t i = 0; i < ntri; ++i) lbvh_put_tri(out.tris[i].q, tri_pos + (size_t)ids[i] * 9, ids[i]);
 }
 
+// ---- PLOC: host restatement of the device build (bvh_gpu.cu build_ploc_device; shared arithmetic in lbvh.cuh) -------------
+// Same keys and sort as the linear BVH, then rounds of nearest-partner search / mutual merge / compaction, a top-down pass
+// that numbers the triangles in depth-first order (so that a collapsed leaf's triangles are consecutive), and the emission
+// of the quantised nodes.  Every step is a deterministic function of its inputs, so the arrays equal the device build's
+// word for word (ptc_debug_bvh_hash).
+void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth) {
+    const int n = (int)ntri;
+    std::vector<PlocBox> box((size_t)2 * n - 1);
+    std::vector<PlocBox> prim(ntri);
+    float slo[3], shi[3], clo[3], chi[3];
+    for (int a = 0; a < 3; ++a) { slo[a] = clo[a] = std::numeric_limits<float>::infinity(); shi[a] = chi[a] = -slo[a]; }
+    for (uint32_t i = 0; i < ntri; ++i) {
+        lbvh_tri_box(tri_pos + (size_t)i * 9, prim[i].lo, prim[i].hi);
+        for (int a = 0; a < 3; ++a) {
+            float c = 0.5f * (prim[i].lo[a] + prim[i].hi[a]);
+            slo[a] = fminf(slo[a], prim[i].lo[a]); shi[a] = fmaxf(shi[a], prim[i].hi[a]);
+            clo[a] = fminf(clo[a], c); chi[a] = fmaxf(chi[a], c);
+        }
+    }
+    float scale[3];
+    for (int a = 0; a < 3; ++a) { float ext = chi[a] - clo[a]; scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f; }
+    std::vector<uint64_t> key(ntri);
+    std::vector<uint32_t> ids(ntri);
+    for (uint32_t i = 0; i < ntri; ++i) { key[i] = lbvh_key(tri_pos + (size_t)i * 9, clo, scale); ids[i] = i; }
+    std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    // nodes 0 .. n-1: the sorted primitives; n .. 2n-2: merged clusters in order of creation (the last one is the root)
+    std::vector<uint32_t> left((size_t)2 * n - 1, 0xFFFFFFFFu), right((size_t)2 * n - 1, 0xFFFFFFFFu), count((size_t)2 * n - 1, 1u);
+    std::vector<uint32_t> kc((size_t)2 * n - 1, 0u);       // emitted (count > PTC_PLOC_MAX_LEAF) nodes in the subtree, the node included
+    for (int k = 0; k < n; ++k) box[k] = prim[ids[k]];
+    std::vector<uint32_t> cur(n), nxt(n);
+    std::vector<int> nn(n);
+    for (int k = 0; k < n; ++k) cur[k] = (uint32_t)k;
+    std::vector<uint32_t> round_base;                 // first node created in each round (top-down passes walk the rounds backwards)
+    uint32_t next_node = (uint32_t)n;
+    int m = n;
+    const int nthreads = std::max(1u, std::thread::hardware_concurrency());
+    auto par = [&](int cnt, auto&& fn) {
+        if (cnt < 4096 || nthreads == 1) { fn(0, cnt); return; }
+        std::vector<std::thread> th; const int chunk = (cnt + nthreads - 1) / nthreads;
+        for (int t = 0; t < nthreads; ++t) { const int b = t * chunk, e = std::min(cnt, b + chunk); if (b < e) th.emplace_back([&, b, e] { fn(b, e); }); }
+        for (auto& x : th) x.join();
+    };
+    while (m > 1) {
+        par(m, [&](int b, int e) { for (int i = b; i < e; ++i) nn[i] = ploc_nearest(box.data(), cur.data(), m, i); });
+        round_base.push_back(next_node);
+        int w = 0;
+        for (int i = 0; i < m; ++i) {
+            const int j = nn[i];
+            const bool mutual = nn[j] == i;
+            if (mutual && i > j) continue;                                   // the right partner disappears into the merged cluster
+            if (mutual) {
+                const uint32_t a = cur[i], b = cur[j], nd = next_node++;
+                left[nd] = a; right[nd] = b; count[nd] = count[a] + count[b];
+                kc[nd] = kc[a] + kc[b] + (count[nd] > PTC_PLOC_MAX_LEAF ? 1u : 0u);
+                for (int x = 0; x < 3; ++x) { box[nd].lo[x] = fminf(box[a].lo[x], box[b].lo[x]); box[nd].hi[x] = fmaxf(box[a].hi[x], box[b].hi[x]); }
+                nxt[w++] = nd;
+            } else nxt[w++] = cur[i];
+        }
+        m = w;
+        cur.swap(nxt);
+    }
+    const uint32_t root = cur[0], total = next_node;
+    round_base.push_back(total);
+    // top-down: position of every subtree's first triangle in depth-first order, emitted ancestors above it, and the node's
+    // number in DEPTH-FIRST (pre-)order — a child follows its parent directly, so a descent walks forward through memory
+    // (numbering the nodes in order of creation, i.e. level by level, cost 15-25 % of the traversal speed on the 890 MB tree)
+    std::vector<uint32_t> offset(total, 0), depth(total, 0), new_id(total, 0);
+    auto kept = [&](uint32_t nd) { return nd >= (uint32_t)n && count[nd] > PTC_PLOC_MAX_LEAF; };
+    for (int r = (int)round_base.size() - 2; r >= 0; --r)
+        for (uint32_t nd = round_base[r + 1]; nd-- > round_base[r];) {
+            const uint32_t a = left[nd], b = right[nd], k = kept(nd) ? 1u : 0u;
+            offset[a] = offset[nd]; offset[b] = offset[nd] + count[a];
+            depth[a] = depth[b] = depth[nd] + k;
+            new_id[a] = new_id[nd] + 1u; new_id[b] = new_id[nd] + 1u + kc[a];
+        }
+    uint32_t dmax = 0;
+    for (int k = 0; k < n; ++k) dmax = std::max(dmax, depth[k]);
+    max_depth = dmax + 1;
+    const uint32_t num_nodes = kc[root];
+    LbvhFrame fr; lbvh_frame(slo, shi, fr);
+    out.grid = fr.grid;
+    out.nodes.assign(num_nodes, DevNode2{});
+    for (uint32_t nd = (uint32_t)n; nd < total; ++nd) {
+        if (!kept(nd)) continue;
+        DevNode2 d;
+        const uint32_t ch[2] = {left[nd], right[nd]};
+        for (int c = 0; c < 2; ++c) {
+            lbvh_put_box(&d.w[c * 4], box[ch[c]].lo, box[ch[c]].hi, fr.pad, fr.grid.base, fr.step);
+            d.w[c * 4 + 3] = count[ch[c]] <= PTC_PLOC_MAX_LEAF ? ~((offset[ch[c]] << 3) | (count[ch[c]] - 1u)) : new_id[ch[c]];
+        }
+        out.nodes[new_id[nd]] = d;
+    }
+    out.tris.resize(ntri);
+    for (int k = 0; k < n; ++k) lbvh_put_tri(out.tris[offset[k]].q, tri_pos + (size_t)ids[k] * 9, ids[k]);
+}
+
 }  // namespace ptc

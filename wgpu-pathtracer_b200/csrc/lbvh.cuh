@@ -124,17 +124,25 @@ PT_HD float ploc_joint_area(const PlocBox& a, const PlocBox& b) {        // half
     return dx * dy + (dy * dz + dz * dx);
 }
 // best partner of cluster i among its neighbours in the current cluster array (m clusters, cur[] = node index per cluster).
-// Candidates are ordered by (area, min(i,j), max(i,j)): a strict total order on PAIRS, so the globally best pair is mutual
-// and every round merges at least one pair whatever the ties.
+// Candidate PAIRS are ordered by (area, index distance, parity of the lower index — even first —, lower index): a strict total
+// order on pairs, so the globally best pair is always mutual and every round merges at least one pair whatever the ties; and
+// among clusters with IDENTICAL boxes (coincident triangles) the order pairs neighbours (0,1) (2,3) ... so the tree stays
+// balanced instead of degenerating into a chain.
 PT_HD int ploc_nearest(const PlocBox* box, const uint32_t* cur, int m, int i) {
     const PlocBox bi = box[cur[i]];
     const int j0 = i - PTC_PLOC_RADIUS < 0 ? 0 : i - PTC_PLOC_RADIUS, j1 = i + PTC_PLOC_RADIUS > m - 1 ? m - 1 : i + PTC_PLOC_RADIUS;
-    float best = INFINITY; int bj = -1;
+    float best = INFINITY; int bj = -1, bd = 0, bmn = 0;
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float c = ploc_joint_area(bi, box[cur[j]]);
-        // ascending j: among equal areas, j < i are ordered by j (= the pair's min), then j > i (pair (i, j): min is i, larger than any j < i)
-        if (c < best) { best = c; bj = j; }
+        const int d = j < i ? i - j : j - i, mn = j < i ? j : i;
+        bool better = c < best;
+        if (c == best && bj >= 0) {
+            if (d != bd) better = d < bd;
+            else if ((mn & 1) != (bmn & 1)) better = (mn & 1) == 0;
+            else better = mn < bmn;
+        }
+        if (better || bj < 0) { best = c; bj = j; bd = d; bmn = mn; }
     }
     return bj;
 }

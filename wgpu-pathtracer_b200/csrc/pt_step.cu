@@ -278,7 +278,8 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
         CK(cudaMalloc(&d_pos, ps.tri_pos.size() * 4));
         cudaError_t ce = cudaMemcpyAsync(d_pos, ps.tri_pos.data(), ps.tri_pos.size() * 4, cudaMemcpyHostToDevice, s->stream);
         GpuBvh g;
-        rc = ce == cudaSuccess ? build_lbvh_device(d_pos, ps.num_tris, s->stream, g) : PTC_ERR_CUDA;
+        rc = ce != cudaSuccess ? PTC_ERR_CUDA : (s->cfg.bvh_build == PTC_BVH_PLOC_DEVICE ? build_ploc_device(d_pos, ps.num_tris, s->stream, g)
+                                                                                                 : build_lbvh_device(d_pos, ps.num_tris, s->stream, g));
         cudaFree(d_pos);
         if (rc != PTC_OK) { if (ce != cudaSuccess) set_error(std::string("position upload: ") + cudaGetErrorString(ce)); return rc; }
         if (g.max_depth >= PTC_STACK_SIZE) {
@@ -458,7 +459,7 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     if (config->max_bounces + 1 > PTC_MAX_SEGMENTS) { set_error("max_bounces too large"); return PTC_ERR_INVALID; }
     if (config->accum_mode > PTC_ACCUM_SUM) { set_error("bad accum_mode"); return PTC_ERR_INVALID; }
     if (config->light_sampling > PTC_LIGHTS_MIS) { set_error("bad light_sampling"); return PTC_ERR_INVALID; }
-    if (config->bvh_build > PTC_BVH_LBVH_DEVICE) { set_error("bad bvh_build"); return PTC_ERR_INVALID; }
+    if (config->bvh_build > PTC_BVH_PLOC_DEVICE) { set_error("bad bvh_build"); return PTC_ERR_INVALID; }
     // fields this build gives no meaning to must be zero, so a caller never believes an option took effect
     if (config->bvh_width != 0 && config->bvh_width != 2) { set_error("bad bvh_width (0 = library default, 2 = BVH2)"); return PTC_ERR_INVALID; }
     if (config->compat_flags != PTC_COMPAT_NONE) { set_error("unknown compat_flags (none are defined)"); return PTC_ERR_INVALID; }

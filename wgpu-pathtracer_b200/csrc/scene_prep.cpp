@@ -74,12 +74,14 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
         for (uint64_t t = b; t < e; ++t)
             for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], v->vertices[v->indices[(size_t)t * 3 + k]].position, 12);
     });
-    const bool lbvh = cfg.bvh_build == PTC_BVH_LBVH_DEVICE && ntri > PTC_LBVH_MAX_LEAF;
+    const bool ploc = cfg.bvh_build == PTC_BVH_PLOC_DEVICE && ntri > 4;
+    const bool lbvh = ploc || (cfg.bvh_build == PTC_BVH_LBVH_DEVICE && ntri > PTC_LBVH_MAX_LEAF);
     if (lbvh && caller_builds_bvh) out.tri_pos = pos;
     else {
         bool sah = !lbvh;
         if (lbvh) {
-            build_lbvh_host(pos.data(), ntri, out.bvh, out.max_depth);
+            if (ploc) build_ploc_host(pos.data(), ntri, out.bvh, out.max_depth);
+            else build_lbvh_host(pos.data(), ntri, out.bvh, out.max_depth);
             if (out.max_depth >= PTC_STACK_SIZE) { out.bvh = DevBvh2{}; sah = true; }     // degenerate input: fall back to the SAH tree
         }
         if (sah) {
