@@ -192,7 +192,7 @@ int emu_warpsim(const void* scene, const float* rays, uint64_t n, const SimParam
                         out->it_node++; out->ln_node += act;
                         if (getenv("WS_DIAG")) { static uint64_t a_leaf = 0, a_idle = 0, its = 0; uint32_t nl = 0, ni = 0;
                             for (int l = 0; l < 32; ++l) { if (L[l].node == PTC_SENTINEL) ni++; else if (L[l].node < 0) nl++; }
-                            a_leaf += nl; a_idle += ni; its++; if (its % 200000 == 0) fprintf(stderr, "node its %llu: after-step at_leaf %.2f idle %.2f\n", (unsigned long long)its, (double)a_leaf / its, (double)a_idle / its); }
+                            a_leaf += nl; a_idle += ni; its++; if (its % 20000 == 0) fprintf(stderr, "node its %llu: after-step at_leaf %.2f idle %.2f\n", (unsigned long long)its, (double)a_leaf / its, (double)a_idle / its); }
                         if (P->node_inner) {
                             uint32_t still = 0;
                             for (int l = 0; l < 32; ++l) if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL) still++;

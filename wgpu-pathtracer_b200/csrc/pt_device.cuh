@@ -172,12 +172,22 @@ struct HitRec { float t, b1, b2; uint32_t tri; };   // tri = global triangle id,
 #define PTC_SENTINEL 0x7fffffff
 
 // ---- slab test ------------------------------------------------------------------------------------------
-// A box plane is stored as q in [0, 32767] on the scene grid: position = base + q * extent / 32768.  One PRMT turns the
-// stored 16 bits into the float F = 1 + q / 32768, and the plane's ray distance is ONE FMA:
-//     t = (base + q * extent / 32768 - o) / d = F * A + C,   A = extent / d,   C = (base - o) / d - A.
-// Which of a box's two planes per axis the ray enters through depends only on the sign of d, so the PRMT selector
-// (a per-ray register) picks the entry plane and the exit plane directly: no per-node min/max per axis.
-// Error: |fma(F, A, C) - t| <= 2^-21 (|A| + |(base - o) / d|) (roundings of 1/d, A, C and the FMA itself; F <= 2), an
+// A box plane is stored as q in [0, 32767] on the scene grid: position = base + q * extent / 32768; a node word holds the two
+// planes of one axis as 16-bit halves `0x8000 | q`.  ONE instruction turns a half into the float F = 1 + q / 65536 and the
+// plane's ray distance is one FMA with per-ray constants:
+//     t = (base + q * extent / 32768 - o) / d = F * A + C,   A = 2 extent / d,   C = (base - o) / d - A.
+// Which of a box's two planes per axis the ray enters through depends only on the sign of d, so the decode's selector (a
+// per-ray register) picks the entry plane and the exit plane directly: no per-node min/max per axis.
+// The decode is IDP.2A (dp2a.lo: c + w.h0 * sel.b0 + w.h1 * sel.b1 with sel = (128, 0) or (0, 128) and c = 0x3F800000 -
+// (0x8000 << 7), i.e. float bits 0x3F800000 + (q << 7)), an FMA-pipe instruction: the kernel's busiest unit is the ALU pipe
+// (ncu: 65 % of its peak at 70 % issue-active; min/max, selects, compares and logic all live there), and the same decode
+// written as PRMT sat on that pipe too.  Entry and exit distance of an axis can also come from ONE FFMA2 (f32x2, sm_100):
+// {F_entry, F_exit} * {A, A} + {C_entry, C_exit} (-DPTC_FFMA2).  Measured on B200 (tools/microbench/slab.cu,
+// profiles/r02k_slab.txt), cycles per two-box test per scheduler: PRMT + FFMA 46.7, IDP.2A + FFMA 42.7, IDP.2A + FFMA2 39.0 —
+// but k_trace itself does not follow (profiles/r02l_ab_slab.log, r02m_ab_push.log: all three within +-0.5 %): its time goes
+// to waiting for the slowest lane's node load, not to the arithmetic.  FFMA2 needs aligned register pairs and costs 28 more
+// bytes of spills at 48 registers, so the default is IDP.2A + FFMA; -DPTC_SLAB_PRMT restores the PRMT form (A/B).
+// Error: |fma(F, A, C) - t| <= 2^-21 (|A| + |(base - o) / d|) (roundings of 1/d, A, C and the FMA itself; F < 1.5), an
 // ABSOLUTE bound that is largest for a ray nearly parallel to the axis.  Twice that bound is folded into the constant:
 // the entry plane moves back, the exit plane forward, so the test is conservative with respect to pt_ray_tri (hit
 // identity can never depend on it) at no extra instruction, and a near-parallel ray only loses culling along the one
@@ -186,12 +196,30 @@ struct HitRec { float t, b1, b2; uint32_t tri; };   // tri = global triangle id,
 struct RaySlab {
     float ax, ay, az;             // A per axis
     float nx, fx, ny, fy, nz, fz; // C for the entry (near) / exit (far) plane of each axis
-    uint32_t sx, sy, sz;          // PRMT selector of the entry plane; the exit plane's is sel ^ PT_SEL_FLIP
+    uint32_t sx, sy, sz;          // decode selector of the entry plane; the exit plane's is sel ^ PT_SEL_FLIP
 };
-#define PT_SEL_LO 0x7104u          // bytes {0x00, w.b0, w.b1, 0x3F}: the low 16 bits of the word -> float bits
+#if defined(PTC_SLAB_PRMT)
+#define PT_SEL_LO 0x7104u          // PRMT bytes {0x00, w.b0, w.b1, 0x3F}: the low 16 bits of the word -> float bits 0x3F000000 + (h << 8)
 #define PT_SEL_HI 0x7324u          // bytes {0x00, w.b2, w.b3, 0x3F}: the high 16 bits
 #define PT_SEL_FLIP 0x0220u
 #define PT_SEL_POOL 0x3F000000u
+#define PT_SLAB_SCALE 1.0f         // F = 1 + q / 32768
+#else
+#define PT_SEL_LO 0x00000080u      // dp2a.lo multipliers (b0, b1) = (128, 0): the low 16 bits of the word
+#define PT_SEL_HI 0x00008000u      // (0, 128): the high 16 bits
+#define PT_SEL_FLIP 0x00008080u
+#define PT_SEL_BIAS 0x3F400000u    // + (0x8000 | q) * 128 = 0x3F800000 + (q << 7)
+#define PT_SLAB_SCALE 2.0f         // F = 1 + q / 65536
+#endif
+
+// dp2a.lo.u32.u32: c + a.h0 * b.b0 + a.h1 * b.b1 (16-bit halves of a, low two bytes of b)
+PT_HD uint32_t pt_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(a, b, c);
+#else
+    return c + (a & 0xFFFFu) * (b & 0xFFu) + (a >> 16) * ((b >> 8) & 0xFFu);
+#endif
+}
 
 PT_HD float pt_min3(float a, float b, float c) {
 #if defined(__CUDA_ARCH__) && !defined(PTC_NO_MINMAX3)
@@ -213,7 +241,7 @@ PT_HD void slab_axis(float o, float d, float base, float extent, float& a, float
     const float kErr = 9.5367431640625e-7f;       // 2^-20
     const float dd = pt_abs(d) > kTiny ? d : copysignf(kTiny, d);
     const float inv = pt_div(1.0f, dd);
-    a = extent * inv;
+    a = (extent * PT_SLAB_SCALE) * inv;
     const float b = (base - o) * inv;
     const float c = b - a;
     const float e = (pt_abs(a) + pt_abs(b)) * kErr;
@@ -238,14 +266,29 @@ PT_HD bool ray_is_finite(pt_v3 o, pt_v3 d) {
 }
 
 // Both children of one BVH2 node against the ray: hit flags and entry distances.
-PT_HD float slab_plane(uint32_t w, uint32_t sel, float a, float c) { return pt_fma(u2f(pt_prmt(w, PT_SEL_POOL, sel)), a, c); }
+// slab_pair: entry and exit distance of the ray to the two planes of one axis word.
+PT_HD void slab_pair(uint32_t w, uint32_t sel, float a, float cn, float cf, float& tn, float& tf) {
+#if defined(PTC_SLAB_PRMT)
+    const uint32_t n = pt_prmt(w, PT_SEL_POOL, sel), f = pt_prmt(w, PT_SEL_POOL, sel ^ PT_SEL_FLIP);
+#else
+    const uint32_t n = pt_dp2a_lo(w, sel, PT_SEL_BIAS), f = pt_dp2a_lo(w, sel ^ PT_SEL_FLIP, PT_SEL_BIAS);
+#endif
+#if defined(__CUDA_ARCH__) && defined(PTC_FFMA2)
+    const float2 t = __ffma2_rn(make_float2(u2f(n), u2f(f)), make_float2(a, a), make_float2(cn, cf));   // two IEEE fmas, one instruction
+    tn = t.x; tf = t.y;
+#else
+    tn = pt_fma(u2f(n), a, cn); tf = pt_fma(u2f(f), a, cf);
+#endif
+}
 PT_HD void node_test(const RaySlab& r, const NodeQ& n, float tmax, bool& h0, bool& h1, float& tn0, float& tn1) {
-    const uint32_t fx = r.sx ^ PT_SEL_FLIP, fy = r.sy ^ PT_SEL_FLIP, fz = r.sz ^ PT_SEL_FLIP;
+    float nx, fx, ny, fy, nz, fz;
     // fmin/fmax drop NaNs, so a degenerate plane simply stops constraining the interval
-    tn0 = pt_max3(slab_plane(n.w[0], r.sx, r.ax, r.nx), slab_plane(n.w[1], r.sy, r.ay, r.ny), fmaxf(slab_plane(n.w[2], r.sz, r.az, r.nz), 0.0f));
-    const float tf0 = pt_min3(slab_plane(n.w[0], fx, r.ax, r.fx), slab_plane(n.w[1], fy, r.ay, r.fy), fminf(slab_plane(n.w[2], fz, r.az, r.fz), tmax));
-    tn1 = pt_max3(slab_plane(n.w[4], r.sx, r.ax, r.nx), slab_plane(n.w[5], r.sy, r.ay, r.ny), fmaxf(slab_plane(n.w[6], r.sz, r.az, r.nz), 0.0f));
-    const float tf1 = pt_min3(slab_plane(n.w[4], fx, r.ax, r.fx), slab_plane(n.w[5], fy, r.ay, r.fy), fminf(slab_plane(n.w[6], fz, r.az, r.fz), tmax));
+    slab_pair(n.w[0], r.sx, r.ax, r.nx, r.fx, nx, fx); slab_pair(n.w[1], r.sy, r.ay, r.ny, r.fy, ny, fy); slab_pair(n.w[2], r.sz, r.az, r.nz, r.fz, nz, fz);
+    tn0 = pt_max3(nx, ny, fmaxf(nz, 0.0f));
+    const float tf0 = pt_min3(fx, fy, fminf(fz, tmax));
+    slab_pair(n.w[4], r.sx, r.ax, r.nx, r.fx, nx, fx); slab_pair(n.w[5], r.sy, r.ay, r.ny, r.fy, ny, fy); slab_pair(n.w[6], r.sz, r.az, r.nz, r.fz, nz, fz);
+    tn1 = pt_max3(nx, ny, fmaxf(nz, 0.0f));
+    const float tf1 = pt_min3(fx, fy, fminf(fz, tmax));
     h0 = tn0 <= tf0;
     h1 = tn1 <= tf1;
 }

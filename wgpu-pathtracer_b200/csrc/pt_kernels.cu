@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
         __syncthreads();
     }
 #endif
+    // (keeping the top of the stack in a register, so that a pop hands over the next node without waiting for local memory,
+    // measured 2.5-3 % SLOWER on every workload, profiles/r02n_ab_top.log: three more instructions per node step cost more
+    // than the shorter dependent chain gains)
     int stack[PTC_STACK_SIZE];
     int node = PTC_SENTINEL, sp = 0;
     uint32_t ray = kNoRay, tri_i = 0, tri_end = 0;
@@ -260,8 +263,14 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
                         // the child visited next is c1 when c0 is missed, or when both are hit and c1 is nearer (irrelevant when both are missed)
                         const bool take1 = !h0 || (h1 && tn1 < tn0);
                         const int next = take1 ? c1 : c0, other = take1 ? c0 : c1;
+#ifdef PTC_PUSH_UNCOND
                         stack[sp] = other;                                  // unconditional: the slot above the top is scratch
                         if (h0 && h1) sp++;
+#else
+                        // predicated store: local-memory stores are written through to L2 (ncu: 20 M sectors = 640 MB per launch when
+                        // every node step stored), and only ~1/3 of the steps push
+                        if (h0 && h1) { stack[sp] = other; sp++; }
+#endif
                         if (!(h0 || h1)) { sp--; node = stack[sp]; } else node = next;
                     }
                 }
