@@ -473,6 +473,15 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32u; base < n; base += nwarps * 32u) {
         const uint32_t i = base + lane;
+#ifdef PTC_SHADE_PREFETCH
+        {   // the next batch's queue entries on their way from HBM to L2 while this batch is shaded (A/B)
+            const uint32_t j = i + nwarps * 32u;
+            if (j < n) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(qin.ray_o + j)); asm volatile("prefetch.global.L2 [%0];" :: "l"(qin.ray_d + j));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(hits + j)); if (!FIRST) asm volatile("prefetch.global.L2 [%0];" :: "l"(qin.mask + j));
+            }
+        }
+#endif
         bool alive = false;
         uint32_t pixel = 0, rng = 0;
         pt_v3 no = pt_mk3(0.0f, 0.0f, 0.0f), nd = no, mask = pt_mk3(1.0f, 1.0f, 1.0f), acc = no;
@@ -494,9 +503,13 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             }
             float pdf_prev = -1.0f;
             if (!FIRST) {
-                asm volatile("" ::: "memory");                        // keep these two loads AFTER the BSDF code (register pressure)
-                const F4 m = ld4_stream(qin.mask + i), a = ld4_stream(qin.acc + i);
-                mask = pt_mk3(m.x, m.y, m.z); acc = pt_mk3(a.x, a.y, a.z);
+                asm volatile("" ::: "memory");                        // keep these loads AFTER the BSDF code (register pressure)
+                const F4 m = ld4_stream(qin.mask + i);
+                mask = pt_mk3(m.x, m.y, m.z);
+                // Without light sampling a path that is still alive has added nothing but `0 * mask` to its accumulated colour (an
+                // emissive hit ends it, pathtracer/pathtracer.wgsl:204-206), so that queue entry is all zero bits unless the
+                // throughput went non-finite (0 * inf): mask.w says whether it was written at all.  -32 B of queue traffic per ray.
+                if (MIS || m.w != 0.0f) { const F4 a = ld4_stream(qin.acc + i); acc = pt_mk3(a.x, a.y, a.z); }
                 if (MIS) pdf_prev = m.w;
             }
             if (MIS) { nee = so.nee; nee_d = so.nee_d; nee_tmax = so.nee_tmax; nee_c = pt_mul(so.nee_c, mask); pdf_next = so.pdf_next; }
@@ -529,8 +542,9 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 const uint32_t slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
                 st4_stream(qout.ray_o + slot, no.x, no.y, no.z, __uint_as_float(pixel));
                 st4_stream(qout.ray_d + slot, nd.x, nd.y, nd.z, __uint_as_float(rng));
-                st4_stream(qout.mask + slot, mask.x, mask.y, mask.z, MIS ? pdf_next : 0.0f);
-                st4_stream(qout.acc + slot, acc.x, acc.y, acc.z, 0.0f);
+                const bool acc_set = (f2u(acc.x) | f2u(acc.y) | f2u(acc.z)) != 0u;           // any bit: -0 and NaN travel too
+                st4_stream(qout.mask + slot, mask.x, mask.y, mask.z, MIS ? pdf_next : (acc_set ? 1.0f : 0.0f));
+                if (MIS || acc_set) st4_stream(qout.acc + slot, acc.x, acc.y, acc.z, 0.0f);
                 if (MIS) pixel = slot;                                    // the shadow entry names the path by its slot
             }
         }
