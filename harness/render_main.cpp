@@ -1,11 +1,12 @@
 // render_main.cpp — plays the reference's `Raytracer` (src/raytracer.rs:40-199) headless, in compiled host code over the
 // C ABI: Scene::new + load_obj, Camera::new, RTStep::create, then the per-frame loop of Raytracer::render — frame counter
 // from 1 (raytracer.rs:180), step.update, step.render — and a dump of what the window would show (PPM, through the blit
-// pass) plus the raw accumulation (PFM).  Image decoding is the caller's job in this library (texture.rs:232-253), so the
-// harness takes the environment map as raw float32 RGBA (--env-raw) or uses a constant sky; OBJ scenes whose materials
-// reference image files need a caller with a decoder (the Python mirror uses OpenCV).
+// pass) plus the raw accumulation (PFM).  The textures an OBJ's materials name are decoded by the library
+// (ptc_scene_decode_textures: PNG / PFM on the host threads, JPEG by nvJPEG on the GPU — Texture::load, texture.rs:232-243).
+// The environment map (the reference's res/knob/envmap.exr; no OpenEXR decoder in this image) comes as a PFM (--env), as raw
+// float32 RGBA (--env-raw), or is a constant sky.
 //
-//   ptrender --obj scene.obj [--env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z]
+//   ptrender --obj scene.obj [--env sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z]
 //            [--fov deg] [--lbvh] [--lights-mis] [--out prefix]
 #include "../include/ptcore.hpp"
 
@@ -15,9 +16,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <vector>
 
 int main(int argc, char** argv) {
-    std::string obj, env_raw, out = "ptrender";
+    std::string obj, env_raw, env_pfm, out = "ptrender";
     uint32_t W = 512, H = 512, env_w = 0, env_h = 0, frames = 16, bounces = 4;
     float pos[3] = {0, 0, 0}, fov = 60.0f;
     double look[3] = {1, 0, 0};
@@ -26,6 +29,7 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         auto need = [&](int n) { if (i + n >= argc) { fprintf(stderr, "ptrender: %s needs %d value(s)\n", a.c_str(), n); exit(2); } };
         if (a == "--obj") { need(1); obj = argv[++i]; }
+        else if (a == "--env") { need(1); env_pfm = argv[++i]; }
         else if (a == "--env-raw") { need(3); env_raw = argv[++i]; env_w = (uint32_t)atoi(argv[++i]); env_h = (uint32_t)atoi(argv[++i]); }
         else if (a == "--size") { need(1); if (sscanf(argv[++i], "%ux%u", &W, &H) != 2) { fprintf(stderr, "ptrender: --size WxH\n"); return 2; } }
         else if (a == "--frames") { need(1); frames = (uint32_t)atoi(argv[++i]); }
@@ -37,7 +41,7 @@ int main(int argc, char** argv) {
         else if (a == "--lights-mis") mis = true;
         else if (a == "--out") { need(1); out = argv[++i]; }
         else if (a == "--help" || a == "-h") {
-            printf("ptrender --obj scene.obj [--env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
+            printf("ptrender --obj scene.obj [--env sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
             return 0;
         } else { fprintf(stderr, "ptrender: unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -45,16 +49,27 @@ int main(int argc, char** argv) {
     try {
         ptcore::Scene scene("envmap");                                     // Scene::new: textures 0..8 constants, 9 = environment
         std::vector<float> env;
-        if (!env_raw.empty()) {
+        if (!env_pfm.empty()) {
+            std::ifstream f(env_pfm, std::ios::binary);
+            std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            uint32_t fmt = 0; void* px = nullptr;
+            ptcore::check(ptc_decode_image(bytes.data(), bytes.size(), 0, &env_w, &env_h, &fmt, &px));
+            if (fmt != PTC_TEXEL_RGBA32F) { fprintf(stderr, "ptrender: --env wants a float image (PFM)\n"); return 2; }
+            env.assign((const float*)px, (const float*)px + (size_t)env_w * env_h * 4);
+            ptc_free(px);
+        } else if (!env_raw.empty()) {
             env.resize((size_t)env_w * env_h * 4);
             std::ifstream f(env_raw, std::ios::binary);
             if (!f.read((char*)env.data(), (std::streamsize)(env.size() * 4))) { fprintf(stderr, "ptrender: cannot read %s\n", env_raw.c_str()); return 2; }
         } else { env_w = env_h = 1; env = {0.5f, 0.6f, 0.8f, 1.0f}; }
         scene.set_texels(9, env_w, env_h, PTC_TEXEL_RGBA32F, env.data());
         scene.load_obj(obj);
-        for (uint64_t t = 0; t < scene.num_textures(); ++t) {
-            ptc_scene_texture_info ti = scene.texture_info(t);
-            if (ti.source == PTC_TEX_FILE && ti.width == 0) { fprintf(stderr, "ptrender: texture %s needs an image decoder (use the Python mirror)\n", ti.path ? ti.path : "?"); return 2; }
+        {
+            auto td = std::chrono::steady_clock::now();
+            scene.decode_textures(0, 0);                                   // Texture::load on every file the materials name
+            uint64_t files = 0;
+            for (uint64_t t = 0; t < scene.num_textures(); ++t) files += scene.texture_info(t).source == PTC_TEX_FILE ? 1 : 0;
+            if (files) printf("ptrender: %llu texture file(s) decoded in %.3f s\n", (unsigned long long)files, std::chrono::duration<double>(std::chrono::steady_clock::now() - td).count());
         }
         ptcore::Camera cam(W, H, fov, pos);                                // Camera::new
         if (have_look) {                                                   // steer as the window's mouse handler would: theta from the target

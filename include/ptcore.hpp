@@ -1,7 +1,7 @@
 // ptcore.hpp — header-only C++ face of the C ABI (include/ptcore.h), shaped like the reference's own host types so that
 // compiled host code reads like the Rust it replaces:
 //   ptcore::Camera      <- src/camera.rs:5-79        (Camera::new / update, Uniforms::new)
-//   ptcore::Scene       <- src/scene.rs:65-128       (Scene::new / load_obj; textures handed over as decoded texels)
+//   ptcore::Scene       <- src/scene.rs:65-128       (Scene::new / load_obj; textures decoded by the library or handed over as texels)
 //   ptcore::RenderStep  <- src/render_steps/mod.rs:20-25 (trait RenderStep: create / update / render / resize)
 //   ptcore::RTStep      <- src/render_steps/pt.rs:12-25, 341-565, 732-745
 // Errors: the reference panics (unwrap / expect); here every failed call throws ptcore::Error carrying ptc_last_error().
@@ -43,7 +43,9 @@ public:
     void load_obj_text(const std::string& obj, const std::string& mtl, const std::string& dir) { check(ptc_scene_load_obj_text(s_, obj.c_str(), mtl.c_str(), dir.c_str())); }
     uint64_t num_textures() const { return ptc_scene_num_textures(s_); }
     ptc_scene_texture_info texture_info(uint64_t i) const { ptc_scene_texture_info t; check(ptc_scene_texture_info_at(s_, i, &t)); return t; }
-    // Texture::load's decode step (texture.rs:232-253) happens in the caller: hand the texels over
+    // Texture::load's decode step (texture.rs:232-243): either the library decodes the files (PNG / PFM on the host threads, JPEG by
+    // nvJPEG on the GPU; scene.rs:239-254 runs it on 32 threads), or the caller hands decoded texels over
+    void decode_textures(int cuda_device = 0, int n_threads = 0) { check(ptc_scene_decode_textures(s_, cuda_device, n_threads)); }
     void set_texels(uint64_t i, uint32_t w, uint32_t h, uint32_t format, const void* texels) { check(ptc_scene_set_texels(s_, i, w, h, format, texels)); }
     ptc_scene_view view() const { ptc_scene_view v; check(ptc_scene_get_view(s_, &v)); return v; }
 };

@@ -4,9 +4,9 @@
 // tests/test_rust_boundary.py fails when the two drift apart.
 use std::{env, path::PathBuf, process::Command};
 
-const CUDA_SOURCES: [&str; 3] = ["pt_kernels.cu", "pt_step.cu", "bvh_gpu.cu"];
+const CUDA_SOURCES: [&str; 4] = ["pt_kernels.cu", "pt_step.cu", "bvh_gpu.cu", "img_decode.cu"];
 const HOST_SOURCES: [&str; 3] = ["pt_host.cpp", "bvh_build.cpp", "scene_prep.cpp"];
-const LINK_LIBS: [&str; 2] = ["-lpthread", "-ldl"];      // -ldl: ptc_reduce binds the process's NCCL with dlopen / dlsym
+const LINK_LIBS: [&str; 3] = ["-lpthread", "-ldl", "-lz"];      // -ldl: NCCL (ptc_reduce) and nvJPEG (JPEG textures) are bound with dlopen / dlsym; -lz: the PNG decoder inflates with zlib
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
@@ -27,7 +27,7 @@ fn main() {
         objs.push(obj);
         println!("cargo:rerun-if-changed={}", csrc.join(src).display());
     }
-    for hdr in ["pt_device.cuh", "pt_kernels.cuh", "bvh_build.h", "bvh_gpu.h", "lbvh.cuh", "scene_prep.h", "pt_error.h"] {
+    for hdr in ["img_decode.h", "pt_device.cuh", "pt_kernels.cuh", "bvh_build.h", "bvh_gpu.h", "lbvh.cuh", "scene_prep.h", "pt_error.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(hdr).display());
     }
     let lib = out.join("libptcore.so");

@@ -115,6 +115,9 @@ extern "C" {
     pub fn ptc_scene_num_textures(scene: *const ptc_scene) -> u64;
     pub fn ptc_scene_texture_info_at(scene: *const ptc_scene, index: u64, out: *mut ptc_scene_texture_info) -> c_int;
     pub fn ptc_scene_set_texels(scene: *mut ptc_scene, index: u64, width: u32, height: u32, format: u32, texels: *const c_void) -> c_int;
+    pub fn ptc_scene_decode_textures(scene: *mut ptc_scene, cuda_device: c_int, n_threads: c_int) -> c_int;
+    pub fn ptc_decode_image(data: *const c_void, bytes: usize, cuda_device: c_int, width: *mut u32, height: *mut u32, format: *mut u32, texels: *mut *mut c_void) -> c_int;
+    pub fn ptc_free(p: *mut c_void);
     pub fn ptc_scene_get_view(scene: *const ptc_scene, out: *mut ptc_scene_view) -> c_int;
     pub fn ptc_scene_free(scene: *mut ptc_scene);
 }

@@ -1,0 +1,313 @@
+"""Texture decode inside the library (ptc_scene_decode_textures / ptc_decode_image; reference: Texture::load,
+src/texture.rs:232-243, run on 32 threads by Scene::load_obj, src/scene.rs:239-254).
+
+PNG and PFM are decoded on the host: checked bit for bit against OpenCV / Pillow on every colour type and bit depth, on
+Adam7 streams written by an independent encoder in this file, and on damaged files.  JPEG goes through nvJPEG on the GPU
+(`-m gpu`): the reference's real Sponza JPGs (tests/golden/ref_res, baseline and progressive) against OpenCV's libjpeg
+within the tolerance two conforming IDCTs may differ by, then a textured OBJ rendered by the compiled host (ptrender)."""
+import ctypes as C
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+RES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_res")
+
+
+def lib_decode(ptc, data, device=0):
+    L = ptc._lib.lib()
+    w, h, fmt, px = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_void_p()
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    rc = L.ptc_decode_image(buf, len(data), device, C.byref(w), C.byref(h), C.byref(fmt), C.byref(px))
+    if rc != 0:
+        return rc, L.ptc_last_error().decode()
+    n = w.value * h.value
+    dt, k = (np.uint8, 4) if fmt.value == ptc.types.TEXEL_RGBA8 else (np.float32, 16)
+    arr = np.frombuffer(C.string_at(px, n * k), dtype=dt).reshape(h.value, w.value, 4).copy()
+    L.ptc_free(px)
+    return 0, arr
+
+
+def png_bytes(ihdr, rows_of_pass, extra_chunks=()):
+    """A PNG written from scratch: rows_of_pass = list (one entry, or the seven Adam7 passes) of lists of raw row bytes."""
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body) & 0xFFFFFFFF)
+    raw = b"".join(b"\x00" + r for rows in rows_of_pass for r in rows)
+    z = zlib.compress(raw, 6)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr)
+    for t, body in extra_chunks:
+        out += chunk(t, body)
+    half = len(z) // 2
+    return out + chunk(b"IDAT", z[:half]) + chunk(b"IDAT", z[half:]) + chunk(b"IEND", b"")      # two IDAT chunks: they must be concatenated
+
+
+def expected_rgba(im):
+    """decode_image's convention (wgpu-pathtracer_b200/scene.py) for an array in RGB(A) / grey order"""
+    if im.ndim == 2:
+        im = np.repeat(im[:, :, None], 3, axis=2)
+    if im.shape[2] == 3:
+        one = 255 if im.dtype == np.uint8 else 65535
+        im = np.concatenate([im, np.full(im.shape[:2] + (1,), one, dtype=im.dtype)], axis=2)
+    if im.dtype == np.uint16:
+        im = im.astype(np.float32) / np.float32(65535.0)
+    return im
+
+
+@pytest.mark.parametrize("kind", ["grey8", "rgb8", "rgba8", "grey16", "rgb16", "rgba16"])
+def test_png_matches_opencv(ptc, tmp_path, kind):
+    import cv2
+    rng = np.random.default_rng(7)
+    H, W = 37, 53                                             # odd sizes: every filter meets a short last pixel
+    dt = np.uint16 if kind.endswith("16") else np.uint8
+    ch = {"grey": 0, "rgb": 3, "rgba": 4}[kind.rstrip("0123456789")]
+    shape = (H, W) if ch == 0 else (H, W, ch)
+    # smooth gradients + noise so that the encoder picks all five filter types
+    base = (np.add.outer(np.arange(H), np.arange(W)) * (np.iinfo(dt).max // (H + W))).astype(np.int64)
+    im = (base if ch == 0 else base[:, :, None] + np.arange(ch) * 1000) + rng.integers(0, 40, shape)
+    im = np.clip(im, 0, np.iinfo(dt).max).astype(dt)
+    path = str(tmp_path / f"{kind}.png")
+    assert cv2.imwrite(path, im if ch < 3 else im[:, :, [2, 1, 0] + ([3] if ch == 4 else [])])
+    rc, got = lib_decode(ptc, open(path, "rb").read())
+    assert rc == 0, got
+    want = expected_rgba(im)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_png_palette_low_bit_depths_and_transparency(ptc, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    H, W = 19, 45
+    # palette with per-entry alpha (tRNS)
+    idx = rng.integers(0, 13, (H, W)).astype(np.uint8)
+    pal = rng.integers(0, 256, (13, 3)).astype(np.uint8)
+    alpha = rng.integers(0, 256, 9).astype(np.uint8)                    # shorter than the palette: the rest is opaque
+    for depth in (8, 4):
+        if depth == 8:
+            rows = [bytes(r) for r in idx]
+        else:
+            rows = [bytes(((np.pad(r, (0, W % 2))[0::2] << 4) | np.pad(r, (0, W % 2))[1::2]).astype(np.uint8)) for r in idx]
+        data = png_bytes(struct.pack(">IIBBBBB", W, H, depth, 3, 0, 0, 0), [rows], [(b"PLTE", pal.tobytes()), (b"tRNS", alpha.tobytes())])
+        rc, got = lib_decode(ptc, data)
+        assert rc == 0, got
+        want = np.concatenate([pal[idx], np.where(idx < 9, alpha[np.minimum(idx, 8)], 255)[:, :, None].astype(np.uint8)], axis=2)
+        assert np.array_equal(got, want)
+        p = tmp_path / f"pal{depth}.png"; p.write_bytes(data)
+        assert np.array_equal(np.asarray(Image.open(p).convert("RGBA")), want)           # the hand-written file is a valid PNG
+    # 1 / 2 / 4-bit grey: scaled to 8 bits
+    for depth in (1, 2, 4):
+        g = rng.integers(0, 1 << depth, (H, W)).astype(np.uint8)
+        per = 8 // depth
+        rows = []
+        for r in g:
+            r = np.pad(r, (0, (-W) % per)).reshape(-1, per)
+            rows.append(bytes(sum((r[:, k].astype(np.uint32) << (8 - depth * (k + 1))) for k in range(per)).astype(np.uint8)))
+        rc, got = lib_decode(ptc, png_bytes(struct.pack(">IIBBBBB", W, H, depth, 0, 0, 0, 0), [rows]))
+        assert rc == 0, got
+        v = (g.astype(np.uint32) * 255 // ((1 << depth) - 1)).astype(np.uint8)
+        assert np.array_equal(got[..., 0], v) and np.array_equal(got[..., 1], v) and (got[..., 3] == 255).all()
+    # grey + alpha, and a transparent colour key on RGB
+    ga = rng.integers(0, 256, (H, W, 2)).astype(np.uint8)
+    rc, got = lib_decode(ptc, png_bytes(struct.pack(">IIBBBBB", W, H, 8, 4, 0, 0, 0), [[bytes(r.reshape(-1)) for r in ga]]))
+    assert rc == 0 and np.array_equal(got[..., 0], ga[..., 0]) and np.array_equal(got[..., 2], ga[..., 0]) and np.array_equal(got[..., 3], ga[..., 1])
+    rgb = rng.integers(0, 4, (H, W, 3)).astype(np.uint8)
+    key = rgb[5, 7]
+    data = png_bytes(struct.pack(">IIBBBBB", W, H, 8, 2, 0, 0, 0), [[bytes(r.reshape(-1)) for r in rgb]], [(b"tRNS", struct.pack(">HHH", *map(int, key)))])
+    rc, got = lib_decode(ptc, data)
+    assert rc == 0 and np.array_equal(got[..., :3], rgb)
+    assert np.array_equal(got[..., 3] == 0, (rgb == key).all(axis=2)) and got[5, 7, 3] == 0
+
+
+@pytest.mark.parametrize("size", [(1, 1), (3, 2), (8, 8), (29, 17)])
+def test_png_adam7(ptc, size):
+    W, H = size
+    rng = np.random.default_rng(W * 100 + H)
+    im = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    X0, Y0, DX, DY = (0, 4, 0, 2, 0, 1, 0), (0, 0, 4, 0, 2, 0, 1), (8, 8, 4, 4, 2, 2, 1), (8, 8, 8, 4, 4, 2, 2)
+    passes = []
+    for k in range(7):
+        sub = im[Y0[k]::DY[k], X0[k]::DX[k]]
+        passes.append([bytes(r.reshape(-1)) for r in sub] if sub.size else [])
+    rc, got = lib_decode(ptc, png_bytes(struct.pack(">IIBBBBB", W, H, 8, 2, 0, 0, 1), passes))
+    assert rc == 0, got
+    assert np.array_equal(got[..., :3], im) and (got[..., 3] == 255).all()
+
+
+def test_png_all_filter_types_by_hand(ptc):
+    """rows filtered with each of the five types by an encoder written here (Sub, Up, Average, Paeth arithmetic mod 256)"""
+    rng = np.random.default_rng(11)
+    H, W, bpp = 10, 21, 4
+    im = rng.integers(0, 256, (H, W, 4)).astype(np.uint8)
+    flat = im.reshape(H, -1).astype(np.int32)
+    raw = b""
+    for y in range(H):
+        cur, up = flat[y], (flat[y - 1] if y else np.zeros_like(flat[0]))
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        ul = np.concatenate([np.zeros(bpp, np.int32), up[:-bpp]])
+        t = y % 5
+        if t == 0: f = cur
+        elif t == 1: f = cur - left
+        elif t == 2: f = cur - up
+        elif t == 3: f = cur - ((left + up) >> 1)
+        else:
+            p = left + up - ul
+            pa, pb, pc = abs(p - left), abs(p - up), abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+            f = cur - pred
+        raw += bytes([t]) + bytes((f % 256).astype(np.uint8))
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body) & 0xFFFFFFFF)
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    rc, got = lib_decode(ptc, data)
+    assert rc == 0 and np.array_equal(got, im)
+
+
+def test_damaged_files_are_errors_not_crashes(ptc):
+    im = np.arange(5 * 4 * 3, dtype=np.uint8).reshape(5, 4, 3)
+    good = png_bytes(struct.pack(">IIBBBBB", 4, 5, 8, 2, 0, 0, 0), [[bytes(r.reshape(-1)) for r in im]])
+    assert lib_decode(ptc, good)[0] == 0
+    for bad, why in [(good[:40], "truncated"), (good[:30] + bytes([good[30] ^ 1]) + good[31:], "CRC"), (b"GIF89a" + good[6:], "unknown image format"),
+                     (good.replace(b"IDAT", b"iDAT"), "CRC")]:
+        rc, msg = lib_decode(ptc, bad)
+        assert rc != 0 and why.lower() in msg.lower(), (why, msg)
+    # image data that inflates to the wrong size
+    short = png_bytes(struct.pack(">IIBBBBB", 4, 6, 8, 2, 0, 0, 0), [[bytes(r.reshape(-1)) for r in im]])
+    rc, msg = lib_decode(ptc, short)
+    assert rc != 0 and "expected size" in msg
+
+
+def test_pfm(ptc):
+    rng = np.random.default_rng(5)
+    im = rng.random((6, 9, 3)).astype(np.float32) * 4
+    for endian, scale in (("<", b"-1.0"), (">", b"1.0")):
+        data = b"PF\n9 6\n" + scale + b"\n" + im[::-1].astype(endian + "f4").tobytes()
+        rc, got = lib_decode(ptc, data)
+        assert rc == 0 and got.dtype == np.float32 and np.array_equal(got[..., :3], im) and (got[..., 3] == 1).all()
+    grey = rng.random((4, 3)).astype(np.float32)
+    rc, got = lib_decode(ptc, b"Pf\n3 4\n-1.0\n" + grey[::-1].tobytes())
+    assert rc == 0 and np.array_equal(got[..., 0], grey) and np.array_equal(got[..., 2], grey)
+
+
+OBJ = """mtllib m.mtl
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+usemtl a
+f 1/1 2/2 3/3
+usemtl b
+f 1/1 3/3 4/4
+"""
+
+
+def test_scene_decode_equals_the_python_decoder(ptc, tmp_path):
+    """load_obj(decode="library") — PNG files named by an MTL, decoded on the library's threads — gives the same scene,
+    texel for texel, as the OpenCV path; a missing file is reported by name and the other textures stay decoded"""
+    import cv2
+    rng = np.random.default_rng(1)
+    names = []
+    for i, (dt, ch) in enumerate([(np.uint8, 3), (np.uint8, 4), (np.uint16, 3), (np.uint8, 0)]):
+        shape = (16 + i, 24 - i) if ch == 0 else (16 + i, 24 - i, ch)
+        im = rng.integers(0, np.iinfo(dt).max, shape).astype(dt)
+        names.append(f"t{i}.png"); assert cv2.imwrite(str(tmp_path / names[-1]), im)
+    (tmp_path / "m.mtl").write_text(f"newmtl a\nKd 1 1 1\nmap_Kd {names[0]}\nmap_Bump {names[1]}\nnewmtl b\nmap_Kd {names[2]}\nmap_Ks {names[3]}\n")
+    (tmp_path / "s.obj").write_text(OBJ)
+    env = np.ones((1, 1, 4), np.float32)
+    a = ptc.Scene(env).load_obj(path=str(tmp_path / "s.obj"), decode="library", decode_threads=3)
+    b = ptc.Scene(env).load_obj(path=str(tmp_path / "s.obj"))
+    assert len(a.textures) == len(b.textures) > 10
+    nfile = 0
+    for ta, tb in zip(a.textures, b.textures):
+        assert ta.texels.dtype == tb.texels.dtype and np.array_equal(ta.texels, tb.texels)
+        nfile += ta.path is not None
+    assert nfile == 4 and np.array_equal(a.materials, b.materials)
+    os.remove(tmp_path / names[2])
+    with pytest.raises(ptc.PtcError, match=names[2]):
+        ptc.Scene(env).load_obj(path=str(tmp_path / "s.obj"), decode="library")
+
+
+def test_jpeg_without_a_gpu_fails_loudly(ptc):
+    """JPEG is decoded by nvJPEG on the GPU: on a box without one the call says so (there is no CPU fallback to hide behind)"""
+    if ptc._lib.lib().ptc_device_count() > 0:
+        pytest.skip("GPU present")
+    data = open(os.path.join(RES, "sponza", "KAMEN.JPG"), "rb").read()
+    rc, msg = lib_decode(ptc, data)
+    assert rc != 0 and ("CUDA device" in msg or "nvjpeg" in msg.lower())
+
+
+def sponza_jpgs():
+    d = os.path.join(RES, "sponza")
+    return sorted(f for f in os.listdir(d) if f.lower().endswith(".jpg"))
+
+
+@pytest.mark.gpu
+def test_jpeg_nvjpeg_matches_libjpeg_on_the_reference_textures(ptc):
+    """every Sponza JPG of the reference (baseline and progressive, grey and colour): same size, and texels within what two
+    conforming decoders may differ by (IDCT and YCbCr rounding): |diff| <= 4 everywhere, mean |diff| <= 0.5 LSB"""
+    import cv2
+    files = sponza_jpgs()
+    assert len(files) >= 18
+    progressive = 0
+    for f in files:
+        data = open(os.path.join(RES, "sponza", f), "rb").read()
+        progressive += b"\xff\xc2" in data[:4096]
+        rc, got = lib_decode(ptc, data)
+        assert rc == 0, (f, got)
+        ref = cv2.imread(os.path.join(RES, "sponza", f), cv2.IMREAD_UNCHANGED)
+        ref = np.repeat(ref[:, :, None], 3, axis=2) if ref.ndim == 2 else ref[:, :, ::-1]
+        assert got.dtype == np.uint8 and got.shape[:2] == ref.shape[:2] and (got[..., 3] == 255).all(), f
+        diff = np.abs(got[..., :3].astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 4 and diff.mean() <= 0.5, (f, int(diff.max()), float(diff.mean()))
+    assert progressive >= 5
+
+
+@pytest.mark.gpu
+def test_ptrender_loads_a_textured_obj(ptc, standins, tmp_path):
+    """the compiled host renders an OBJ whose MTL is the reference's real sponza.mtl (JPG textures decoded by the library) and
+    gets, bit for bit, the image the Python mirror renders from the same library-decoded textures"""
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "wgpu-pathtracer_b200", "csrc")
+    subprocess.check_call(["make", "-s", "-C", csrc, "ptrender"], stdout=subprocess.DEVNULL)
+    d = tmp_path / "sponza"
+    shutil.copytree(os.path.join(RES, "sponza"), d)
+    mats = [l.split()[1] for l in open(d / "sponza.mtl") if l.startswith("newmtl")]
+    # a wall of quads, one per material, facing the camera
+    lines = ["mtllib sponza.mtl"]
+    n = len(mats)
+    for i in range(n):
+        x0, x1 = i * 1.0, i * 1.0 + 1.0
+        lines += [f"v 4 0 {x0}", f"v 4 0 {x1}", f"v 4 2 {x1}", f"v 4 2 {x0}"]
+    lines += ["vt 0 0", "vt 3 0", "vt 3 3", "vt 0 3", "vn -1 0 0"]
+    for i, m in enumerate(mats):
+        b = i * 4
+        lines += [f"usemtl {m}", f"f {b + 1}/1/1 {b + 2}/2/1 {b + 3}/3/1", f"f {b + 1}/1/1 {b + 3}/3/1 {b + 4}/4/1"]
+    (d / "wall.obj").write_text("\n".join(lines) + "\n")
+    env = standins.make_envmap(64, 32)
+    pfm = b"PF\n64 32\n-1.0\n" + env.texels[::-1, :, :3].astype("<f4").tobytes()
+    (tmp_path / "sky.pfm").write_bytes(pfm)
+    W, H, frames = 256, 96, 2
+    pos, look = (-6.0, 1.0, n / 2), (4.0, 1.0, n / 2)
+    r = subprocess.run([os.path.join(csrc, "ptrender"), "--obj", str(d / "wall.obj"), "--env", str(tmp_path / "sky.pfm"), "--size", f"{W}x{H}",
+                        "--frames", str(frames), "--pos", *map(str, pos), "--look", *map(str, look), "--fov", "90", "--out", str(tmp_path / "cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "texture file(s) decoded" in r.stdout
+    got = np.fromfile(tmp_path / "cpp.rgba32f", np.float32).reshape(H, W, 4)
+    scene = ptc.Scene(ptc.Texture(env.texels[:, :, :].astype(np.float32)))
+    scene.load_obj(path=str(d / "wall.obj"), decode="library")
+    assert sum(t.path is not None for t in scene.textures) >= 18
+    camera = standins.make_camera({"position": pos, "fov": 90.0, "target": look}, W, H)
+    step = ptc.RTStep.create(scene, ptc.make_config(W, H))
+    for f in range(1, frames + 1):
+        step.update(camera.uniforms(frame=f)); step.render()
+    ref = step.read(ptc.types.PLANE_COLOR)
+    step.destroy()
+    assert np.array_equal(got, ref)
+    assert len(np.unique(np.round(got[..., :3], 3).reshape(-1, 3), axis=0)) > 500          # textured, not flat

@@ -77,6 +77,9 @@ def lib():
         "ptc_scene_num_textures": (u64, [vp]),
         "ptc_scene_texture_info_at": (i32, [vp, u64, P(T.SceneTextureInfo)]),
         "ptc_scene_set_texels": (i32, [vp, u64, u32, u32, u32, vp]),
+        "ptc_scene_decode_textures": (i32, [vp, i32, i32]),
+        "ptc_decode_image": (i32, [vp, C.c_size_t, i32, P(u32), P(u32), P(u32), P(vp)]),
+        "ptc_free": (None, [vp]),
         "ptc_scene_get_view": (i32, [vp, P(T.SceneView)]),
         "ptc_scene_free": (None, [vp]),
     }

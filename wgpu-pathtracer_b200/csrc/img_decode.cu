@@ -1,0 +1,273 @@
+// img_decode.cu — see img_decode.h.  Host code (compiled by nvcc only for the CUDA runtime and nvjpeg.h declarations).
+#include "img_decode.h"
+#include "../../include/ptcore_types.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h>
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace ptc {
+
+ImageKind sniff_image(const uint8_t* d, size_t n) {
+    static const uint8_t png_sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (n >= 8 && std::memcmp(d, png_sig, 8) == 0) return IMG_PNG;
+    if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return IMG_JPEG;
+    if (n >= 3 && d[0] == 'P' && (d[1] == 'F' || d[1] == 'f') && (d[2] == '\n' || d[2] == ' ' || d[2] == '\r')) return IMG_PFM;
+    return IMG_UNKNOWN;
+}
+
+// ---- PNG (ISO/IEC 15948) -----------------------------------------------------------------------------------------
+namespace {
+
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+inline int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// reverses the row filters of one (sub-)image in place: `raw` holds h rows of (1 filter byte + rowbytes)
+bool unfilter(uint8_t* raw, uint32_t h, size_t rowbytes, uint32_t bpp) {
+    const size_t stride = rowbytes + 1;
+    for (uint32_t y = 0; y < h; ++y) {
+        uint8_t* row = raw + (size_t)y * stride + 1;
+        const uint8_t* up = y ? raw + (size_t)(y - 1) * stride + 1 : nullptr;
+        switch (raw[(size_t)y * stride]) {
+            case 0: break;
+            case 1: for (size_t i = bpp; i < rowbytes; ++i) row[i] = (uint8_t)(row[i] + row[i - bpp]); break;
+            case 2: if (up) for (size_t i = 0; i < rowbytes; ++i) row[i] = (uint8_t)(row[i] + up[i]); break;
+            case 3: for (size_t i = 0; i < rowbytes; ++i) row[i] = (uint8_t)(row[i] + (((i >= bpp ? row[i - bpp] : 0) + (up ? up[i] : 0)) >> 1)); break;
+            case 4: for (size_t i = 0; i < rowbytes; ++i) row[i] = (uint8_t)(row[i] + paeth(i >= bpp ? row[i - bpp] : 0, up ? up[i] : 0, (up && i >= bpp) ? up[i - bpp] : 0)); break;
+            default: return false;
+        }
+    }
+    return true;
+}
+
+struct PngInfo { uint32_t w, h, depth, ctype, channels; bool interlace; };
+
+// sample k (0-based, in units of `depth` bits) of a row
+inline uint32_t sample_at(const uint8_t* row, uint32_t depth, size_t k) {
+    switch (depth) {
+        case 8: return row[k];
+        case 16: return ((uint32_t)row[k * 2] << 8) | row[k * 2 + 1];
+        case 4: return (row[k >> 1] >> ((1 - (k & 1)) * 4)) & 15u;
+        case 2: return (row[k >> 2] >> ((3 - (k & 3)) * 2)) & 3u;
+        default: return (row[k >> 3] >> (7 - (k & 7))) & 1u;
+    }
+}
+
+}  // namespace
+
+int decode_png(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    if (sniff_image(d, n) != IMG_PNG) { err = "not a PNG"; return 1; }
+    PngInfo I{}; bool have_ihdr = false, done = false;
+    std::vector<uint8_t> idat, plte, trns;
+    size_t p = 8;
+    while (!done && p + 12 <= n) {
+        const uint32_t len = be32(d + p);
+        const uint8_t* type = d + p + 4, *body = d + p + 8;
+        if ((size_t)len > n - p - 12) { err = "truncated PNG chunk"; return 1; }
+        if (crc32(crc32(0L, type, 4), body, len) != be32(body + len)) { err = "PNG chunk CRC mismatch"; return 1; }
+        if (!std::memcmp(type, "IHDR", 4)) {
+            if (len != 13) { err = "bad IHDR"; return 1; }
+            I.w = be32(body); I.h = be32(body + 4); I.depth = body[8]; I.ctype = body[9]; I.interlace = body[12] != 0;
+            if (body[10] != 0 || body[11] != 0 || body[12] > 1) { err = "unsupported PNG compression / filter / interlace method"; return 1; }
+            static const int ch_of[7] = {1, 0, 3, 1, 2, 0, 4};
+            if (I.ctype > 6 || ch_of[I.ctype] == 0) { err = "bad PNG colour type"; return 1; }
+            I.channels = (uint32_t)ch_of[I.ctype];
+            const bool depth_ok = I.ctype == 0 ? (I.depth == 1 || I.depth == 2 || I.depth == 4 || I.depth == 8 || I.depth == 16)
+                                : I.ctype == 3 ? (I.depth == 1 || I.depth == 2 || I.depth == 4 || I.depth == 8) : (I.depth == 8 || I.depth == 16);
+            if (!depth_ok || I.w == 0 || I.h == 0 || (uint64_t)I.w * I.h > (1ull << 30)) { err = "bad PNG dimensions or bit depth"; return 1; }
+            have_ihdr = true;
+        } else if (!std::memcmp(type, "PLTE", 4)) plte.assign(body, body + len);
+        else if (!std::memcmp(type, "tRNS", 4)) trns.assign(body, body + len);
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+        else if (!std::memcmp(type, "IEND", 4)) done = true;
+        p += 12 + (size_t)len;
+    }
+    if (!done) { err = "truncated PNG (no IEND chunk)"; return 1; }
+    if (!have_ihdr || idat.empty()) { err = "PNG without IHDR / IDAT"; return 1; }
+    if (I.ctype == 3 && plte.size() < 3) { err = "palette PNG without PLTE"; return 1; }
+
+    const uint32_t bits_px = I.depth * I.channels, bpp = bits_px >= 8 ? bits_px / 8 : 1;
+    auto rowbytes_of = [&](uint32_t w) { return ((size_t)w * bits_px + 7) / 8; };
+    // the (sub-)images of the stream: one, or the seven Adam7 passes
+    struct Pass { uint32_t x0, y0, dx, dy, w, h; size_t offset; };
+    std::vector<Pass> passes;
+    size_t raw_bytes = 0;
+    if (!I.interlace) { passes.push_back({0, 0, 1, 1, I.w, I.h, 0}); raw_bytes = (size_t)I.h * (rowbytes_of(I.w) + 1); }
+    else {
+        static const uint32_t X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1}, DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int k = 0; k < 7; ++k) {
+            const uint32_t w = I.w > X0[k] ? (I.w - X0[k] + DX[k] - 1) / DX[k] : 0, h = I.h > Y0[k] ? (I.h - Y0[k] + DY[k] - 1) / DY[k] : 0;
+            if (w == 0 || h == 0) continue;
+            passes.push_back({X0[k], Y0[k], DX[k], DY[k], w, h, raw_bytes});
+            raw_bytes += (size_t)h * (rowbytes_of(w) + 1);
+        }
+    }
+    std::vector<uint8_t> raw(raw_bytes);
+    {
+        z_stream zs; std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit(&zs) != Z_OK) { err = "zlib inflateInit failed"; return 1; }
+        zs.next_in = idat.data(); zs.avail_in = (uInt)idat.size();
+        zs.next_out = raw.data(); zs.avail_out = (uInt)raw.size();
+        if (idat.size() > 0xFFFFFFFFull || raw.size() > 0xFFFFFFFFull) { inflateEnd(&zs); err = "PNG too large"; return 1; }
+        const int rc = inflate(&zs, Z_FINISH);
+        const bool full = zs.avail_out == 0;
+        inflateEnd(&zs);
+        if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || !full) { err = "PNG image data does not inflate to the expected size"; return 1; }
+    }
+    const bool wide = I.depth == 16;
+    out.width = I.w; out.height = I.h; out.format = wide ? PTC_TEXEL_RGBA32F : PTC_TEXEL_RGBA8;
+    out.texels.assign((size_t)I.w * I.h * (wide ? 16 : 4), 0);
+    const uint32_t maxv = (1u << I.depth) - 1u;
+    // a single transparent colour (tRNS of grey / rgb images): samples compared at the file's bit depth
+    uint32_t key[3] = {0, 0, 0}; bool have_key = false;
+    if (I.ctype == 0 && trns.size() >= 2) { key[0] = ((uint32_t)trns[0] << 8) | trns[1]; have_key = true; }
+    if (I.ctype == 2 && trns.size() >= 6) { for (int k = 0; k < 3; ++k) key[k] = ((uint32_t)trns[k * 2] << 8) | trns[k * 2 + 1]; have_key = true; }
+    for (const Pass& P : passes) {
+        const size_t rb = rowbytes_of(P.w);
+        if (!unfilter(raw.data() + P.offset, P.h, rb, bpp)) { err = "bad PNG filter type"; return 1; }
+        for (uint32_t y = 0; y < P.h; ++y) {
+            const uint8_t* row = raw.data() + P.offset + (size_t)y * (rb + 1) + 1;
+            for (uint32_t x = 0; x < P.w; ++x) {
+                uint32_t c[4] = {0, 0, 0, maxv};
+                switch (I.ctype) {
+                    case 0: c[0] = c[1] = c[2] = sample_at(row, I.depth, x); if (have_key && c[0] == key[0]) c[3] = 0; break;
+                    case 2: for (int k = 0; k < 3; ++k) c[k] = sample_at(row, I.depth, (size_t)x * 3 + k);
+                            if (have_key && c[0] == key[0] && c[1] == key[1] && c[2] == key[2]) c[3] = 0; break;
+                    case 3: { const uint32_t idx = sample_at(row, I.depth, x);
+                              if ((size_t)idx * 3 + 2 >= plte.size()) { err = "PNG palette index out of range"; return 1; }
+                              c[0] = plte[idx * 3]; c[1] = plte[idx * 3 + 1]; c[2] = plte[idx * 3 + 2]; c[3] = idx < trns.size() ? trns[idx] : 255u; break; }
+                    case 4: c[0] = c[1] = c[2] = sample_at(row, I.depth, (size_t)x * 2); c[3] = sample_at(row, I.depth, (size_t)x * 2 + 1); break;
+                    default: for (int k = 0; k < 4; ++k) c[k] = sample_at(row, I.depth, (size_t)x * 4 + k); break;
+                }
+                const size_t px = (size_t)(P.y0 + y * P.dy) * I.w + (P.x0 + x * P.dx);
+                if (wide) {
+                    float* o = reinterpret_cast<float*>(out.texels.data()) + px * 4;
+                    for (int k = 0; k < 4; ++k) o[k] = (float)c[k] / 65535.0f;
+                } else {
+                    uint8_t* o = out.texels.data() + px * 4;
+                    if (I.ctype == 3 || I.depth == 8) for (int k = 0; k < 4; ++k) o[k] = (uint8_t)c[k];
+                    else for (int k = 0; k < 4; ++k) o[k] = (uint8_t)((c[k] * 255u + maxv / 2u) / maxv);     // 1/2/4-bit grey scaled to 8 bits
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ---- PFM ("PF" = rgb, "Pf" = grey; rows bottom-up; negative scale = little endian) ---------------------------------------
+int decode_pfm(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    if (sniff_image(d, n) != IMG_PFM) { err = "not a PFM"; return 1; }
+    const int ch = d[1] == 'F' ? 3 : 1;
+    size_t p = 2; long vals[2] = {0, 0}; double scale = 0.0;
+    auto token = [&](std::string& t) { while (p < n && std::isspace(d[p])) ++p; t.clear(); while (p < n && !std::isspace(d[p])) t.push_back((char)d[p++]); return !t.empty(); };
+    std::string t;
+    for (int k = 0; k < 2; ++k) { if (!token(t)) { err = "bad PFM header"; return 1; } vals[k] = std::atol(t.c_str()); }
+    if (!token(t)) { err = "bad PFM header"; return 1; }
+    scale = std::atof(t.c_str());
+    ++p;                                              // the single whitespace byte after the scale
+    if (vals[0] <= 0 || vals[1] <= 0 || (uint64_t)vals[0] * (uint64_t)vals[1] > (1ull << 30) || scale == 0.0) { err = "bad PFM header"; return 1; }
+    const size_t W = (size_t)vals[0], H = (size_t)vals[1];
+    if (n < p || n - p < W * H * ch * 4) { err = "truncated PFM"; return 1; }
+    const bool little = scale < 0.0;
+    out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA32F;
+    out.texels.resize(W * H * 16);
+    float* o = reinterpret_cast<float*>(out.texels.data());
+    for (size_t y = 0; y < H; ++y)
+        for (size_t x = 0; x < W; ++x) {
+            float v[3] = {0, 0, 0};
+            for (int k = 0; k < ch; ++k) {
+                const uint8_t* s = d + p + (((H - 1 - y) * W + x) * ch + k) * 4;
+                uint32_t u = little ? ((uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24)) : be32(s);
+                std::memcpy(&v[k], &u, 4);
+            }
+            if (ch == 1) v[1] = v[2] = v[0];
+            float* q = o + (y * W + x) * 4; q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = 1.0f;
+        }
+    return 0;
+}
+
+// ---- JPEG through nvJPEG (bound at run time) ---------------------------------------------------------------------------
+namespace {
+struct NvjpegApi {
+    nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t*) = nullptr;
+    nvjpegStatus_t (*Destroy)(nvjpegHandle_t) = nullptr;
+    nvjpegStatus_t (*StateCreate)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+    nvjpegStatus_t (*StateDestroy)(nvjpegJpegState_t) = nullptr;
+    nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char*, size_t, int*, nvjpegChromaSubsampling_t*, int*, int*) = nullptr;
+    nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*, cudaStream_t) = nullptr;
+    bool ok = false; std::string why;
+};
+const NvjpegApi& nvjpeg_api() {
+    static NvjpegApi api; static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12", "/usr/local/cuda/targets/x86_64-linux/lib/libnvjpeg.so.12"})
+            if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
+        if (!h) { api.why = "libnvjpeg.so.12 not found (JPEG textures are decoded by nvJPEG)"; return; }
+        api.CreateSimple = (decltype(api.CreateSimple))dlsym(h, "nvjpegCreateSimple");
+        api.Destroy = (decltype(api.Destroy))dlsym(h, "nvjpegDestroy");
+        api.StateCreate = (decltype(api.StateCreate))dlsym(h, "nvjpegJpegStateCreate");
+        api.StateDestroy = (decltype(api.StateDestroy))dlsym(h, "nvjpegJpegStateDestroy");
+        api.GetImageInfo = (decltype(api.GetImageInfo))dlsym(h, "nvjpegGetImageInfo");
+        api.Decode = (decltype(api.Decode))dlsym(h, "nvjpegDecode");
+        api.ok = api.CreateSimple && api.Destroy && api.StateCreate && api.StateDestroy && api.GetImageInfo && api.Decode;
+        if (!api.ok) api.why = "libnvjpeg lacks an expected entry point";
+    });
+    return api;
+}
+}  // namespace
+
+JpegDecoder::JpegDecoder(int cuda_device) : device_(cuda_device) {
+    const NvjpegApi& A = nvjpeg_api();
+    if (!A.ok) { why_ = A.why; return; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); why_ = "no CUDA device: JPEG textures are decoded on the GPU (nvJPEG)"; return; }
+    if (cuda_device < 0 || cuda_device >= ndev || cudaSetDevice(cuda_device) != cudaSuccess) { why_ = "bad CUDA device for the JPEG decoder"; return; }
+    nvjpegHandle_t h = nullptr; nvjpegJpegState_t st = nullptr; cudaStream_t s = nullptr;
+    if (A.CreateSimple(&h) != NVJPEG_STATUS_SUCCESS) { why_ = "nvjpegCreateSimple failed"; return; }
+    if (A.StateCreate(h, &st) != NVJPEG_STATUS_SUCCESS) { A.Destroy(h); why_ = "nvjpegJpegStateCreate failed"; return; }
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { A.StateDestroy(st); A.Destroy(h); why_ = "stream creation failed"; return; }
+    handle_ = h; state_ = st; stream_ = s; ok_ = true;
+}
+JpegDecoder::~JpegDecoder() {
+    const NvjpegApi& A = nvjpeg_api();
+    if (ok_) { cudaSetDevice(device_); cudaFree(d_buf_); A.StateDestroy((nvjpegJpegState_t)state_); A.Destroy((nvjpegHandle_t)handle_); cudaStreamDestroy((cudaStream_t)stream_); }
+}
+int JpegDecoder::decode(const uint8_t* data, size_t n, DecodedImage& out, std::string& err) {
+    if (!ok_) { err = why_; return 1; }
+    const NvjpegApi& A = nvjpeg_api();
+    cudaSetDevice(device_);
+    int ncomp = 0, w[NVJPEG_MAX_COMPONENT] = {0}, h[NVJPEG_MAX_COMPONENT] = {0}; nvjpegChromaSubsampling_t sub;
+    if (A.GetImageInfo((nvjpegHandle_t)handle_, data, n, &ncomp, &sub, w, h) != NVJPEG_STATUS_SUCCESS || w[0] <= 0 || h[0] <= 0) { err = "nvjpegGetImageInfo failed (not a JPEG nvJPEG can read)"; return 1; }
+    const size_t W = (size_t)w[0], H = (size_t)h[0], bytes = W * H * 3;
+    if (d_bytes_ < bytes) {
+        cudaFree(d_buf_); d_buf_ = nullptr; d_bytes_ = 0;
+        if (cudaMalloc(&d_buf_, bytes) != cudaSuccess) { cudaGetLastError(); err = "JPEG decode: device allocation failed"; return 1; }
+        d_bytes_ = bytes;
+    }
+    nvjpegImage_t img; std::memset(&img, 0, sizeof(img));
+    img.channel[0] = d_buf_; img.pitch[0] = W * 3;
+    // interleaved RGB, grey images replicated, as image::open(..).to_rgba32f() sees them
+    const nvjpegStatus_t rc = A.Decode((nvjpegHandle_t)handle_, (nvjpegJpegState_t)state_, data, n, NVJPEG_OUTPUT_RGBI, &img, (cudaStream_t)stream_);
+    if (rc != NVJPEG_STATUS_SUCCESS) { err = "nvjpegDecode failed (status " + std::to_string((int)rc) + ")"; return 1; }
+    std::vector<uint8_t> rgb(bytes);
+    if (cudaMemcpyAsync(rgb.data(), d_buf_, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream_) != cudaSuccess || cudaStreamSynchronize((cudaStream_t)stream_) != cudaSuccess) {
+        err = std::string("JPEG decode: ") + cudaGetErrorString(cudaGetLastError()); return 1;
+    }
+    out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA8;
+    out.texels.resize(W * H * 4);
+    for (size_t i = 0; i < W * H; ++i) { out.texels[i * 4] = rgb[i * 3]; out.texels[i * 4 + 1] = rgb[i * 3 + 1]; out.texels[i * 4 + 2] = rgb[i * 3 + 2]; out.texels[i * 4 + 3] = 255; }
+    return 0;
+}
+
+}  // namespace ptc

@@ -8,6 +8,7 @@
 // the caller decodes and hands texels in with ptc_scene_set_texels.
 #include "../../include/ptcore.h"
 #include "pt_error.h"
+#include "img_decode.h"
 
 #include <algorithm>
 #include <atomic>
@@ -18,6 +19,8 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -693,6 +696,73 @@ PTC_API int ptc_scene_set_texels(ptc_scene* s, uint64_t i, uint32_t w, uint32_t 
     t.width = w; t.height = h; t.format = format;
     return PTC_OK;
 }
+
+// Texture::load for every file-backed texture that has no texels yet (texture.rs:232-243), on n_threads host threads as
+// Scene::load_obj does (scene.rs:239-254, chunks of 32 threads).  PNG and PFM are decoded on the host, JPEG by nvJPEG on
+// `cuda_device` (each worker owns its decoder: handle, state, stream, device buffer).
+static int read_file(const std::string& path, std::vector<uint8_t>& out) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return 1;
+    std::fseek(f, 0, SEEK_END); long n = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+    if (n < 0) { std::fclose(f); return 1; }
+    out.resize((size_t)n);
+    const size_t got = n ? std::fread(out.data(), 1, (size_t)n, f) : 0;
+    std::fclose(f);
+    return got == (size_t)n ? 0 : 1;
+}
+static int decode_bytes(const uint8_t* data, size_t n, int cuda_device, std::unique_ptr<ptc::JpegDecoder>& jpeg, ptc::DecodedImage& img, std::string& err) {
+    switch (ptc::sniff_image(data, n)) {
+        case ptc::IMG_PNG: return ptc::decode_png(data, n, img, err);
+        case ptc::IMG_PFM: return ptc::decode_pfm(data, n, img, err);
+        case ptc::IMG_JPEG:
+            if (!jpeg) jpeg.reset(new ptc::JpegDecoder(cuda_device));
+            return jpeg->decode(data, n, img, err);
+        default: err = "unknown image format (this library decodes PNG, JPEG and PFM)"; return 1;
+    }
+}
+PTC_API int ptc_scene_decode_textures(ptc_scene* s, int cuda_device, int n_threads) {
+    if (!s) { set_error("null scene"); return PTC_ERR_INVALID; }
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < s->textures.size(); ++i) if (s->textures[i].source == PTC_TEX_FILE && s->textures[i].texels.empty()) todo.push_back(i);
+    if (todo.empty()) return PTC_OK;
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    n_threads = std::max(1, std::min(n_threads, (int)todo.size()));
+    std::atomic<size_t> next{0};
+    std::mutex mu; std::string first_error;
+    auto worker = [&] {
+        std::unique_ptr<ptc::JpegDecoder> jpeg;
+        std::vector<uint8_t> bytes;
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= todo.size()) break;
+            SceneTexture& t = s->textures[todo[k]];
+            ptc::DecodedImage img; std::string err;
+            int rc = read_file(t.path, bytes);
+            if (rc) err = "cannot read the file";
+            else rc = decode_bytes(bytes.data(), bytes.size(), cuda_device, jpeg, img, err);
+            if (rc) { std::lock_guard<std::mutex> l(mu); if (first_error.empty()) first_error = "texture " + t.path + ": " + err; continue; }
+            t.texels.swap(img.texels); t.width = img.width; t.height = img.height; t.format = img.format;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
+    worker();
+    for (auto& x : th) x.join();
+    if (!first_error.empty()) { set_error(first_error); return PTC_ERR_INVALID; }
+    return PTC_OK;
+}
+
+PTC_API int ptc_decode_image(const void* data, size_t bytes, int cuda_device, uint32_t* width, uint32_t* height, uint32_t* format, void** texels) {
+    if (!data || !width || !height || !format || !texels) { set_error("null argument"); return PTC_ERR_INVALID; }
+    std::unique_ptr<ptc::JpegDecoder> jpeg; ptc::DecodedImage img; std::string err;
+    if (decode_bytes((const uint8_t*)data, bytes, cuda_device, jpeg, img, err)) { set_error(err); return PTC_ERR_INVALID; }
+    void* p = std::malloc(img.texels.size());
+    if (!p) { set_error("out of memory"); return PTC_ERR_OOM; }
+    std::memcpy(p, img.texels.data(), img.texels.size());
+    *width = img.width; *height = img.height; *format = img.format; *texels = p;
+    return PTC_OK;
+}
+PTC_API void ptc_free(void* p) { std::free(p); }
 
 PTC_API int ptc_scene_get_view(const ptc_scene* cs, ptc_scene_view* out) {
     ptc_scene* s = const_cast<ptc_scene*>(cs);

@@ -95,13 +95,15 @@ struct ptc_step {
     // Sponza / San Miguel, where ~24 of 32 lanes enter a child at the average node visit, 0.7-0.86x on classroom / dragon
     // (~20 lanes: triangles smaller than a tile).  The kernel counts exactly that; the step samples the counters with an
     // asynchronous read-back every kPacketSample frames and keeps packets on while the coherence stays above kPacketMinLanes,
-    // probing with one packet frame per sample period while they are off.  Either kernel produces the same hits.
+    // probing with one packet frame per sample period while they are off.  Either kernel produces the same hits.  A sample is
+    // applied exactly kPacketLag frames after it was taken (waiting for the copy if it ever were that late), so which kernel a
+    // frame uses depends on the frame sequence only, not on how fast the host thread runs.
     int packets_mode = -1;                         // PTC_PRIMARY_PACKETS: 0 never, 1 always, unset (-1) adaptive
     bool primary_packets = true;
     unsigned long long* h_packet_stats = nullptr;  // pinned: [0] node visits, [1] lane visits at the last sample
     unsigned long long packet_prev[2] = {0, 0};
     cudaEvent_t packet_ev = nullptr; bool packet_pending = false;
-    uint64_t packet_frame = 0;
+    uint64_t packet_frame = 0, packet_sample_frame = 0;
     int trace_impl = 0;                            // 0 = k_trace, 1 = k_trace_simple (PTC_TRACE_IMPL=simple, A/B timing only)
     uint64_t frames = 0, launches = 0;
     // optional per-stage timing (CUDA events on the render stream)
@@ -544,8 +546,9 @@ PTC_API int ptc_render(ptc_step* s) {
     // primary rays: packets or per-ray traversal, by the measured coherence (see ptc_step::packets_mode)
     bool use_packets = s->primary_packets && s->trace_impl != 1;
     if (s->packets_mode < 0 && s->trace_impl != 1) {
-        static const uint64_t kPacketSample = 32; static const double kPacketMinLanes = 21.5;
-        if (s->packet_pending && cudaEventQuery(s->packet_ev) == cudaSuccess) {
+        static const uint64_t kPacketSample = 32, kPacketLag = 4; static const double kPacketMinLanes = 21.5;
+        if (s->packet_pending && s->packet_frame >= s->packet_sample_frame + kPacketLag) {
+            CK(cudaEventSynchronize(s->packet_ev));                               // four frames old: long complete
             s->packet_pending = false;
             const unsigned long long dn = s->h_packet_stats[0] - s->packet_prev[0], dl = s->h_packet_stats[1] - s->packet_prev[1];
             s->packet_prev[0] = s->h_packet_stats[0]; s->packet_prev[1] = s->h_packet_stats[1];
@@ -602,7 +605,7 @@ PTC_API int ptc_render(ptc_step* s) {
         if (s->packet_frame % 32 == 0 && !s->packet_pending) {
             CK(cudaMemcpyAsync(s->h_packet_stats, s->d_total_rays + 1, 16, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaEventRecord(s->packet_ev, s->stream));
-            s->packet_pending = true;
+            s->packet_pending = true; s->packet_sample_frame = s->packet_frame;
         }
         s->packet_frame++;
     }

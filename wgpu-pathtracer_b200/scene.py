@@ -86,10 +86,11 @@ class Scene:
         self._keep = None
 
     # -- ingest ------------------------------------------------------------------------------------
-    def load_obj(self, path=None, obj_text=None, mtl_text=None, obj_dir="", fix_normals=False, decode=decode_image, decode_threads=0):
+    def load_obj(self, path=None, obj_text=None, mtl_text=None, obj_dir="", fix_normals=False, decode=decode_image, decode_threads=0, cuda_device=0):
         """``Scene::load_obj`` (scene.rs:124-257) through the C++ loader; appends to this scene.  Only valid on
         a scene that has not been modified since construction or a previous load_obj (the loader replays the
-        same texture/material numbering)."""
+        same texture/material numbering).  decode: a callable path -> Texture (default: OpenCV), or "library" =
+        ``ptc_scene_decode_textures`` (PNG / PFM on the library's host threads, JPEG by nvJPEG on ``cuda_device``)."""
         L = lib()
         h = C.c_void_p()
         check(L.ptc_scene_new(b"<envmap>", C.byref(h)))
@@ -115,7 +116,12 @@ class Scene:
                     texs.append(Texture(np.array(list(info.color), dtype=np.float32).reshape(1, 1, 4)))
             # decode the files on a pool of threads, as the reference does (32 loader threads per chunk, scene.rs:239-254);
             # OpenCV releases the GIL while decoding.  Results are stored by index, so the order of completion does not matter.
-            if len(files) > 1 and decode_threads != 1:
+            if decode == "library":
+                for i, t in enumerate(texs[:10]):                 # the environment map (slot 9) is this scene's, not a file of the loader's
+                    w, hh = t.size
+                    check(L.ptc_scene_set_texels(h, i, w, hh, t.format, t.texels.ctypes.data_as(C.c_void_p)))
+                check(L.ptc_scene_decode_textures(h, cuda_device, decode_threads))
+            elif len(files) > 1 and decode_threads != 1:
                 from concurrent.futures import ThreadPoolExecutor
                 with ThreadPoolExecutor(max_workers=min(decode_threads or 32, len(files))) as pool:
                     for (slot, _), tex in zip(files, pool.map(decode, [p for _, p in files])):
@@ -125,10 +131,20 @@ class Scene:
                     texs[slot] = decode(path)
             # give the loader texels so get_view succeeds
             for i, t in enumerate(texs):
+                if t is None:
+                    continue                      # decoded by the library
                 w, hh = t.size
                 check(L.ptc_scene_set_texels(h, i, w, hh, t.format, t.texels.ctypes.data_as(C.c_void_p)))
             v = T.SceneView()
             check(L.ptc_scene_get_view(h, C.byref(v)))
+            descs = C.cast(v.textures, C.POINTER(T.TextureDesc))
+            for slot, fpath in files:
+                if texs[slot] is None:
+                    d = descs[slot]
+                    px = d.width * d.height
+                    raw = C.string_at(d.texels, px * (4 if d.format == T.TEXEL_RGBA8 else 16))
+                    arr = np.frombuffer(raw, dtype=np.uint8 if d.format == T.TEXEL_RGBA8 else np.float32).reshape(d.height, d.width, 4).copy()
+                    texs[slot] = Texture(arr, path=fpath)
             self.vertices = np.frombuffer(C.string_at(v.vertices, v.num_vertices * 48), dtype=T.VERTEX_DT).copy()
             self.indices = np.frombuffer(C.string_at(v.indices, v.num_indices * 4), dtype=np.uint32).copy()
             self.meshes = np.frombuffer(C.string_at(v.meshes, v.num_meshes * 20), dtype=T.MESH_DT).copy()
