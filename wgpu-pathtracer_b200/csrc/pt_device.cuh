@@ -196,7 +196,7 @@ struct HitRec { float t, b1, b2; uint32_t tri; };   // tri = global triangle id,
 struct RaySlab {
     float ax, ay, az;             // A per axis
     float nx, fx, ny, fy, nz, fz; // C for the entry (near) / exit (far) plane of each axis
-    uint32_t sx, sy, sz;          // decode selector of the entry plane; the exit plane's is sel ^ PT_SEL_FLIP
+    uint32_t sx, sy, sz;          // decode selector: entry plane in the low half, exit plane in the high half (PRMT form: sel ^ PT_SEL_FLIP)
 };
 #if defined(PTC_SLAB_PRMT)
 #define PT_SEL_LO 0x7104u          // PRMT bytes {0x00, w.b0, w.b1, 0x3F}: the low 16 bits of the word -> float bits 0x3F000000 + (h << 8)
@@ -205,9 +205,10 @@ struct RaySlab {
 #define PT_SEL_POOL 0x3F000000u
 #define PT_SLAB_SCALE 1.0f         // F = 1 + q / 32768
 #else
-#define PT_SEL_LO 0x00000080u      // dp2a.lo multipliers (b0, b1) = (128, 0): the low 16 bits of the word
-#define PT_SEL_HI 0x00008000u      // (0, 128): the high 16 bits
-#define PT_SEL_FLIP 0x00008080u
+// one selector word serves both planes of an axis: dp2a.lo reads its multipliers from bytes 0-1 (the entry plane's), dp2a.hi
+// from bytes 2-3 (the exit plane's) — no per-step flip of the selector
+#define PT_SEL_LO 0x80000080u      // entry plane = low 16 bits of the word (b0, b1) = (128, 0); exit plane = high 16 bits (b2, b3) = (0, 128)
+#define PT_SEL_HI 0x00808000u      // entry plane = high 16 bits (0, 128); exit plane = low 16 bits (128, 0)
 #define PT_SEL_BIAS 0x3F400000u    // + (0x8000 | q) * 128 = 0x3F800000 + (q << 7)
 #define PT_SLAB_SCALE 2.0f         // F = 1 + q / 65536
 #endif
@@ -218,6 +219,14 @@ PT_HD uint32_t pt_dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
     return __dp2a_lo(a, b, c);
 #else
     return c + (a & 0xFFFFu) * (b & 0xFFu) + (a >> 16) * ((b >> 8) & 0xFFu);
+#endif
+}
+// dp2a.hi.u32.u32: c + a.h0 * b.b2 + a.h1 * b.b3
+PT_HD uint32_t pt_dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_hi(a, b, c);
+#else
+    return c + (a & 0xFFFFu) * ((b >> 16) & 0xFFu) + (a >> 16) * ((b >> 24) & 0xFFu);
 #endif
 }
 
@@ -271,7 +280,7 @@ PT_HD void slab_pair(uint32_t w, uint32_t sel, float a, float cn, float cf, floa
 #if defined(PTC_SLAB_PRMT)
     const uint32_t n = pt_prmt(w, PT_SEL_POOL, sel), f = pt_prmt(w, PT_SEL_POOL, sel ^ PT_SEL_FLIP);
 #else
-    const uint32_t n = pt_dp2a_lo(w, sel, PT_SEL_BIAS), f = pt_dp2a_lo(w, sel ^ PT_SEL_FLIP, PT_SEL_BIAS);
+    const uint32_t n = pt_dp2a_lo(w, sel, PT_SEL_BIAS), f = pt_dp2a_hi(w, sel, PT_SEL_BIAS);
 #endif
 #if defined(__CUDA_ARCH__) && defined(PTC_FFMA2)
     const float2 t = __ffma2_rn(make_float2(u2f(n), u2f(f)), make_float2(a, a), make_float2(cn, cf));   // two IEEE fmas, one instruction
