@@ -610,6 +610,27 @@ def test_cpp_harness_matches_python_mirror(ptc, standins, tmp_path):
     step.destroy()
 
 
+def test_non_finite_throughput_is_carried_like_the_oracle(ptc, standins, oracle):
+    """The accumulated-colour queue entry is only written when it is not all zero bits (k_shade).  Without light sampling that
+    happens when the throughput overflows: an albedo of 1e30 makes `mask` inf after two bounces and `acc += 0 * mask` NaN.  The
+    kernels must carry exactly that: every plane equal to the oracle's, NaNs and infinities included."""
+    T = ptc.types
+    env = standins.make_envmap(64, 32)
+    sc = ptc.Scene(env)
+    sc.load_obj(obj_text=standins._obj_text([("room", "huge", standins.box((-1, -1, -1), (1, 1, 1))),
+                                             ("slab", "plain", standins.grid((-0.5, -0.2, -0.5), (1, 0, 0), (0, 0, 1), 2, 2))]),
+                mtl_text="newmtl huge\nKd 1 1 1\nPr 0.8\nmap_Kd huge.f32tex\n\nnewmtl plain\nKd 0.7 0.6 0.5\nPr 0.6\n", obj_dir="standin",
+                decode=lambda path: ptc.Texture(np.full((2, 2, 4), 1e30, np.float32), path=path))
+    cam = {"position": (0.0, 0.3, 0.0), "fov": 70.0, "target": (1.0, 0.0, 0.2)}
+    step, ref = render_both(ptc, standins, oracle, sc, cam, 160, 96, 2, max_bounces=5)
+    got = {"color": step.read(T.PLANE_COLOR), "albedo": step.read(T.PLANE_ALBEDO), "depth": step.read(T.PLANE_DEPTH), "normal": step.read(T.PLANE_NORMAL)}
+    step.destroy()
+    for k in got:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), f"{k} plane differs"
+    rgb = ref["color"][..., :3]
+    assert np.isnan(rgb).any() and np.isfinite(rgb).any()          # the fixture does produce non-finite radiance next to ordinary pixels
+
+
 @pytest.mark.parametrize("build", [0, 1, 2])
 def test_degenerate_and_tied_geometry_gpu(ptc, standins, oracle, build):
     """Coincident duplicates (equal t: smaller triangle id wins), zero-area and sliver triangles, coplanar overlaps and a
