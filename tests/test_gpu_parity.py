@@ -169,7 +169,8 @@ def test_ray_count_matches_oracle(ptc, standins, oracle):
     step.poll(True)
     s = step.stats()
     assert s["rays_traced"] == rays
-    assert s["frames_rendered"] == 3 and s["kernel_launches"] == 3 * s["frame_parts"] * (1 + 2 * 5)
+    # per frame and part: raygen, (trace + shade) x (MAX_BOUNCES + 1), and the dense sky pass of the escaped paths
+    assert s["frames_rendered"] == 3 and s["kernel_launches"] == 3 * s["frame_parts"] * (1 + 2 * 5 + 1)
 
 
 @pytest.mark.parametrize("nee", [0.0, 0.5])
@@ -401,7 +402,7 @@ def test_light_sampling_mis_bit_exact(ptc, standins, oracle, which):
     check_all_planes(ptc, step, ref)
     s = step.stats()
     assert s["rays_traced"] == rays
-    assert s["kernel_launches"] == 3 * s["frame_parts"] * (1 + 2 * 6 + 5)            # one any-hit launch per bounce that can take a light sample
+    assert s["kernel_launches"] == 3 * s["frame_parts"] * (1 + 2 * 6 + 5 + 1)        # one any-hit launch per bounce that can take a light sample; the sky pass
     step.destroy()
 
 

@@ -589,7 +589,10 @@ PT_HD pt_v3 emissive_at(const DevScene& s, uint32_t tri, float w0, float w1, flo
     return pt_mk3(c.x, c.y, c.z);
 }
 
-template <bool MIS>
+// DEFER_SKY (kernels only): a path that escaped is returned as SURF_MISS WITHOUT its environment lookup — k_shade queues it and
+// k_sky evaluates sky_radiance for all of a frame's escaped paths in one dense pass (the lookup ran with the 2-5 lanes of a warp
+// that missed while the others waited: ~1/5 of k_shade's issue slots on the later segments).
+template <bool MIS, bool DEFER_SKY = false>
 PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_o, pt_v3 ray_d, uint32_t rng_in, const HitRec& hit, uint32_t bounce) {
     SurfaceOut out;
     out.first_t = 0.0f; out.first_normal = pt_mk3(0.0f, 0.0f, 0.0f); out.first_albedo = pt_mk3(0.0f, 0.0f, 0.0f);
@@ -605,6 +608,7 @@ PT_HD SurfaceOut shade_surface(const DevScene& s, const PathCfg& cfg, pt_v3 ray_
     const MatDev* mp = s.mats;
     uint32_t todo;
     if (miss) {                                                            // :229-232
+        if (DEFER_SKY) { out.kind = SURF_MISS; out.light = pt_mk3(0.0f, 0.0f, 0.0f); return out; }
         sky_uv(ray_d, u, v);
         todo = 1u << SLOT_SKY;
     } else {

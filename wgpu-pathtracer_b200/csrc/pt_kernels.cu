@@ -464,9 +464,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_any(DevScene s, const F
 // MIS (PTC_LIGHTS_MIS, a separate instantiation so the reference path keeps its register budget): the hit also takes a
 // light sample; its shadow ray is queued (second ballot compaction) for k_trace<true>, which adds the carried radiance to
 // this path's slot of the next queue before the next shade reads it.  mask.w carries p_b of the scattered direction.
-template <bool FIRST, bool MIS>
+// DEFER: escaped paths are not finished here but compacted into the frame's sky queue (third ballot), for k_sky.
+template <bool FIRST, bool MIS, bool DEFER>
 __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(DevScene s, PathCfg cfg, Queue qin, Queue qout, const U4* __restrict__ hits,
-                                                          FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh) {
+                                                          FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh, SkyQueue sky) {
     const uint32_t n = fc->count[segment];
     uint32_t* next_count = &fc->count[segment + 1];
     const uint32_t lane = threadIdx.x & 31;
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             }
         }
 #endif
-        bool alive = false;
+        bool alive = false, escaped = false;
         uint32_t pixel = 0, rng = 0;
         pt_v3 no = pt_mk3(0.0f, 0.0f, 0.0f), nd = no, mask = pt_mk3(1.0f, 1.0f, 1.0f), acc = no;
         bool nee = false; pt_v3 nee_d = no, nee_c = no; float nee_tmax = 0.0f, pdf_next = -1.0f;
@@ -493,7 +494,8 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 const uint4 hr = __ldcs(reinterpret_cast<const uint4*>(hits) + i);
                 pixel = __float_as_uint(o.w);
                 HitRec h; h.t = __uint_as_float(hr.x); h.b1 = __uint_as_float(hr.y); h.b2 = __uint_as_float(hr.z); h.tri = hr.w;
-                so = shade_surface<MIS>(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
+                so = shade_surface<MIS, DEFER>(s, cfg, pt_mk3(o.x, o.y, o.z), pt_mk3(d.x, d.y, d.z), __float_as_uint(d.w), h, FIRST ? 0u : segment);
+                if (DEFER && so.kind == SURF_MISS) { escaped = true; so.next_d = pt_mk3(d.x, d.y, d.z); }
                 if (FIRST) {                                          // pathtracer/pathtracer.wgsl:270-273
                     planes.depth[pixel] = so.first_t;
                     reinterpret_cast<float4*>(planes.normal)[pixel] = make_float4(so.first_normal.x, so.first_normal.y, so.first_normal.z, 1.0f);
@@ -514,9 +516,9 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
             }
             if (MIS) { nee = so.nee; nee_d = so.nee_d; nee_tmax = so.nee_tmax; nee_c = pt_mul(so.nee_c, mask); pdf_next = so.pdf_next; }
             pt_v3 radiance;
-            alive = combine_path(so, mask, acc, radiance, pdf_prev);
+            alive = !escaped && combine_path(so, mask, acc, radiance, pdf_prev);
             no = so.next_o; nd = so.next_d; rng = so.rng;
-            if (!alive) {
+            if (!alive && !escaped) {
                 if (cfg.spp > 1u) {
                     // SAMPLES_PER_PIXEL > 1 (pathtracer/pathtracer.wgsl:258-266): the samples of a pixel run one after the other
                     // on one RNG stream; their sum lives in spp_sum, the stream's state in spp_rng, and the last sample hands
@@ -548,6 +550,21 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 if (MIS) pixel = slot;                                    // the shadow entry names the path by its slot
             }
         }
+        if (DEFER) {
+            const uint32_t eb = __ballot_sync(0xffffffffu, escaped);
+            if (eb) {
+                uint32_t k0 = 0;
+                if (lane == 0) k0 = atomicAdd(&fc->sky_count, (uint32_t)__popc(eb));
+                k0 = __shfl_sync(0xffffffffu, k0, 0);
+                if (escaped) {
+                    const uint32_t k = k0 + __popc(eb & ((1u << lane) - 1u));
+                    const bool acc_set = (f2u(acc.x) | f2u(acc.y) | f2u(acc.z)) != 0u;
+                    st4_stream(sky.dir + k, nd.x, nd.y, nd.z, __uint_as_float(pixel));
+                    st4_stream(sky.mask + k, mask.x, mask.y, mask.z, acc_set ? 1.0f : 0.0f);
+                    if (acc_set) st4_stream(sky.acc + k, acc.x, acc.y, acc.z, 0.0f);
+                }
+            }
+        }
         if (MIS) {
             const uint32_t sb = __ballot_sync(0xffffffffu, alive && nee);
             if (sb) {
@@ -577,16 +594,37 @@ void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue 
     else if (impl == 4) k_trace_pp<PTC_TRACE_MIN_BLOCKS><<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
     else k_trace_simple<<<grid, kTraceThreads, 0, st>>>(s, q.ray_o, q.ray_d, hits, &fc->count[segment], &fc->trace_cursor[segment], total_rays);
 }
-void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
-                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh) {
-    const bool mis = cfg.light_sampling == PTC_LIGHTS_MIS && s.num_real_lights != 0;
-    if (!mis) {
-        if (segment == 0) k_shade<true, false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
-        else k_shade<false, false><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
-    } else {
-        if (segment == 0) k_shade<true, true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
-        else k_shade<false, true><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh);
+// ---- sky: the environment lookup of every path of the frame that escaped, one dense pass (see shade_surface DEFER_SKY) ----
+__global__ void __launch_bounds__(128) k_sky(DevScene s, PathCfg cfg, SkyQueue sky, const uint32_t* __restrict__ count_ptr, Planes planes) {
+    const uint32_t n = *count_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const F4 d = ld4_stream(sky.dir + i), m = ld4_stream(sky.mask + i);
+        pt_v3 acc = pt_mk3(0.0f, 0.0f, 0.0f);
+        if (m.w != 0.0f) { const F4 a = ld4_stream(sky.acc + i); acc = pt_mk3(a.x, a.y, a.z); }
+        const pt_v3 light = sky_radiance(s, pt_mk3(d.x, d.y, d.z));
+        const pt_v3 radiance = pt_add(acc, pt_mul(light, pt_mk3(m.x, m.y, m.z)));          // combine_path, SURF_MISS
+        accumulate_pixel(planes.color + __float_as_uint(d.w), radiance, cfg.accum_mode, cfg.is_grabbed);
     }
+}
+
+template <bool MIS, bool DEFER>
+static void launch_shade_t(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
+                           FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh, SkyQueue sky) {
+    if (segment == 0) k_shade<true, MIS, DEFER><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh, sky);
+    else k_shade<false, MIS, DEFER><<<grid, kShadeThreads, 0, st>>>(s, cfg, qin, qout, hits, fc, segment, planes, sh, sky);
+}
+void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
+                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh, SkyQueue sky) {
+    const bool mis = cfg.light_sampling == PTC_LIGHTS_MIS && s.num_real_lights != 0;
+    const bool defer = sky.dir != nullptr;
+    if (!mis) { if (defer) launch_shade_t<false, true>(st, grid, s, cfg, qin, qout, hits, fc, segment, planes, sh, sky);
+                else launch_shade_t<false, false>(st, grid, s, cfg, qin, qout, hits, fc, segment, planes, sh, sky); }
+    else { if (defer) launch_shade_t<true, true>(st, grid, s, cfg, qin, qout, hits, fc, segment, planes, sh, sky);
+           else launch_shade_t<true, false>(st, grid, s, cfg, qin, qout, hits, fc, segment, planes, sh, sky); }
+}
+void launch_sky(cudaStream_t st, int device, const DevScene& s, const PathCfg& cfg, SkyQueue sky, FrameCounters* fc, Planes planes) {
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    k_sky<<<(sms > 0 ? sms : 1) * 8, 128, 0, st>>>(s, cfg, sky, &fc->sky_count, planes);
 }
 void launch_trace_shadow(cudaStream_t st, int grid, const DevScene& s, ShadowQueue sh, F4* acc_next, FrameCounters* fc, uint32_t segment,
                          unsigned long long* total_rays) {
@@ -734,6 +772,6 @@ int trace_grid_size(int device, int impl) {
                   : impl == 4 ? (const void*)k_trace_pp<PTC_TRACE_MIN_BLOCKS> : (const void*)k_trace_simple;
     return persistent_grid(k, kTraceThreads, device);
 }
-int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false, false>, kShadeThreads, device); }
+int shade_grid_size(int device) { return persistent_grid((const void*)k_shade<false, false, true>, kShadeThreads, device); }
 
 }  // namespace ptc

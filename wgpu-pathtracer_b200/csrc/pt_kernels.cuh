@@ -23,6 +23,13 @@ struct FrameCounters {
     uint32_t shade_cursor[PTC_MAX_SEGMENTS];
     uint32_t shadow_count[PTC_MAX_SEGMENTS];   // PTC_LIGHTS_MIS: shadow rays queued by shade(b)
     uint32_t shadow_cursor[PTC_MAX_SEGMENTS];
+    uint32_t sky_count;                        // escaped paths queued for k_sky by this frame's shade launches
+};
+
+struct SkyQueue {         // escaped paths of one frame awaiting their environment lookup (at most one per pixel)
+    F4* dir;              // direction.xyz, pixel index (bits)
+    F4* mask;             // color_mask.rgb, 1 if `acc` was written (it is all zero bits otherwise)
+    F4* acc;              // accumulated_color.rgb
 };
 
 struct ShadowQueue {      // PTC_LIGHTS_MIS: one entry per light sample awaiting its visibility test
@@ -53,8 +60,11 @@ void launch_raygen(cudaStream_t st, const ptc_uniforms& un, Queue q, FrameCounte
 // impl 3 = packet traversal (primary rays in tile order); packet_stats (optional): [0] += node visits, [1] += lanes entering a child
 void launch_trace(cudaStream_t st, int grid, int impl, const DevScene& s, Queue q, U4* hits, FrameCounters* fc, uint32_t segment,
                   unsigned long long* total_rays, unsigned long long* packet_stats = nullptr);
+// sky.dir == nullptr: escaped paths are finished inside k_shade; else they are queued and launch_sky finishes them
 void launch_shade(cudaStream_t st, int grid, const DevScene& s, const PathCfg& cfg, Queue qin, Queue qout, const U4* hits,
-                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh);
+                  FrameCounters* fc, uint32_t segment, Planes planes, ShadowQueue sh, SkyQueue sky);
+// the frame's escaped paths: sky lookup (sky.wgsl:1-12), radiance = acc + sky * mask, accumulation (pathtracer.wgsl:32-42)
+void launch_sky(cudaStream_t st, int device, const DevScene& s, const PathCfg& cfg, SkyQueue sky, FrameCounters* fc, Planes planes);
 // PTC_LIGHTS_MIS: any-hit traversal of the shadow rays shade(segment) queued; unoccluded ones add into acc_next
 void launch_trace_shadow(cudaStream_t st, int grid, const DevScene& s, ShadowQueue sh, F4* acc_next, FrameCounters* fc, uint32_t segment,
                          unsigned long long* total_rays);

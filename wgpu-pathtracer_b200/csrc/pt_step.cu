@@ -56,6 +56,7 @@ struct ptc_step {
         cudaEvent_t done = nullptr, primary_done = nullptr, primary_free = nullptr;
         Queue q[2]{}; U4* d_hits = nullptr; ShadowQueue shq{};
         Queue qp{}; U4* d_hits_p = nullptr;
+        SkyQueue sky{};                            // escaped paths of the frame in flight (deferred environment lookup, k_sky)
         uint32_t n = 0;                            // queue slots (= pixels) of this part
     };
     bool overlap = true;
@@ -89,6 +90,7 @@ struct ptc_step {
     bool invalid = false;                          // a failed ptc_resize left the step without frame buffers
     cudaEvent_t ev_display_free = nullptr; bool display_busy = false;   // a read_async snapshot of DISPLAY is pending on the ordering stream
     bool blit_by_parts = true;                     // PTC_BLIT_PARTS=0: always tonemap on the ordering stream (A/B timing)
+    bool defer_sky = true;                         // PTC_DEFER_SKY=0: escaped paths are finished inside k_shade (A/B timing)
     uint32_t npix = 0;
     int trace_grid = 0, shade_grid = 0;
     // Primary rays: packet traversal (k_trace_packet) pays off when the 32 rays of a tile stay together — 1.3-1.45x on
@@ -210,6 +212,7 @@ static void free_frame_buffers(ptc_step* s) {
         cudaFree(P.d_hits); P.d_hits = nullptr;
         cudaFree(P.qp.ray_o); cudaFree(P.qp.ray_d); P.qp = Queue{}; cudaFree(P.d_hits_p); P.d_hits_p = nullptr;
         cudaFree(P.shq.ray_o); cudaFree(P.shq.ray_d); cudaFree(P.shq.contrib); P.shq = ShadowQueue{};
+        cudaFree(P.sky.dir); cudaFree(P.sky.mask); cudaFree(P.sky.acc); P.sky = SkyQueue{};
         P.n = 0;
     }
     cudaFree(s->owned_color); s->owned_color = nullptr;
@@ -232,6 +235,9 @@ static int alloc_part(ptc_step* s, ptc_step::FramePart& P, uint32_t n) {
     CK(cudaMalloc(&P.qp.ray_o, m * 16)); CK(cudaMalloc(&P.qp.ray_d, m * 16)); CK(cudaMalloc(&P.d_hits_p, m * 16));
     if (s->cfg.light_sampling == PTC_LIGHTS_MIS) {
         CK(cudaMalloc(&P.shq.ray_o, m * 16)); CK(cudaMalloc(&P.shq.ray_d, m * 16)); CK(cudaMalloc(&P.shq.contrib, m * 16));
+    }
+    if (s->defer_sky && s->cfg.samples_per_pixel == 1) {      // every pixel's path escapes at most once per frame
+        CK(cudaMalloc(&P.sky.dir, m * 16)); CK(cudaMalloc(&P.sky.mask, m * 16)); CK(cudaMalloc(&P.sky.acc, m * 16));
     }
     return PTC_OK;
 }
@@ -489,6 +495,7 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
         }
         { const char* e = getenv("PTC_OVERLAP"); s->overlap = !(e && std::strcmp(e, "0") == 0); }
         { const char* e = getenv("PTC_BLIT_PARTS"); s->blit_by_parts = !(e && std::strcmp(e, "0") == 0); }
+        { const char* e = getenv("PTC_DEFER_SKY"); s->defer_sky = !(e && std::strcmp(e, "0") == 0); }
         if (!parts_ok) { set_error("stream/event creation failed"); rc = PTC_ERR_CUDA; break; }
         if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming) != cudaSuccess ||
@@ -591,12 +598,14 @@ PTC_API int ptc_render(ptc_step* s) {
             for (uint32_t seg = 0; seg <= s->cfg.max_bounces; ++seg) {
                 if (seg) { prof_mark(s, 1); launch_trace(st, s->trace_grid, s->trace_impl, s->scene, P.q[seg & 1], P.d_hits, fc, seg, s->d_total_rays); s->launches++; }
                 prof_mark(s, 2);
-                launch_shade(st, s->shade_grid, s->scene, pc, seg ? P.q[seg & 1] : P.qp, P.q[(seg + 1) & 1], seg ? P.d_hits : P.d_hits_p, fc, seg, s->planes, P.shq);
+                launch_shade(st, s->shade_grid, s->scene, pc, seg ? P.q[seg & 1] : P.qp, P.q[(seg + 1) & 1], seg ? P.d_hits : P.d_hits_p, fc, seg, s->planes, P.shq, P.sky);
                 if (seg == 0 && prefetch) CK(cudaEventRecord(P.primary_free, st));
                 s->launches++;
                 // PTC_LIGHTS_MIS: the shadow rays shade(b) queued are traced (any-hit) before shade(b+1) reads the accumulated colours
                 if (mis && seg < s->cfg.max_bounces) { prof_mark(s, 1); launch_trace_shadow(st, s->trace_grid, s->scene, P.shq, P.q[(seg + 1) & 1].acc, fc, seg, s->d_total_rays); s->launches++; }
             }
+            // the frame's escaped paths: one dense environment pass (counted with the shade stage)
+            if (P.sky.dir) { prof_mark(s, 2); launch_sky(st, s->device, s->scene, pc, P.sky, fc, s->planes); s->launches++; }
         }
         if (!s->profiling) { CK(cudaEventRecord(P.done, st)); CK(cudaStreamWaitEvent(s->stream, P.done, 0)); }
     }
