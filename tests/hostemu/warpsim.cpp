@@ -340,3 +340,119 @@ int emu_packet_trace(const void* scene, const float* rays, uint64_t n, uint32_t*
     }
     return 0;
 }
+
+// ---- model of a CTA-level triangle pool (development aid) ----------------------------------------------------------------
+// G warps share one queue of (ray slot, triangle) requests.  A lane that reaches a leaf pushes one request per triangle and
+// keeps descending (its closest hit may shrink late: a few more nodes); it blocks only when it would exceed `cap` requests in
+// flight.  Any warp runs a TRIANGLE PASS (32 requests of any lane of the CTA, one triangle each, all lanes busy) when the queue
+// holds a full batch, or a partial one when none of its own lanes can take a node step; otherwise it runs a node step.
+// Counts warp iterations per kind so that sum(iterations x instructions) can be compared with emu_warpsim's.
+struct PoolParams { uint32_t warps_per_cta, ctas, cap, refill_vote, node_min, _pad[3]; };
+struct PoolOut { uint64_t it_refill, it_tri, it_node, ln_tri, ln_node, node_visits, tri_tests, rays, mismatches, it_decide, blocked_lane_steps, _pad; };
+
+extern "C" __attribute__((visibility("default")))
+int emu_warpsim_pool(const void* scene, const float* rays, uint64_t n, const PoolParams* P, PoolOut* out) {
+    const DevScene& s = *emu_dev_scene(scene);
+    std::memset(out, 0, sizeof(*out));
+    const uint32_t G = P->warps_per_cta ? P->warps_per_cta : 4, NC = P->ctas ? P->ctas : 16, NW = G * NC;
+    struct PLane : Lane { uint32_t inflight = 0; };
+    struct Req { uint32_t lane; uint32_t tri; };
+    std::vector<PLane> lanes((size_t)NW * 32);
+    std::vector<std::vector<Req>> queue(NC);
+    std::vector<size_t> qhead(NC, 0);
+    std::vector<uint8_t> exhausted(NW, 0), finished(NW, 0);
+    std::vector<HitRec> res(n);
+    uint64_t cursor = 0; uint32_t live = NW;
+    auto tri_one = [&](PLane& X, uint32_t ti) {
+        const F4* tp = s.tris + (size_t)ti * 4;
+        F4 a, b; ld8(tp, a, b); const F4 c = ld4(tp + 2);
+        float t, b1, b2;
+        if (pt_ray_tri(X.o, X.d, pt_mk3(a.x, a.y, a.z), pt_mk3(b.x, b.y, b.z), pt_mk3(c.x, c.y, c.z), PT_RAY_TMIN, PT_RAY_TMAX, &t, &b1, &b2)) {
+            const uint32_t id = f2u(a.w);
+            if (t < X.best.t || (t == X.best.t && id < X.best.tri)) { X.best.t = t; X.best.b1 = b1; X.best.b2 = b2; X.best.tri = id; }
+        }
+    };
+    while (live) {
+        for (uint32_t w = 0; w < NW; ++w) {
+            if (finished[w]) continue;
+            const uint32_t cta = w / G;
+            PLane* L = &lanes[(size_t)w * 32];
+            uint32_t nidle = 0, can_node = 0, blocked = 0;
+            for (int l = 0; l < 32; ++l) {
+                const bool done = L[l].node == PTC_SENTINEL && L[l].inflight == 0;
+                if (done) nidle++;
+                else if ((uint32_t)L[l].node < (uint32_t)PTC_SENTINEL || L[l].node < 0) {
+                    // at a leaf: can proceed only if its requests fit
+                    if (L[l].node < 0) { const uint32_t cnt = ((~(uint32_t)L[l].node) & 7u) + 1u; if (L[l].inflight + cnt <= P->cap) can_node++; else blocked++; }
+                    else can_node++;
+                } else blocked++;             // traversal finished, results outstanding
+            }
+            out->it_decide++;
+            const size_t qn = queue[cta].size() - qhead[cta];
+            if (nidle == 32 || (!exhausted[w] && nidle >= P->refill_vote)) {
+                out->it_refill++;
+                for (int l = 0; l < 32; ++l) if (L[l].node == PTC_SENTINEL && L[l].inflight == 0 && L[l].ray != 0xFFFFFFFFu) { res[L[l].ray] = L[l].best; L[l].ray = 0xFFFFFFFFu; }
+                if (!exhausted[w]) {
+                    for (int l = 0; l < 32; ++l) if (L[l].node == PTC_SENTINEL && L[l].inflight == 0 && L[l].ray == 0xFFFFFFFFu) {
+                        const uint64_t i = cursor++;
+                        if (i >= n) { exhausted[w] = 1; continue; }
+                        PLane& X = L[l];
+                        X.ray = (uint32_t)i;
+                        X.o = pt_mk3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]); X.d = pt_mk3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]);
+                        X.r = make_ray_slab(s, X.o, X.d);
+                        X.best.t = PT_RAY_TMAX; X.best.b1 = X.best.b2 = 0.0f; X.best.tri = 0xFFFFFFFFu;
+                        X.stack[0] = PTC_SENTINEL; X.sp = 1; X.inflight = 0;
+                        if (s.num_nodes != 0 && ray_is_finite(X.o, X.d)) X.node = 0;
+                        out->rays++;
+                    }
+                    if (cursor >= n) exhausted[w] = 1;
+                }
+                bool any = false;
+                for (int l = 0; l < 32; ++l) any |= L[l].ray != 0xFFFFFFFFu;
+                if (!any) {
+                    // a finished warp may still be needed to drain the CTA's queue
+                    bool cta_busy = qn != 0;
+                    if (!cta_busy) { finished[w] = 1; --live; }
+                    else goto tri_pass;
+                }
+                continue;
+            }
+            if (qn >= 32 || (can_node < P->node_min && qn > 0)) {
+            tri_pass:
+                const size_t qn2 = queue[cta].size() - qhead[cta];
+                const size_t take = qn2 < 32 ? qn2 : 32;
+                if (take == 0) continue;
+                out->it_tri++; out->ln_tri += take;
+                for (size_t k = 0; k < take; ++k) {
+                    const Req r = queue[cta][qhead[cta]++];
+                    PLane& X = lanes[r.lane];
+                    tri_one(X, r.tri); X.inflight--; out->tri_tests++;
+                }
+                if (qhead[cta] > 4096 && qhead[cta] * 2 > queue[cta].size()) { queue[cta].erase(queue[cta].begin(), queue[cta].begin() + (long)qhead[cta]); qhead[cta] = 0; }
+                continue;
+            }
+            if (can_node == 0) { out->blocked_lane_steps += blocked; continue; }    // nothing to do: waits for another warp's triangle pass
+            out->it_node++;
+            for (int l = 0; l < 32; ++l) {
+                PLane& X = L[l];
+                if (X.node < 0) {
+                    // a leaf reached in an earlier step: push its triangles now if they fit, then go on
+                    const uint32_t enc = ~(uint32_t)X.node, first = enc >> 3, cnt = (enc & 7u) + 1u;
+                    if (X.inflight + cnt > P->cap) continue;
+                    for (uint32_t k = 0; k < cnt; ++k) queue[cta].push_back(Req{(uint32_t)(w * 32 + l), first + k});
+                    X.inflight += cnt;
+                    X.node = X.stack[--X.sp];
+                    out->ln_node++;
+                    continue;
+                }
+                if ((uint32_t)X.node < (uint32_t)PTC_SENTINEL) { node_step(s, X); out->node_visits++; out->ln_node++; }
+            }
+            out->blocked_lane_steps += blocked;
+        }
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        HitRec h = trace_closest_bvh2(s, pt_mk3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]), pt_mk3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]), nullptr);
+        if (h.tri != res[i].tri || std::memcmp(&h.t, &res[i].t, 4) != 0) out->mismatches++;
+    }
+    return 0;
+}
