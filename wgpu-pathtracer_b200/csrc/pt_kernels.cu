@@ -472,8 +472,69 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
     uint32_t* next_count = &fc->count[segment + 1];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t base = warp * 32u; base < n; base += nwarps * 32u) {
-        const uint32_t i = base + lane;
+    // Experiment (-DPTC_SHADE_COMPACT, off): a batch of 32 queue slots is first CLASSIFIED by its hit records.  Escaped paths
+    // leave at once for the sky queue (12-37 % of the rays of a later Sponza segment); the slots that hit something collect in a
+    // small per-warp ring in shared memory and are shaded 32 at a time, so the ~900 instructions of the surface code run with
+    // (almost) every lane busy.  Same image (51 GPU tests), but SLOWER on every workload — shade +7 % Sponza, +14 % classroom and
+    // San Miguel (profiles/r02y_ab_compact.log), also at 72 / 80 registers without spills: k_shade waits for its gather chain, not
+    // for issue slots, and a dense batch only puts more of that chain on one warp.
+#ifdef PTC_SHADE_COMPACT
+    constexpr bool COMPACT = DEFER;
+#else
+    constexpr bool COMPACT = false;
+#endif
+    __shared__ uint32_t pend[COMPACT ? kShadeThreads / 32 : 1][COMPACT ? 64 : 1];
+    uint32_t head = 0, npend = 0;                                  // warp-uniform: ring position and fill
+    for (uint32_t base = warp * 32u;; base += nwarps * 32u) {
+        const bool more = base < n;                                // warp-uniform
+        uint32_t i = base + lane;
+        bool work = more && i < n;
+        if (!COMPACT) { if (!more) break; }
+        else {
+            uint32_t* ring = pend[(threadIdx.x >> 5) % (kShadeThreads / 32)];
+            if (more) {
+                uint32_t tri = 0u;
+                if (work) tri = __ldcs(reinterpret_cast<const uint32_t*>(hits + i) + 3);
+                const bool miss = work && tri == 0xFFFFFFFFu, hit = work && !miss;
+                const uint32_t eb = __ballot_sync(0xffffffffu, miss);
+                if (eb) {
+                    uint32_t k0 = 0;
+                    if (lane == 0) k0 = atomicAdd(&fc->sky_count, (uint32_t)__popc(eb));
+                    k0 = __shfl_sync(0xffffffffu, k0, 0);
+                    if (miss) {
+                        const uint32_t k = k0 + __popc(eb & ((1u << lane) - 1u));
+                        const F4 o = ld4_stream(qin.ray_o + i), d = ld4_stream(qin.ray_d + i);
+                        const uint32_t px = __float_as_uint(o.w);
+                        F4 m = {1.0f, 1.0f, 1.0f, 0.0f};
+                        if (!FIRST) m = ld4_stream(qin.mask + i);
+                        st4_stream(sky.dir + k, d.x, d.y, d.z, o.w);
+                        if (!FIRST && (MIS || m.w != 0.0f)) {
+                            const F4 a = ld4_stream(qin.acc + i);
+                            const bool acc_set = (f2u(a.x) | f2u(a.y) | f2u(a.z)) != 0u;
+                            st4_stream(sky.mask + k, m.x, m.y, m.z, acc_set ? 1.0f : 0.0f);
+                            if (acc_set) st4_stream(sky.acc + k, a.x, a.y, a.z, 0.0f);
+                        } else st4_stream(sky.mask + k, m.x, m.y, m.z, 0.0f);
+                        if (FIRST) {                                  // pathtracer/pathtracer.wgsl:270-273 for a primary ray that escaped
+                            planes.depth[px] = 0.0f;
+                            reinterpret_cast<float4*>(planes.normal)[px] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                            reinterpret_cast<float4*>(planes.albedo)[px] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                            planes.hit_tri[px] = 0xFFFFFFFFu;
+                        }
+                    }
+                }
+                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                if (hit) ring[(head + npend + __popc(hb & ((1u << lane) - 1u))) & 63u] = i;
+                npend += (uint32_t)__popc(hb);
+                __syncwarp();
+            }
+            if (npend >= 32u || (!more && npend != 0u)) {
+                const uint32_t take = npend < 32u ? npend : 32u;
+                work = lane < take;
+                i = ring[(head + lane) & 63u];
+                head = (head + take) & 63u; npend -= take;
+                __syncwarp();
+            } else { if (!more) break; continue; }
+        }
 #ifdef PTC_SHADE_PREFETCH
         {   // the next batch's queue entries on their way from HBM to L2 while this batch is shaded (A/B)
             const uint32_t j = i + nwarps * 32u;
@@ -487,7 +548,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
         uint32_t pixel = 0, rng = 0;
         pt_v3 no = pt_mk3(0.0f, 0.0f, 0.0f), nd = no, mask = pt_mk3(1.0f, 1.0f, 1.0f), acc = no;
         bool nee = false; pt_v3 nee_d = no, nee_c = no; float nee_tmax = 0.0f, pdf_next = -1.0f;
-        if (i < n) {
+        if (work) {
             SurfaceOut so;
             {
                 const F4 o = ld4_stream(qin.ray_o + i), d = ld4_stream(qin.ray_d + i);
@@ -550,7 +611,7 @@ __global__ void __launch_bounds__(kShadeThreads, PTC_SHADE_MIN_BLOCKS) k_shade(D
                 if (MIS) pixel = slot;                                    // the shadow entry names the path by its slot
             }
         }
-        if (DEFER) {
+        if (DEFER && !COMPACT) {
             const uint32_t eb = __ballot_sync(0xffffffffu, escaped);
             if (eb) {
                 uint32_t k0 = 0;
