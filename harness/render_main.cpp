@@ -3,10 +3,10 @@
 // from 1 (raytracer.rs:180), step.update, step.render — and a dump of what the window would show (PPM, through the blit
 // pass) plus the raw accumulation (PFM).  The textures an OBJ's materials name are decoded by the library
 // (ptc_scene_decode_textures: PNG / PFM on the host threads, JPEG by nvJPEG on the GPU — Texture::load, texture.rs:232-243).
-// The environment map (the reference's res/knob/envmap.exr; no OpenEXR decoder in this image) comes as a PFM (--env), as raw
+// The environment map (the reference hard-codes res/knob/envmap.exr, scene.rs:93) comes as an OpenEXR or PFM file (--env), as raw
 // float32 RGBA (--env-raw), or is a constant sky.
 //
-//   ptrender --obj scene.obj [--env sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z]
+//   ptrender --obj scene.obj [--env sky.exr | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z]
 //            [--fov deg] [--lbvh] [--lights-mis] [--out prefix]
 #include "../include/ptcore.hpp"
 
@@ -41,28 +41,23 @@ int main(int argc, char** argv) {
         else if (a == "--lights-mis") mis = true;
         else if (a == "--out") { need(1); out = argv[++i]; }
         else if (a == "--help" || a == "-h") {
-            printf("ptrender --obj scene.obj [--env sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
+            printf("ptrender --obj scene.obj [--env sky.exr|sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
             return 0;
         } else { fprintf(stderr, "ptrender: unknown argument %s\n", a.c_str()); return 2; }
     }
     if (obj.empty()) { fprintf(stderr, "ptrender: --obj is required (try --help)\n"); return 2; }
     try {
-        ptcore::Scene scene("envmap");                                     // Scene::new: textures 0..8 constants, 9 = environment
+        // Scene::new(envmap path): texture 9 is a file like any other and is decoded with the rest (OpenEXR or PFM give float texels)
+        ptcore::Scene scene(env_pfm.empty() ? "envmap" : env_pfm);           // textures 0..8 constants, 9 = environment
         std::vector<float> env;
-        if (!env_pfm.empty()) {
-            std::ifstream f(env_pfm, std::ios::binary);
-            std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-            uint32_t fmt = 0; void* px = nullptr;
-            ptcore::check(ptc_decode_image(bytes.data(), bytes.size(), 0, &env_w, &env_h, &fmt, &px));
-            if (fmt != PTC_TEXEL_RGBA32F) { fprintf(stderr, "ptrender: --env wants a float image (PFM)\n"); return 2; }
-            env.assign((const float*)px, (const float*)px + (size_t)env_w * env_h * 4);
-            ptc_free(px);
-        } else if (!env_raw.empty()) {
-            env.resize((size_t)env_w * env_h * 4);
-            std::ifstream f(env_raw, std::ios::binary);
-            if (!f.read((char*)env.data(), (std::streamsize)(env.size() * 4))) { fprintf(stderr, "ptrender: cannot read %s\n", env_raw.c_str()); return 2; }
-        } else { env_w = env_h = 1; env = {0.5f, 0.6f, 0.8f, 1.0f}; }
-        scene.set_texels(9, env_w, env_h, PTC_TEXEL_RGBA32F, env.data());
+        if (env_pfm.empty()) {
+            if (!env_raw.empty()) {
+                env.resize((size_t)env_w * env_h * 4);
+                std::ifstream f(env_raw, std::ios::binary);
+                if (!f.read((char*)env.data(), (std::streamsize)(env.size() * 4))) { fprintf(stderr, "ptrender: cannot read %s\n", env_raw.c_str()); return 2; }
+            } else { env_w = env_h = 1; env = {0.5f, 0.6f, 0.8f, 1.0f}; }
+            scene.set_texels(9, env_w, env_h, PTC_TEXEL_RGBA32F, env.data());
+        }
         scene.load_obj(obj);
         {
             auto td = std::chrono::steady_clock::now();

@@ -1,8 +1,9 @@
 """Texture decode inside the library (ptc_scene_decode_textures / ptc_decode_image; reference: Texture::load,
 src/texture.rs:232-243, run on 32 threads by Scene::load_obj, src/scene.rs:239-254).
 
-PNG and PFM are decoded on the host: checked bit for bit against OpenCV / Pillow on every colour type and bit depth, on
-Adam7 streams written by an independent encoder in this file, and on damaged files.  JPEG goes through nvJPEG on the GPU
+PNG, OpenEXR and PFM are decoded on the host: PNG checked bit for bit against OpenCV / Pillow on every colour type and bit depth, on
+Adam7 streams written by an independent encoder in this file, and on damaged files; OpenEXR (NONE / ZIPS / ZIP / PIZ, HALF / FLOAT)
+against OpenCV's OpenEXR, including the reference's real 71 MB environment map where the reference checkout is present.  JPEG goes through nvJPEG on the GPU
 (`-m gpu`): the reference's real Sponza JPGs (tests/golden/ref_res, baseline and progressive) against OpenCV's libjpeg
 within the tolerance two conforming IDCTs may differ by, then a textured OBJ rendered by the compiled host (ptrender)."""
 import ctypes as C
@@ -188,6 +189,78 @@ def test_pfm(ptc):
     grey = rng.random((4, 3)).astype(np.float32)
     rc, got = lib_decode(ptc, b"Pf\n3 4\n-1.0\n" + grey[::-1].tobytes())
     assert rc == 0 and np.array_equal(got[..., 0], grey) and np.array_equal(got[..., 2], grey)
+
+
+def _cv2_exr():
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    return cv2
+
+
+def _exr_expected(path):
+    cv2 = _cv2_exr()
+    ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert ref is not None
+    if ref.ndim == 2:
+        ref = np.repeat(ref[:, :, None], 3, axis=2)
+    else:
+        ref = ref[:, :, [2, 1, 0] + ([3] if ref.shape[2] == 4 else [])]
+    if ref.shape[2] == 3:
+        ref = np.concatenate([ref, np.ones(ref.shape[:2] + (1,), np.float32)], axis=2)
+    return ref.astype(np.float32)
+
+
+@pytest.mark.parametrize("compression", ["none", "zips", "zip", "piz"])
+@pytest.mark.parametrize("half", [False, True])
+def test_exr_matches_openexr(ptc, tmp_path, compression, half):
+    """OpenEXR scan-line files written by OpenCV's OpenEXR (every compression this library reads, HALF and FLOAT, grey / RGB /
+    RGBA, sizes that leave partial chunks and odd wavelet levels) decode to the same floats, bit for bit"""
+    cv2 = _cv2_exr()
+    comp = {"none": cv2.IMWRITE_EXR_COMPRESSION_NO, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS, "zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP,
+            "piz": cv2.IMWRITE_EXR_COMPRESSION_PIZ}[compression]
+    rng = np.random.default_rng(9)
+    for (H, W, ch) in [(1, 1, 3), (37, 53, 3), (70, 33, 4), (64, 64, 0), (45, 130, 3)]:
+        shape = (H, W) if ch == 0 else (H, W, ch)
+        smooth = np.add.outer(np.arange(H), np.arange(W)).astype(np.float32) / (H + W)
+        im = (smooth if ch == 0 else smooth[:, :, None] * np.arange(1, ch + 1)) + rng.random(shape).astype(np.float32) * (0.05 if H > 1 else 1.0)
+        im = im.astype(np.float32)
+        if H == 45:
+            im[:20] = 0.25                                     # constant rows: Huffman run-length codes, and a short value bitmap
+        path = str(tmp_path / f"t_{compression}_{int(half)}_{H}x{W}.exr")
+        assert cv2.imwrite(path, im, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF if half else cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, comp])
+        rc, got = lib_decode(ptc, open(path, "rb").read())
+        assert rc == 0, (path, got)
+        want = _exr_expected(path)
+        assert got.dtype == np.float32 and got.shape == want.shape and np.array_equal(got, want), path
+
+
+def test_exr_reference_environment_map(ptc):
+    """the reference's own res/knob/envmap.exr (4096 x 2048 FLOAT RGBA, PIZ; what Scene::new loads, scene.rs:93): every texel equal
+    to OpenEXR's decode.  The file is 71 MB and lives only where /root/reference does."""
+    path = "/root/reference/res/knob/envmap.exr"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present on this box")
+    rc, got = lib_decode(ptc, open(path, "rb").read())
+    assert rc == 0, got
+    want = _exr_expected(path)
+    assert got.shape == (2048, 4096, 4) and np.array_equal(got, want)
+    assert 0.04 < got[..., :3].min() < 0.05 and 0.9 < got[..., :3].max() <= 1.0    # the range SURVEY records for this map (0.045 .. 1.0)
+
+
+def test_exr_damaged_or_unsupported(ptc, tmp_path):
+    cv2 = _cv2_exr()
+    im = np.random.default_rng(2).random((40, 24, 3)).astype(np.float32)
+    path = str(tmp_path / "a.exr")
+    assert cv2.imwrite(path, im, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+    good = open(path, "rb").read()
+    assert lib_decode(ptc, good)[0] == 0
+    for bad in (good[:200], good[:len(good) - 50], good[:len(good) // 2] + bytes(len(good) - len(good) // 2)):
+        rc, msg = lib_decode(ptc, bad)
+        assert rc != 0 and "OpenEXR" in msg, msg
+    path = str(tmp_path / "b.exr")
+    assert cv2.imwrite(path, im, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_RLE])
+    rc, msg = lib_decode(ptc, open(path, "rb").read())
+    assert rc != 0 and "compression" in msg
 
 
 OBJ = """mtllib m.mtl

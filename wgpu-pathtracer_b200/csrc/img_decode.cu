@@ -7,6 +7,7 @@
 #include <nvjpeg.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,7 @@ ImageKind sniff_image(const uint8_t* d, size_t n) {
     if (n >= 8 && std::memcmp(d, png_sig, 8) == 0) return IMG_PNG;
     if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return IMG_JPEG;
     if (n >= 3 && d[0] == 'P' && (d[1] == 'F' || d[1] == 'f') && (d[2] == '\n' || d[2] == ' ' || d[2] == '\r')) return IMG_PFM;
+    if (n >= 8 && d[0] == 0x76 && d[1] == 0x2F && d[2] == 0x31 && d[3] == 0x01) return IMG_EXR;
     return IMG_UNKNOWN;
 }
 
@@ -193,6 +195,274 @@ int decode_pfm(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
             if (ch == 1) v[1] = v[2] = v[0];
             float* q = o + (y * W + x) * 4; q[0] = v[0]; q[1] = v[1]; q[2] = v[2]; q[3] = 1.0f;
         }
+    return 0;
+}
+
+// ---- OpenEXR: single-part scan-line images, HALF / FLOAT channels, compression NONE / ZIPS / ZIP / PIZ ---------------------
+// (the reference's environment map res/knob/envmap.exr is 4096 x 2048 FLOAT RGBA, PIZ: Scene::new, scene.rs:93.)  Restated from
+// the published file format: chunk = y, byte count, data; rows inside a chunk hold the channels in name order; ZIP = zlib +
+// byte-delta predictor + even/odd de-interleave; PIZ = bitmap of used 16-bit values -> LUT, canonical Huffman with a run-length
+// symbol, 2-D Haar-like wavelet per channel and per 16-bit half, LUT back.
+namespace {
+
+struct ExrChan { std::string name; int type; };          // type: 1 HALF, 2 FLOAT (0 UINT is not accepted)
+
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+
+float half_to_float(uint16_t h) {
+    const uint32_t sgn = (uint32_t)(h >> 15) << 31, e = (h >> 10) & 31u, m = h & 1023u;
+    uint32_t u;
+    if (e == 0) {
+        if (m == 0) u = sgn;
+        else { int k = 0; uint32_t mm = m; while (!(mm & 1024u)) { mm <<= 1; ++k; } u = sgn | ((uint32_t)(113 - k) << 23) | ((mm & 1023u) << 13); }
+    } else if (e == 31) u = sgn | 0x7F800000u | (m << 13);
+    else u = sgn | ((e + 112u) << 23) | (m << 13);
+    float f; std::memcpy(&f, &u, 4); return f;
+}
+
+bool zip_block(const uint8_t* src, size_t n, uint8_t* dst, size_t raw) {
+    std::vector<uint8_t> tmp(raw);
+    uLongf got = (uLongf)raw;
+    if (uncompress(tmp.data(), &got, src, (uLong)n) != Z_OK || got != raw) return false;
+    for (size_t i = 1; i < raw; ++i) tmp[i] = (uint8_t)(tmp[i - 1] + tmp[i] - 128);       // predictor
+    const size_t half = (raw + 1) / 2;                                                    // de-interleave
+    for (size_t i = 0; i < raw; ++i) dst[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+    return true;
+}
+
+// --- PIZ: Huffman ---
+const int kHufEncSize = (1 << 16) + 1;
+struct BitReader {
+    const uint8_t* p; const uint8_t* end; uint64_t c = 0; int lc = 0;
+    uint32_t get(int n) { while (lc < n) { c = (c << 8) | (p < end ? *p : 0); ++p; lc += 8; } lc -= n; return (uint32_t)((c >> lc) & ((1ull << n) - 1)); }
+};
+bool huf_uncompress(const uint8_t* src, size_t n, uint16_t* out, size_t nout) {
+    if (n < 20) return nout == 0;
+    const uint32_t im = le32(src), iM = le32(src + 4), nbits = le32(src + 12);
+    if (im >= (uint32_t)kHufEncSize || iM >= (uint32_t)kHufEncSize || im > iM) return false;
+    std::vector<uint8_t> len((size_t)kHufEncSize, 0);
+    BitReader br{src + 20, src + n};
+    for (uint32_t i = im; i <= iM; ++i) {                      // packed code lengths: 6 bits each, 59..62 short zero runs, 63 long
+        const uint32_t l = br.get(6);
+        if (l == 63u) { uint32_t z = br.get(8) + 6u; if (i + z > iM + 1) return false; i += z - 1; }
+        else if (l >= 59u) { uint32_t z = l - 59u + 2u; if (i + z > iM + 1) return false; i += z - 1; }
+        else len[i] = (uint8_t)l;
+    }
+    // the table was read by whole bytes: the bit stream starts at the next byte boundary
+    const uint8_t* data = br.p - (br.lc / 8);
+    // canonical codes, longest length first (hufCanonicalCodeTable)
+    uint64_t cnt[59] = {0}, base[59] = {0};
+    for (int i = 0; i < kHufEncSize; ++i) cnt[len[i]]++;
+    { uint64_t c = 0; for (int l = 58; l > 0; --l) { const uint64_t nc = (c + cnt[l]) >> 1; base[l] = c; c = nc; } }
+    std::vector<uint32_t> first(59, 0), sorted;                // symbols of each length in symbol order
+    { uint32_t k = 0; for (int l = 1; l < 59; ++l) { first[l] = k; k += (uint32_t)cnt[l]; } sorted.resize(k); }
+    { std::vector<uint32_t> pos(first); for (int i = 0; i < kHufEncSize; ++i) if (len[i]) sorted[pos[len[i]]++] = (uint32_t)i; }
+    // fast table for codes of up to 12 bits: entry = (symbol << 8) | length, 0 = longer code
+    const int kFast = 12;
+    std::vector<uint32_t> fast((size_t)1 << kFast, 0);
+    for (int l = 1; l <= kFast; ++l)
+        for (uint64_t k = 0; k < cnt[l]; ++k) {
+            const uint64_t code = base[l] + k;
+            if (code >> l) return false;
+            const uint32_t sym = sorted[first[l] + (uint32_t)k];
+            const uint64_t lo = code << (kFast - l), hi = lo + ((uint64_t)1 << (kFast - l));
+            for (uint64_t x = lo; x < hi; ++x) fast[x] = (sym << 8) | (uint32_t)l;
+        }
+    const uint32_t rlc = iM;                                   // the run-length symbol
+    BitReader d{data, src + n};
+    uint64_t bits_left = nbits;
+    size_t o = 0;
+    auto peek = [&](int k) -> uint32_t { while (d.lc < k) { d.c = (d.c << 8) | (d.p < d.end ? *d.p : 0); ++d.p; d.lc += 8; } return (uint32_t)((d.c >> (d.lc - k)) & ((1ull << k) - 1)); };
+    while (bits_left > 0) {
+        uint32_t sym; int l;
+        const uint32_t e = fast[peek(kFast)];
+        if (e) { sym = e >> 8; l = (int)(e & 255u); }
+        else {
+            l = kFast + 1; sym = 0xFFFFFFFFu;
+            for (; l < 59; ++l) {
+                if (!cnt[l]) continue;
+                const uint64_t code = peek(l);
+                if (code >= base[l] && code - base[l] < cnt[l]) { sym = sorted[first[l] + (uint32_t)(code - base[l])]; break; }
+            }
+            if (sym == 0xFFFFFFFFu) return false;
+        }
+        if ((uint64_t)l > bits_left) break;                    // padding bits at the end of the stream
+        d.lc -= l; bits_left -= (uint64_t)l;
+        if (sym == rlc) {
+            if (bits_left < 8 || o == 0) return false;
+            const uint32_t run = peek(8); d.lc -= 8; bits_left -= 8;
+            if (o + run > nout) return false;
+            const uint16_t v = out[o - 1];
+            for (uint32_t k = 0; k < run; ++k) out[o++] = v;
+        } else {
+            if (o >= nout) return false;
+            out[o++] = (uint16_t)sym;
+        }
+    }
+    return o == nout;
+}
+
+// --- PIZ: wavelet ---
+inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int16_t ls = (int16_t)l, hs = (int16_t)h;
+    const int hi = hs, ai = ls + (hi & 1) + (hi >> 1);
+    a = (uint16_t)(int16_t)ai; b = (uint16_t)(int16_t)(ai - hi);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int m = l, d = h, bb = (m - (d >> 1)) & 0xFFFF, aa = (d + bb - 0x8000) & 0xFFFF;
+    b = (uint16_t)bb; a = (uint16_t)aa;
+}
+void wav2_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
+    const bool w14 = mx < (1 << 14);
+    const int n = nx > ny ? ny : nx;
+    int p = 1, p2;
+    while (p <= n) p <<= 1;
+    p >>= 1; p2 = p; p >>= 1;
+    while (p >= 1) {
+        uint16_t* py = in; uint16_t* const ey = in + (ptrdiff_t)oy * (ny - p2);
+        const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
+        uint16_t i00, i01, i10, i11;
+        for (; py <= ey; py += oy2) {
+            uint16_t* px = py; uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+                if (w14) { wdec14(*px, *p10, i00, i10); wdec14(*p01, *p11, i01, i11); wdec14(i00, i01, *px, *p01); wdec14(i10, i11, *p10, *p11); }
+                else { wdec16(*px, *p10, i00, i10); wdec16(*p01, *p11, i01, i11); wdec16(i00, i01, *px, *p01); wdec16(i10, i11, *p10, *p11); }
+            }
+            if (nx & p) { uint16_t* p10 = px + oy1; if (w14) wdec14(*px, *p10, i00, *p10); else wdec16(*px, *p10, i00, *p10); *px = i00; }
+        }
+        if (ny & p) {
+            uint16_t* px = py; uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) { uint16_t* p01 = px + ox1; if (w14) wdec14(*px, *p01, i00, *p01); else wdec16(*px, *p01, i00, *p01); *px = i00; }
+        }
+        p2 = p; p >>= 1;
+    }
+}
+bool piz_block(const uint8_t* src, size_t n, uint8_t* dst, size_t raw, int width, int rows, const std::vector<ExrChan>& ch) {
+    if (n < 4) return false;
+    const uint32_t minnz = src[0] | (src[1] << 8), maxnz = src[2] | (src[3] << 8);
+    std::vector<uint8_t> bitmap(8192, 0);
+    size_t p = 4;
+    if (minnz <= maxnz) {
+        if (maxnz >= 8192 || p + (maxnz - minnz + 1) > n) return false;
+        std::memcpy(bitmap.data() + minnz, src + p, maxnz - minnz + 1); p += maxnz - minnz + 1;
+    }
+    std::vector<uint16_t> lut(65536, 0);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < 65536; ++i) if (i == 0 || (bitmap[i >> 3] & (1u << (i & 7)))) lut[k++] = (uint16_t)i;
+    const uint16_t maxv = (uint16_t)(k - 1);
+    if (p + 4 > n) return false;
+    const uint32_t hlen = le32(src + p); p += 4;
+    if (p + hlen > n) return false;
+    const size_t nvals = raw / 2;
+    std::vector<uint16_t> tmp(nvals);
+    if (!huf_uncompress(src + p, hlen, tmp.data(), nvals)) return false;
+    // per channel: rows x (width * size) values; wavelet per 16-bit half
+    size_t off = 0;
+    std::vector<size_t> start(ch.size());
+    for (size_t c = 0; c < ch.size(); ++c) {
+        const int size = ch[c].type == 1 ? 1 : 2;
+        start[c] = off;
+        for (int j = 0; j < size; ++j) wav2_decode(tmp.data() + off + j, width, size, rows, width * size, maxv);
+        off += (size_t)width * rows * size;
+    }
+    if (off != nvals) return false;
+    for (size_t i = 0; i < nvals; ++i) tmp[i] = lut[tmp[i]];
+    // back to scan-line order: row, then channel
+    uint8_t* o = dst;
+    for (int y = 0; y < rows; ++y)
+        for (size_t c = 0; c < ch.size(); ++c) {
+            const int size = ch[c].type == 1 ? 1 : 2;
+            const uint16_t* r = tmp.data() + start[c] + (size_t)y * width * size;
+            for (int x = 0; x < width * size; ++x) { *o++ = (uint8_t)(r[x] & 255u); *o++ = (uint8_t)(r[x] >> 8); }
+        }
+    return (size_t)(o - dst) == raw;
+}
+
+}  // namespace
+
+int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    if (sniff_image(d, n) != IMG_EXR) { err = "not an OpenEXR file"; return 1; }
+    const uint32_t version = le32(d + 4);
+    if ((version & 0xFFu) != 2 || (version & 0x1A00u)) { err = "unsupported OpenEXR flavour (tiled, deep or multi-part)"; return 1; }
+    std::vector<ExrChan> ch;
+    int compression = -1; int dw[4] = {0, 0, -1, -1};
+    size_t p = 8;
+    for (;;) {                                                  // header: name\0 type\0 size value ... \0
+        if (p >= n) { err = "truncated OpenEXR header"; return 1; }
+        if (d[p] == 0) { ++p; break; }
+        const char* name = (const char*)d + p; const size_t nl = strnlen(name, n - p); p += nl + 1;
+        if (p >= n) { err = "truncated OpenEXR header"; return 1; }
+        const char* type = (const char*)d + p; const size_t tl = strnlen(type, n - p); p += tl + 1;
+        if (p + 4 > n) { err = "truncated OpenEXR header"; return 1; }
+        const uint32_t sz = le32(d + p); p += 4;
+        if ((size_t)sz > n - p) { err = "truncated OpenEXR header"; return 1; }
+        const uint8_t* v = d + p; p += sz;
+        if (!std::strcmp(name, "channels")) {
+            size_t q = 0;
+            while (q < sz && v[q] != 0) {
+                ExrChan c; c.name = (const char*)v + q; q += c.name.size() + 1;
+                if (q + 16 > sz) { err = "bad OpenEXR channel list"; return 1; }
+                c.type = (int)le32(v + q);
+                const uint32_t xs = le32(v + q + 8), ys = le32(v + q + 12); q += 16;
+                if (c.type != 1 && c.type != 2) { err = "OpenEXR UINT channels are not supported"; return 1; }
+                if (xs != 1 || ys != 1) { err = "sub-sampled OpenEXR channels are not supported"; return 1; }
+                ch.push_back(c);
+            }
+        } else if (!std::strcmp(name, "compression") && sz >= 1) compression = v[0];
+        else if (!std::strcmp(name, "dataWindow") && sz >= 16) for (int k = 0; k < 4; ++k) dw[k] = (int)le32(v + 4 * k);
+    }
+    const int64_t W = (int64_t)dw[2] - dw[0] + 1, H = (int64_t)dw[3] - dw[1] + 1;
+    if (ch.empty() || W <= 0 || H <= 0 || W * H > (1ll << 30)) { err = "bad OpenEXR header (channels / dataWindow)"; return 1; }
+    int lines;
+    switch (compression) { case 0: case 2: lines = 1; break; case 3: lines = 16; break; case 4: lines = 32; break;
+        default: err = "unsupported OpenEXR compression (only NONE, ZIPS, ZIP and PIZ)"; return 1; }
+    size_t row_bytes = 0;
+    for (const ExrChan& c : ch) row_bytes += (size_t)W * (c.type == 1 ? 2 : 4);
+    const int64_t nchunks = (H + lines - 1) / lines;
+    if (p + (size_t)nchunks * 8 > n) { err = "truncated OpenEXR offset table"; return 1; }
+    // where R, G, B, A live inside a row (a lone Y channel is grey)
+    int idx[4] = {-1, -1, -1, -1};
+    for (size_t c = 0; c < ch.size(); ++c) {
+        const std::string& nm = ch[c].name;
+        if (nm == "R") idx[0] = (int)c; else if (nm == "G") idx[1] = (int)c; else if (nm == "B") idx[2] = (int)c; else if (nm == "A") idx[3] = (int)c;
+        else if (nm == "Y" && idx[0] < 0) idx[0] = idx[1] = idx[2] = (int)c;
+    }
+    if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0) { err = "OpenEXR image without R, G, B (or Y) channels"; return 1; }
+    std::vector<size_t> chan_off(ch.size());
+    { size_t o = 0; for (size_t c = 0; c < ch.size(); ++c) { chan_off[c] = o; o += (size_t)W * (ch[c].type == 1 ? 2 : 4); } }
+    out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA32F;
+    out.texels.assign((size_t)W * H * 16, 0);
+    float* px = reinterpret_cast<float*>(out.texels.data());
+    std::vector<uint8_t> raw;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const uint64_t at = le64(d + p + (size_t)k * 8);
+        if (at + 8 > n) { err = "bad OpenEXR chunk offset"; return 1; }
+        const int y0 = (int)le32(d + at) - dw[1];
+        const uint32_t csz = le32(d + at + 4);
+        if (y0 < 0 || y0 >= H || at + 8 + csz > n) { err = "bad OpenEXR chunk"; return 1; }
+        const int rows = (int)std::min<int64_t>(lines, H - y0);
+        const size_t want = row_bytes * (size_t)rows;
+        raw.resize(want);
+        const uint8_t* src = d + at + 8;
+        bool ok = true;
+        if (csz == want) std::memcpy(raw.data(), src, want);                          // stored: the compressor did not win
+        else if (compression == 2 || compression == 3) ok = zip_block(src, csz, raw.data(), want);
+        else if (compression == 4) ok = piz_block(src, csz, raw.data(), want, (int)W, rows, ch);
+        else ok = false;
+        if (!ok) { err = "OpenEXR chunk does not decompress"; return 1; }
+        for (int r = 0; r < rows; ++r) {
+            const uint8_t* row = raw.data() + (size_t)r * row_bytes;
+            float* o = px + ((size_t)(y0 + r) * W) * 4;
+            for (int c4 = 0; c4 < 4; ++c4) {
+                if (idx[c4] < 0) { for (int64_t x = 0; x < W; ++x) o[x * 4 + c4] = 1.0f; continue; }
+                const uint8_t* cp = row + chan_off[idx[c4]];
+                if (ch[idx[c4]].type == 1) for (int64_t x = 0; x < W; ++x) o[x * 4 + c4] = half_to_float((uint16_t)(cp[x * 2] | (cp[x * 2 + 1] << 8)));
+                else for (int64_t x = 0; x < W; ++x) { const uint32_t u = le32(cp + x * 4); std::memcpy(&o[x * 4 + c4], &u, 4); }
+            }
+        }
+    }
     return 0;
 }
 

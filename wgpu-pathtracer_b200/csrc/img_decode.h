@@ -4,8 +4,9 @@
 //   PNG  : decoded here (chunk parser + zlib inflate + the five row filters + Adam7), every colour type and bit depth
 //   JPEG : nvJPEG, i.e. decoded on the GPU (baseline and progressive); bound at run time like NCCL, so libptcore has no
 //          link dependency on it and a box without libnvjpeg only loses JPEG textures
-//   PFM  : raw float maps (the stand-in for the reference's EXR environment map, which needs an OpenEXR decoder the
-//          image does not have)
+//   EXR  : decoded here: single-part scan-line files with HALF / FLOAT channels, compression NONE / ZIPS / ZIP / PIZ — what the
+//          reference's environment map (res/knob/envmap.exr: 4096 x 2048 FLOAT RGBA, PIZ) needs
+//   PFM  : raw float maps
 // Output follows decode_image of the Python mirror: 8-bit sources stay RGBA8 (the kernels apply v / 255, no sRGB
 // decode), 16-bit sources become RGBA32F = v / 65535, float sources stay float; grey -> rgb, missing alpha -> 1.
 #pragma once
@@ -21,12 +22,13 @@ struct DecodedImage {
     std::vector<uint8_t> texels;         // width * height * (4 or 16) bytes
 };
 
-enum ImageKind { IMG_UNKNOWN = 0, IMG_PNG, IMG_JPEG, IMG_PFM };
+enum ImageKind { IMG_UNKNOWN = 0, IMG_PNG, IMG_JPEG, IMG_PFM, IMG_EXR };
 ImageKind sniff_image(const uint8_t* data, size_t n);
 
 // 0 on success, else `err` says why
 int decode_png(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
 int decode_pfm(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
+int decode_exr(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
 
 // nvJPEG decoder: one per host thread (own handle, state, stream and device buffer).
 class JpegDecoder {
