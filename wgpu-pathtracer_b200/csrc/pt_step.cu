@@ -249,7 +249,10 @@ static int alloc_frame_buffers(ptc_step* s, uint32_t w, uint32_t h) {
     // slots are dealt to the parts warp by warp: warp t (slots 32t .. 32t+31) belongs to part t % num_parts
     // Parts by frame size (measured, profiles/r01f): the tail a part hides is a fixed ~30-50 us per launch, so mid-size frames
     // gain most (1080p: 3 parts +8 % Sponza, +22 % classroom); at 4K launches are long and a third part only costs locality.
-    uint32_t want = s->want_parts ? s->want_parts : (n < (1u << 20) ? 2u : (n < (1u << 22) ? 3u : 2u));
+    // Round 2 (profiles/r02zc_ab_parts.log): a tree that lives in L1 / L2 altogether (Sponza: 6 MB of nodes + triangles) has short
+    // traversal tails and is faster with 2 parts (+2.8 %), the 48-70 MB trees of classroom and dragon keep 3 (2 parts: -2 to -7 %).
+    const bool small_tree = s->bvh_info[2] + s->bvh_info[3] < (16ull << 20);
+    uint32_t want = s->want_parts ? s->want_parts : (n < (1u << 20) ? 2u : (n < (1u << 22) ? (small_tree ? 2u : 3u) : 2u));
     s->num_parts = std::max(1u, std::min(std::min(want, (uint32_t)ptc_step::kMaxParts), n / 8192u));
     const uint32_t nw = n >> 5, rem = n & 31u, NP = s->num_parts;
     for (uint32_t p = 0; p < NP; ++p) {
