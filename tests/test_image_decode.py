@@ -362,7 +362,8 @@ def test_jpeg_nvjpeg_matches_libjpeg_on_the_reference_textures(ptc):
 
 
 @pytest.mark.gpu
-def test_ptrender_loads_a_textured_obj(ptc, standins, tmp_path):
+@pytest.mark.parametrize("env_format", ["pfm", "exr"])
+def test_ptrender_loads_a_textured_obj(ptc, standins, tmp_path, env_format):
     """the compiled host renders an OBJ whose MTL is the reference's real sponza.mtl (JPG textures decoded by the library) and
     gets, bit for bit, the image the Python mirror renders from the same library-decoded textures"""
     import shutil
@@ -384,11 +385,16 @@ def test_ptrender_loads_a_textured_obj(ptc, standins, tmp_path):
         lines += [f"usemtl {m}", f"f {b + 1}/1/1 {b + 2}/2/1 {b + 3}/3/1", f"f {b + 1}/1/1 {b + 3}/3/1 {b + 4}/4/1"]
     (d / "wall.obj").write_text("\n".join(lines) + "\n")
     env = standins.make_envmap(64, 32)
-    pfm = b"PF\n64 32\n-1.0\n" + env.texels[::-1, :, :3].astype("<f4").tobytes()
-    (tmp_path / "sky.pfm").write_bytes(pfm)
+    env_path = str(tmp_path / f"sky.{env_format}")
+    if env_format == "pfm":
+        open(env_path, "wb").write(b"PF\n64 32\n-1.0\n" + env.texels[::-1, :, :3].astype("<f4").tobytes())
+    else:                                                      # what Scene::new("res/knob/envmap.exr") loads: FLOAT RGBA, PIZ
+        cv2 = _cv2_exr()
+        assert cv2.imwrite(env_path, np.ascontiguousarray(env.texels[:, :, [2, 1, 0, 3]].astype(np.float32)),
+                           [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
     W, H, frames = 256, 96, 2
     pos, look = (-6.0, 1.0, n / 2), (4.0, 1.0, n / 2)
-    r = subprocess.run([os.path.join(csrc, "ptrender"), "--obj", str(d / "wall.obj"), "--env", str(tmp_path / "sky.pfm"), "--size", f"{W}x{H}",
+    r = subprocess.run([os.path.join(csrc, "ptrender"), "--obj", str(d / "wall.obj"), "--env", env_path, "--size", f"{W}x{H}",
                         "--frames", str(frames), "--pos", *map(str, pos), "--look", *map(str, look), "--fov", "90", "--out", str(tmp_path / "cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
