@@ -158,7 +158,10 @@ typedef struct ptc_config {
     uint32_t bvh_width;                /* 0 = library default; 2 = BVH2 */
     uint32_t light_sampling;           /* enum ptc_light_sampling; PTC_LIGHTS_MIS requires send_to_light_probability == 0 */
     uint32_t bvh_build;                /* enum ptc_bvh_build */
-    uint32_t reserved[5];
+    uint32_t ploc_window;              /* PTC_BVH_PLOC_DEVICE: clusters searched on either side for a merge partner; 0 = default (4), at most 64.
+                                          Regular tessellations (the stand-in scenes) build best with 3-4: Morton-aligned blocks; irregular
+                                          meshes are reported to gain up to 8-25.  Must be 0 for the other builders. */
+    uint32_t reserved[4];
 } ptc_config;
 
 /* Planes readable from a step. */

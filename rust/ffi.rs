@@ -27,7 +27,7 @@ pub struct ptc_scene_view {
 pub struct ptc_config {
     pub width: u32, pub height: u32, pub max_bounces: u32, pub samples_per_pixel: u32,
     pub send_to_light_probability: f32, pub env_texture_index: u32, pub accum_mode: u32, pub compat_flags: u32,
-    pub bvh_width: u32, pub light_sampling: u32, pub bvh_build: u32, pub reserved: [u32; 5],
+    pub bvh_width: u32, pub light_sampling: u32, pub bvh_build: u32, pub ploc_window: u32, pub reserved: [u32; 4],
 }
 
 #[repr(C)] #[derive(Copy, Clone, Default)]

@@ -121,6 +121,6 @@ def test_config_fields_without_meaning_are_refused(ptc, standins):
         if rc == 0:
             L.ptc_destroy(h)
         return rc, L.ptc_last_error().decode()
-    for kw in (dict(compat_flags=1), dict(reserved=0), dict(reserved=4), dict(bvh_width=3), dict(samples_per_pixel=0), dict(accum_mode=7)):
+    for kw in (dict(compat_flags=1), dict(reserved=0), dict(reserved=3), dict(ploc_window=4), dict(ploc_window=65, bvh_build=2), dict(bvh_width=3), dict(samples_per_pixel=0), dict(accum_mode=7)):
         rc, msg = create(**kw)
         assert rc == T.ERR_INVALID, (kw, rc, msg)

@@ -611,6 +611,21 @@ def test_cpp_harness_matches_python_mirror(ptc, standins, tmp_path):
     step.destroy()
 
 
+@pytest.mark.parametrize("window", [1, 9, 64])
+def test_ploc_window_is_honoured_on_device_and_host(ptc, standins, oracle, hostemu, window):
+    """ptc_config.ploc_window reaches both builds: device tree == host restatement word for word at every window, trees differ
+    between windows, images do not"""
+    scene, cam = standins.random_soup(20000, seed=5, textured=True)
+    T = ptc.types
+    step, ref = render_both(ptc, standins, oracle, scene, cam, 160, 100, 1, max_bounces=4, bvh_build=T.BVH_PLOC_DEVICE, ploc_window=window)
+    emu = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_PLOC_DEVICE, ploc_window=window))
+    assert step.bvh_hash() == emu.bvh_hash()
+    default = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_PLOC_DEVICE))
+    assert default.bvh_hash() != emu.bvh_hash()              # the default window is 4
+    check_all_planes(ptc, step, ref)
+    step.destroy()
+
+
 def test_non_finite_throughput_is_carried_like_the_oracle(ptc, standins, oracle):
     """The accumulated-colour queue entry is only written when it is not all zero bits (k_shade).  Without light sampling that
     happens when the throughput overflows: an albedo of 1e30 makes `mask` inf after two bounces and `acc += 0 * mask` NaN.  The

@@ -30,7 +30,7 @@ class SceneView(C.Structure):
 class Config(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("max_bounces", u32), ("samples_per_pixel", u32),
                 ("send_to_light_probability", f32), ("env_texture_index", u32), ("accum_mode", u32),
-                ("compat_flags", u32), ("bvh_width", u32), ("light_sampling", u32), ("bvh_build", u32), ("reserved", u32 * 5)]
+                ("compat_flags", u32), ("bvh_width", u32), ("light_sampling", u32), ("bvh_build", u32), ("ploc_window", u32), ("reserved", u32 * 4)]
 
 
 class Stats(C.Structure):

@@ -367,7 +367,7 @@ void build_lbvh_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t
 // that numbers the triangles in depth-first order (so that a collapsed leaf's triangles are consecutive), and the emission
 // of the quantised nodes.  Every step is a deterministic function of its inputs, so the arrays equal the device build's
 // word for word (ptc_debug_bvh_hash).
-void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth) {
+void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth, int radius) {
     const int n = (int)ntri;
     std::vector<PlocBox> box((size_t)2 * n - 1);
     std::vector<PlocBox> prim(ntri);
@@ -405,7 +405,7 @@ void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t
         for (auto& x : th) x.join();
     };
     while (m > 1) {
-        par(m, [&](int b, int e) { for (int i = b; i < e; ++i) nn[i] = ploc_nearest(box.data(), cur.data(), m, i); });
+        par(m, [&](int b, int e) { for (int i = b; i < e; ++i) nn[i] = ploc_nearest(box.data(), cur.data(), m, i, radius); });
         round_base.push_back(next_node);
         int w = 0;
         for (int i = 0; i < m; ++i) {

@@ -68,6 +68,6 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out);
 // harness; the product builds on the GPU.  Needs ntri > 4; max_depth = levels of the collapsed tree.
 void build_lbvh_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth);
 // the same for the PLOC build (parallel locally-ordered clustering, lbvh.cuh): ntri > PTC_PLOC_MAX_LEAF
-void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth);
+void build_ploc_host(const float* tri_pos, uint32_t ntri, DevBvh2& out, uint32_t& max_depth, int radius);
 
 }  // namespace ptc

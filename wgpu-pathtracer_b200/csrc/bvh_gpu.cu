@@ -144,9 +144,9 @@ __global__ void k_ploc_init(const uint32_t* __restrict__ ids, const Box6* __rest
     PlocBox o; for (int a = 0; a < 3; ++a) { o.lo[a] = b.lo[a]; o.hi[a] = b.hi[a]; }
     box[k] = o; cur[k] = k; count[k] = 1u; kc[k] = 0u;
 }
-__global__ void k_ploc_nn(const PlocBox* __restrict__ box, const uint32_t* __restrict__ cur, int m, int* __restrict__ nn) {
+__global__ void k_ploc_nn(const PlocBox* __restrict__ box, const uint32_t* __restrict__ cur, int m, int* __restrict__ nn, int radius) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) nn[i] = ploc_nearest(box, cur, m, i);
+    if (i < m) nn[i] = ploc_nearest(box, cur, m, i, radius);
 }
 // merged[i] = 1 when cluster i is the LEFT partner of a mutual pair (it becomes the merged cluster); valid[i] = 0 for the right partner
 __global__ void k_ploc_flags(const int* __restrict__ nn, int m, uint32_t* __restrict__ merged, uint32_t* __restrict__ valid) {
@@ -294,7 +294,7 @@ done:
     return rc;
 }
 
-int build_ploc_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh& out) {
+int build_ploc_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh& out, int radius) {
     int rc = PTC_OK;
     const int n = (int)ntri;
     out = GpuBvh{};
@@ -348,7 +348,7 @@ int build_ploc_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh
         int m = n;
         while (m > 1) {
             const uint32_t g = ((uint32_t)m + T - 1) / T;
-            k_ploc_nn<<<g, T, 0, st>>>(box, cur, m, nn);
+            k_ploc_nn<<<g, T, 0, st>>>(box, cur, m, nn, radius);
             k_ploc_flags<<<g, T, 0, st>>>(nn, m, merged, valid);
             CKB(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, merged, mpos, m, st));
             CKB(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, valid, vpos, m, st));

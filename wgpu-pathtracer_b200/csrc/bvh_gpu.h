@@ -16,6 +16,6 @@ struct GpuBvh {
 // d_pos: ntri x 9 floats (v0, v1, v2) in device memory; ntri > 4.  Returns PTC_OK or a negative ptc_status.
 int build_lbvh_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh& out);
 // the same interface for the PLOC build (parallel locally-ordered clustering, lbvh.cuh); ntri > 4
-int build_ploc_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh& out);
+int build_ploc_device(const float* d_pos, uint32_t ntri, cudaStream_t st, GpuBvh& out, int radius);
 
 }  // namespace ptc

@@ -129,9 +129,9 @@ PT_HD float ploc_joint_area(const PlocBox& a, const PlocBox& b) {        // half
 // order on pairs, so the globally best pair is always mutual and every round merges at least one pair whatever the ties; and
 // among clusters with IDENTICAL boxes (coincident triangles) the order pairs neighbours (0,1) (2,3) ... so the tree stays
 // balanced instead of degenerating into a chain.
-PT_HD int ploc_nearest(const PlocBox* box, const uint32_t* cur, int m, int i) {
+PT_HD int ploc_nearest(const PlocBox* box, const uint32_t* cur, int m, int i, int radius) {
     const PlocBox bi = box[cur[i]];
-    const int j0 = i - PTC_PLOC_RADIUS < 0 ? 0 : i - PTC_PLOC_RADIUS, j1 = i + PTC_PLOC_RADIUS > m - 1 ? m - 1 : i + PTC_PLOC_RADIUS;
+    const int j0 = i - radius < 0 ? 0 : i - radius, j1 = i + radius > m - 1 ? m - 1 : i + radius;
     float best = INFINITY; int bj = -1, bd = 0, bmn = 0;
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;

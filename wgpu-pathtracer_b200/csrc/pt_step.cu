@@ -4,6 +4,7 @@
 #include "bvh_build.h"
 #include "scene_prep.h"
 #include "bvh_gpu.h"
+#include "lbvh.cuh"
 #include "pt_kernels.cuh"
 #include "pt_error.h"
 
@@ -289,7 +290,7 @@ static int upload_scene(ptc_step* s, const ptc_scene_view* v) {
         CK(cudaMalloc(&d_pos, ps.tri_pos.size() * 4));
         cudaError_t ce = cudaMemcpyAsync(d_pos, ps.tri_pos.data(), ps.tri_pos.size() * 4, cudaMemcpyHostToDevice, s->stream);
         GpuBvh g;
-        rc = ce != cudaSuccess ? PTC_ERR_CUDA : (s->cfg.bvh_build == PTC_BVH_PLOC_DEVICE ? build_ploc_device(d_pos, ps.num_tris, s->stream, g)
+        rc = ce != cudaSuccess ? PTC_ERR_CUDA : (s->cfg.bvh_build == PTC_BVH_PLOC_DEVICE ? build_ploc_device(d_pos, ps.num_tris, s->stream, g, s->cfg.ploc_window ? (int)s->cfg.ploc_window : PTC_PLOC_RADIUS)
                                                                                                  : build_lbvh_device(d_pos, ps.num_tris, s->stream, g));
         cudaFree(d_pos);
         if (rc != PTC_OK) { if (ce != cudaSuccess) set_error(std::string("position upload: ") + cudaGetErrorString(ce)); return rc; }
@@ -475,6 +476,7 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     if (config->bvh_width != 0 && config->bvh_width != 2) { set_error("bad bvh_width (0 = library default, 2 = BVH2)"); return PTC_ERR_INVALID; }
     if (config->compat_flags != PTC_COMPAT_NONE) { set_error("unknown compat_flags (none are defined)"); return PTC_ERR_INVALID; }
     for (uint32_t r : config->reserved) if (r != 0) { set_error("ptc_config.reserved must be zero"); return PTC_ERR_INVALID; }
+    if (config->ploc_window > 64u || (config->ploc_window != 0u && config->bvh_build != PTC_BVH_PLOC_DEVICE)) { set_error("bad ploc_window (0 = default, at most 64, PTC_BVH_PLOC_DEVICE only)"); return PTC_ERR_INVALID; }
     if (config->light_sampling == PTC_LIGHTS_MIS && config->send_to_light_probability != 0.0f) { set_error("PTC_LIGHTS_MIS requires send_to_light_probability == 0"); return PTC_ERR_INVALID; }
     int ndev = ptc_device_count();
     if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }

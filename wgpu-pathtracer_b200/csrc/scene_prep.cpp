@@ -80,7 +80,7 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
     else {
         bool sah = !lbvh;
         if (lbvh) {
-            if (ploc) build_ploc_host(pos.data(), ntri, out.bvh, out.max_depth);
+            if (ploc) build_ploc_host(pos.data(), ntri, out.bvh, out.max_depth, cfg.ploc_window ? (int)cfg.ploc_window : PTC_PLOC_RADIUS);
             else build_lbvh_host(pos.data(), ntri, out.bvh, out.max_depth);
             if (out.max_depth >= PTC_STACK_SIZE) { out.bvh = DevBvh2{}; sah = true; }     // degenerate input: fall back to the SAH tree
         }

@@ -12,13 +12,14 @@ from ._lib import PtcError, check, lib
 
 
 def make_config(width, height, max_bounces=4, samples_per_pixel=1, send_to_light_probability=0.0,
-                env_texture_index=9, accum_mode=T.ACCUM_MEAN, light_sampling=0, bvh_build=0):
+                env_texture_index=9, accum_mode=T.ACCUM_MEAN, light_sampling=0, bvh_build=0, ploc_window=0):
     """The reference's compile-time constants (src/shaders/shader_definitions.rs:3-26) as a run-time struct."""
     c = T.Config()
     c.width, c.height, c.max_bounces, c.samples_per_pixel = width, height, max_bounces, samples_per_pixel
     c.send_to_light_probability, c.env_texture_index, c.accum_mode = send_to_light_probability, env_texture_index, accum_mode
     c.light_sampling = light_sampling          # ptc_light_sampling: 0 = reference behaviour, 1 = shadow rays + MIS (non-parity)
-    c.bvh_build = bvh_build                    # ptc_bvh_build: 0 = binned SAH on the host, 1 = linear BVH built on the GPU
+    c.bvh_build = bvh_build                    # ptc_bvh_build: 0 = binned SAH on the host, 1 = linear BVH, 2 = PLOC, both built on the GPU
+    c.ploc_window = ploc_window                # PLOC only: merge-partner search window (0 = default)
     return c
 
 
