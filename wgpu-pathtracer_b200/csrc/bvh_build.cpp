@@ -24,6 +24,21 @@ constexpr size_t kTopNodes = 128;        // inner nodes numbered breadth-first a
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t id; };
 
+// f(begin, end) over [0, n) on the host threads: the per-triangle and per-node loops around the build proper
+template <class F>
+void par_for(uint64_t n, int nthreads, F f) {
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (n < 65536 || nthreads <= 1) { f((uint64_t)0, n); return; }
+    const uint64_t nt = (uint64_t)std::min(nthreads, 32), chunk = (n + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (uint64_t t = 0; t < nt; ++t) {
+        const uint64_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+
 struct Box {
     float lo[3], hi[3];
     void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
@@ -161,15 +176,22 @@ void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthr
     b.max_leaf = max_leaf;
     b.prims.resize(ntri);
     Box scene; scene.reset();
-    for (uint32_t i = 0; i < ntri; ++i) {
-        Prim& p = b.prims[i]; p.id = i;
-        const float* v = tri_pos + (size_t)i * 9;
-        for (int a = 0; a < 3; ++a) {
-            p.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
-            p.hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
-            p.c[a] = 0.5f * (p.lo[a] + p.hi[a]);
-        }
-        scene.grow(p.lo, p.hi);
+    {
+        std::mutex mu;
+        par_for(ntri, nthreads, [&](uint64_t i0, uint64_t i1) {
+            Box local; local.reset();
+            for (uint64_t i = i0; i < i1; ++i) {
+                Prim& p = b.prims[i]; p.id = (uint32_t)i;
+                const float* v = tri_pos + (size_t)i * 9;
+                for (int a = 0; a < 3; ++a) {
+                    p.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
+                    p.hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
+                    p.c[a] = 0.5f * (p.lo[a] + p.hi[a]);
+                }
+                local.grow(p.lo, p.hi);
+            }
+            std::lock_guard<std::mutex> l(mu); scene.grow(local.lo, local.hi);      // min / max: the order of the merges does not matter
+        });
     }
     // Padding that makes every box conservative with respect to pt_ray_tri: Moeller-Trumbore can accept a
     // ray passing O(eps * distance) outside a triangle edge, so boxes grow by 2e-5 of the scene magnitude.
@@ -186,7 +208,7 @@ void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthr
 
     out.nodes.resize(b.next_node.load());
     out.order.resize(ntri);
-    for (uint32_t i = 0; i < ntri; ++i) out.order[i] = b.prims[i].id;
+    par_for(ntri, nthreads, [&](uint64_t i0, uint64_t i1) { for (uint64_t i = i0; i < i1; ++i) out.order[i] = b.prims[i].id; });
     out.max_depth = b.max_depth.load();
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -196,14 +218,16 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
     if (bvh.nodes.empty()) return;
     uint32_t ntri = (uint32_t)bvh.order.size();
     out.tris.resize(ntri);
-    for (uint32_t i = 0; i < ntri; ++i) {
-        uint32_t id = bvh.order[i];
-        const float* v = tri_pos + (size_t)id * 9;
-        DevTri& t = out.tris[i]; std::memset(&t, 0, sizeof(t));
-        t.q[0] = v[0]; t.q[1] = v[1]; t.q[2] = v[2]; std::memcpy(&t.q[3], &id, 4);
-        t.q[4] = v[3] - v[0]; t.q[5] = v[4] - v[1]; t.q[6] = v[5] - v[2];
-        t.q[8] = v[6] - v[0]; t.q[9] = v[7] - v[1]; t.q[10] = v[8] - v[2];
-    }
+    par_for(ntri, 0, [&](uint64_t i0, uint64_t i1) {
+        for (uint64_t i = i0; i < i1; ++i) {
+            uint32_t id = bvh.order[i];
+            const float* v = tri_pos + (size_t)id * 9;
+            DevTri& t = out.tris[i]; std::memset(&t, 0, sizeof(t));
+            t.q[0] = v[0]; t.q[1] = v[1]; t.q[2] = v[2]; std::memcpy(&t.q[3], &id, 4);
+            t.q[4] = v[3] - v[0]; t.q[5] = v[4] - v[1]; t.q[6] = v[5] - v[2];
+            t.q[8] = v[6] - v[0]; t.q[9] = v[7] - v[1]; t.q[10] = v[8] - v[2];
+        }
+    });
     // quantisation grid: the padded scene box, widened by a few steps so that outward rounding never clamps
     const BuildNode& root = bvh.nodes[0];
     double step[3];
@@ -267,13 +291,15 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
         d.w[3] = d.w[7] = child_ref(0);
         return;
     }
-    for (uint32_t n = 0; n < bvh.nodes.size(); ++n) {
-        if (dev_id[n] < 0) continue;
-        DevNode2& d = out.nodes[dev_id[n]];
-        uint32_t l = bvh.nodes[n].left;
-        put_box(d, 0, bvh.nodes[l]); put_box(d, 1, bvh.nodes[l + 1]);
-        d.w[3] = child_ref(l); d.w[7] = child_ref(l + 1);
-    }
+    par_for(bvh.nodes.size(), 0, [&](uint64_t n0, uint64_t n1) {
+        for (uint64_t n = n0; n < n1; ++n) {
+            if (dev_id[n] < 0) continue;
+            DevNode2& d = out.nodes[dev_id[n]];
+            uint32_t l = bvh.nodes[n].left;
+            put_box(d, 0, bvh.nodes[l]); put_box(d, 1, bvh.nodes[l + 1]);
+            d.w[3] = child_ref(l); d.w[7] = child_ref(l + 1);
+        }
+    });
 }
 
 // ---- linear BVH: host restatement of bvh_gpu.cu --------------------------------------------------------------------
