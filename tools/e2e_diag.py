@@ -1,4 +1,5 @@
-"""Diagnose e2e variance: per-step host-side call times of the bench's e2e loop, repeated."""
+"""Where the e2e loop's time goes: ms per step of the bench's e2e sequence with its pieces added one at a time
+(render only; + blit; + asynchronous read of the DISPLAY plane), and the host time spent inside each call."""
 import importlib, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -9,16 +10,24 @@ scene, cam = st.sponza(); W, H = 1920, 1080
 camera = st.make_camera(cam, W, H)
 step = ptc.RTStep.create(scene, ptc.make_config(W, H))
 pinned = torch.empty(H, W, 4, dtype=torch.uint8).pin_memory()
-for rep in range(6):
-    ts = []
-    t0 = time.perf_counter()
-    for i in range(64):
-        a = time.perf_counter()
-        u = camera.uniforms(frame=1 + i); step.update(u); b = time.perf_counter()
-        step.render(); c = time.perf_counter()
-        step.blit(); step.read_async(T.PLANE_DISPLAY, pinned.data_ptr()); d = time.perf_counter()
-        ts.append((b - a, c - b, d - c))
-    step.poll(True); step.read_wait()
-    dt = time.perf_counter() - t0
-    ts = np.array(ts) * 1e3
-    print(f"rep {rep}: {dt/64*1e3:.3f} ms/step; host ms mean update {ts[:,0].mean():.3f} render {ts[:,1].mean():.3f} blit+read {ts[:,2].mean():.3f}; max {ts.max(axis=0)}")
+step.update(camera.uniforms(frame=1)); step.render(); step.blit(); step.read_async(T.PLANE_DISPLAY, pinned.data_ptr()); step.poll(True); step.read_wait()
+K = 256
+for mode in ("render", "render+blit", "render+blit+read", "render", "render+blit+read"):
+    res = []
+    for rep in range(3):
+        step.poll(True); step.read_wait()
+        host = np.zeros(3)
+        t0 = time.perf_counter()
+        for i in range(K):
+            a = time.perf_counter()
+            step.update(camera.uniforms(frame=1 + i)); step.render(); b = time.perf_counter()
+            if "blit" in mode: step.blit()
+            c = time.perf_counter()
+            if "read" in mode: step.read_async(T.PLANE_DISPLAY, pinned.data_ptr())
+            d = time.perf_counter()
+            host += (b - a, c - b, d - c)
+        step.poll(True); step.read_wait()
+        res.append(((time.perf_counter() - t0) / K * 1e3, host / K * 1e3))
+    ms = np.median([r[0] for r in res])
+    h = res[0][1]
+    print(f"{mode:18s} {ms:.4f} ms/step   host ms per call: update+render {h[0]:.4f} blit {h[1]:.4f} read_async {h[2]:.4f}")

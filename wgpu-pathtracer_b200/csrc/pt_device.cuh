@@ -790,15 +790,25 @@ PT_HD bool reproject_pixel(const ptc_camera& cam, const ptc_camera& prev, uint32
 
 // color.wgsl:4-27 to_khronos_pbr_neutral, F90 = 0.04 (shader_definitions.rs:7); both arms are evaluated and blended
 // with 0/1 weights as the shader does (so a black pixel yields NaN exactly like the reference's).
+// The display image is 8-bit: on the device its divisions are the fast ones (2 ulp, two instructions instead of ~12 — the blit was
+// compute-bound), on the host the IEEE ones; the display test allows the one step by which a result next to a rounding boundary
+// may then differ.  Nothing here feeds the accumulation.
+PT_HD float pt_div_display(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return pt_div(a, b);
+#endif
+}
 PT_HD pt_v3 tonemap_khronos_pbr_neutral(pt_v3 c) {
     const float F90 = 0.04f, k_s = 0.8f - F90, k_d = 0.15f;
     const float x = pt_min(pt_min(c.x, c.y), c.z);
-    const float f = (x - pt_div(x * x, 4.0f * F90)) * (x <= 2.0f * F90 ? 1.0f : 0.0f) + F90 * (x > 2.0f * F90 ? 1.0f : 0.0f);
+    const float f = (x - pt_div_display(x * x, 4.0f * F90)) * (x <= 2.0f * F90 ? 1.0f : 0.0f) + F90 * (x > 2.0f * F90 ? 1.0f : 0.0f);
     const float p = pt_max(pt_max(c.x - f, c.y - f), c.z - f);
-    const float p_n = 1.0f - pt_div((1.0f - k_s) * (1.0f - k_s), p + 1.0f - 2.0f * k_s);
-    const float g = pt_div(1.0f, k_d * (p - p_n) + 1.0f);
+    const float p_n = 1.0f - pt_div_display((1.0f - k_s) * (1.0f - k_s), p + 1.0f - 2.0f * k_s);
+    const float g = pt_div_display(1.0f, k_d * (p - p_n) + 1.0f);
     const float lo = p <= k_s ? 1.0f : 0.0f, hi = p > k_s ? 1.0f : 0.0f;
-    const float r = pt_div(p_n, p), off = p_n * (1.0f - g);
+    const float r = pt_div_display(p_n, p), off = p_n * (1.0f - g);
     return pt_mk3((c.x - f) * lo + ((c.x - f) * r * g + off) * hi,
                   (c.y - f) * lo + ((c.y - f) * r * g + off) * hi,
                   (c.z - f) * lo + ((c.z - f) * r * g + off) * hi);
