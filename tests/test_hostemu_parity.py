@@ -168,6 +168,19 @@ def test_linear_bvh_build_same_images(ptc, standins, oracle, hostemu, which, bui
     assert info["max_depth"] < 64 and info["triangles"] == len(scene.indices) // 3
 
 
+@pytest.mark.parametrize("window", [1, 9, 64])
+def test_ploc_window_changes_the_tree_not_the_image(ptc, standins, oracle, hostemu, window):
+    """ptc_config.ploc_window (PLOC's merge-partner search window): every window builds a different tree and the same image"""
+    scene, cam = standins.random_soup(5000, seed=7, textured=True)
+    T = ptc.types
+    ro, re = both(ptc, standins, oracle, hostemu, scene, cam, 128, 80, 1, max_bounces=4, bvh_build=T.BVH_PLOC_DEVICE, ploc_window=window)
+    assert_identical(ro, re)
+    a = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_PLOC_DEVICE, ploc_window=window)).bvh_hash()
+    b = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_PLOC_DEVICE)).bvh_hash()
+    c = hostemu.scene(scene, ptc.make_config(8, 8, bvh_build=T.BVH_PLOC_DEVICE, ploc_window=4)).bvh_hash()
+    assert a != b and b == c                          # 0 means the default window, which is 4
+
+
 def _degenerate_scene(ptc, standins):
     """Cornell plus geometry that stresses ties and degeneracy: exact duplicates (equal t: the smaller triangle id must win),
     zero-area triangles, a sliver, coplanar overlapping quads, and a far-away huge triangle that stretches the scene box
