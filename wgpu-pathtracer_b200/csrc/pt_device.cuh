@@ -47,8 +47,15 @@ PT_HD void st4_stream(F4* p, float x, float y, float z, float w) { p->x = x; p->
 // l1tex__data_pipe_lsu_wavefronts at 60-80 % of peak), so a BVH node is one such load and a triangle two.
 PT_HD void ld8(const F4* p, F4& a, F4& b) {
 #if defined(__CUDA_ARCH__) && !defined(PTC_NO_LDG256)
+    // leaf triangles are read with the L1 evict-first priority: a triangle record is rarely needed again soon, the nodes above it
+    // are (+1 % on Sponza, classroom and San Miguel 4K, profiles/r02zk_ab_evict.log; evict-last on the node loads: -0.5 %)
+#if !defined(PTC_TRI_NO_EVICT_FIRST)
+    asm("ld.global.nc.L1::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#endif
 #else
     a = ld4(p); b = ld4(p + 1);
 #endif
@@ -57,8 +64,13 @@ struct alignas(32) NodeQ { uint32_t w[8]; };      // device BVH2 node (layout: b
 PT_HD NodeQ ld_node(const NodeQ* p) {
     NodeQ n;
 #if defined(__CUDA_ARCH__) && !defined(PTC_NO_LDG256)
+#if defined(PTC_NODE_EVICT_LAST)
+    asm("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(n.w[0]), "=r"(n.w[1]), "=r"(n.w[2]), "=r"(n.w[3]), "=r"(n.w[4]), "=r"(n.w[5]), "=r"(n.w[6]), "=r"(n.w[7]) : "l"(p));
+#else
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(n.w[0]), "=r"(n.w[1]), "=r"(n.w[2]), "=r"(n.w[3]), "=r"(n.w[4]), "=r"(n.w[5]), "=r"(n.w[6]), "=r"(n.w[7]) : "l"(p));
+#endif
 #elif defined(__CUDA_ARCH__)
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
     n.w[0] = a.x; n.w[1] = a.y; n.w[2] = a.z; n.w[3] = a.w; n.w[4] = b.x; n.w[5] = b.y; n.w[6] = b.z; n.w[7] = b.w;
