@@ -171,7 +171,11 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
         if (idle == FULL || (!exhausted && __popc(idle) >= PTC_REFILL_VOTE)) {
             // ---- retire finished rays, refill idle lanes ----
             if (node == PTC_SENTINEL && ray != kNoRay) {
+#ifndef PTC_TRACE_QUEUE_NO_STREAM
+                if (!ANY) __stcs(reinterpret_cast<uint4*>(hits) + ray, make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri));
+#else
                 if (!ANY) reinterpret_cast<uint4*>(hits)[ray] = make_uint4(__float_as_uint(best.t), __float_as_uint(best.b1), __float_as_uint(best.b2), best.tri);
+#endif
                 else if (best.tri == 0xFFFFFFFFu) {
                     const F4 c = ld4_stream(contrib + ray);
                     F4* a = acc + __float_as_uint(best.b1);                // the slot travelled in best.b1
@@ -189,7 +193,11 @@ __global__ void __launch_bounds__(kTraceThreads, MINB) k_trace(DevScene s, const
                 const uint32_t i = base + __popc(idle & lt);
                 if (node == PTC_SENTINEL && i < n) {
                     ray = i;
+#ifndef PTC_TRACE_QUEUE_NO_STREAM
+                    const F4 ro = ld4_stream(ray_o + i), rd = ld4_stream(ray_d + i);       // read once: streaming, they do not displace nodes in L1 (+0.3 % Sponza, +0.9 % classroom, profiles/r02zm_ab_trace_stream.log)
+#else
                     const F4 ro = ld4(ray_o + i), rd = ld4(ray_d + i);
+#endif
                     o = pt_mk3(ro.x, ro.y, ro.z); d = pt_mk3(rd.x, rd.y, rd.z);
                     r = make_ray_slab(s, o, d);
                     best.t = ANY ? rd.w : PT_RAY_TMAX; best.b1 = ANY ? ro.w : 0.0f; best.b2 = 0.0f; best.tri = 0xFFFFFFFFu;
