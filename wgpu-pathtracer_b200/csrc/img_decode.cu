@@ -118,9 +118,9 @@ int decode_png(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
     {
         z_stream zs; std::memset(&zs, 0, sizeof(zs));
         if (inflateInit(&zs) != Z_OK) { err = "zlib inflateInit failed"; return 1; }
+        if (idat.size() > 0xFFFFFFFFull || raw.size() > 0xFFFFFFFFull) { inflateEnd(&zs); err = "PNG too large"; return 1; }
         zs.next_in = idat.data(); zs.avail_in = (uInt)idat.size();
         zs.next_out = raw.data(); zs.avail_out = (uInt)raw.size();
-        if (idat.size() > 0xFFFFFFFFull || raw.size() > 0xFFFFFFFFull) { inflateEnd(&zs); err = "PNG too large"; return 1; }
         const int rc = inflate(&zs, Z_FINISH);
         const bool full = zs.avail_out == 0;
         inflateEnd(&zs);
@@ -438,10 +438,10 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
     std::vector<uint8_t> raw;
     for (int64_t k = 0; k < nchunks; ++k) {
         const uint64_t at = le64(d + p + (size_t)k * 8);
-        if (at + 8 > n) { err = "bad OpenEXR chunk offset"; return 1; }
-        const int y0 = (int)le32(d + at) - dw[1];
+        if (at > n || n - at < 8) { err = "bad OpenEXR chunk offset"; return 1; }
+        const int64_t y0 = (int64_t)(int32_t)le32(d + at) - dw[1];
         const uint32_t csz = le32(d + at + 4);
-        if (y0 < 0 || y0 >= H || at + 8 + csz > n) { err = "bad OpenEXR chunk"; return 1; }
+        if (y0 < 0 || y0 >= H || (uint64_t)csz > n - at - 8) { err = "bad OpenEXR chunk"; return 1; }
         const int rows = (int)std::min<int64_t>(lines, H - y0);
         const size_t want = row_bytes * (size_t)rows;
         raw.resize(want);
