@@ -8,7 +8,12 @@
  * return 0 (PTC_OK) or a negative `enum ptc_status`; the message for the last
  * failure on the calling thread is `ptc_last_error()`.  Nothing here ever
  * falls back to a CPU implementation: without a CUDA device, ptc_create
- * fails with PTC_ERR_NO_DEVICE.
+ * fails with PTC_ERR_NO_DEVICE.  No C++ exception crosses this boundary and
+ * nothing aborts: host allocation failures come back as PTC_ERR_OOM, damaged
+ * scene files and inconsistent arrays as PTC_ERR_INVALID / PTC_ERR_PARSE with
+ * a message (the Rust shim turns them into the reference's panics).
+ * Triangles with a non-finite corner, or a coordinate beyond 1e37, are
+ * inactive (never hit), as in the reference's Vulkan acceleration structures.
  *
  * The host-side helpers at the bottom (camera, scene ingest) restate
  * src/camera.rs and src/scene.rs so a caller without the Rust crate can

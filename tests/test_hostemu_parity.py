@@ -251,3 +251,38 @@ def test_packet_traversal_same_hits(ptc, standins, oracle, hostemu, which):
     assert np.array_equal(hits, ref)
     if which == "sponza_tiles":
         assert stats[0] / (len(rays) / 32) < 90                          # even at this low resolution a tile visits ~2x what one ray does (1.2x at 1080p)
+
+
+@pytest.mark.parametrize("build", ["sah", "lbvh", "ploc"])
+def test_inactive_triangles_do_not_change_the_image(ptc, standins, hostemu, build):
+    """Triangles with a NaN / infinite / beyond-1e37 corner are inactive, as in the acceleration structures the reference
+    builds (a NaN position makes a Vulkan triangle inactive; pt.rs:391-433 passes the vertex buffer on unchanged): never
+    hit, and harmless to every builder (found by tools/fuzz_scene.cpp: the SAH binning converted a NaN to int).  The scene
+    with such a mesh appended renders bit-identically to the scene without it; numbering of the other meshes is unchanged."""
+    T = ptc.types
+    kind = {"sah": T.BVH_SAH_HOST, "lbvh": T.BVH_LBVH_DEVICE, "ploc": T.BVH_PLOC_DEVICE}[build]
+    clean, cam = standins.cornell()
+    dirty, _ = standins.cornell()
+    bad = np.array([[np.nan, 0.5, 0.0], [1.0, 0.5, 0.5], [1.0, 1.0, 0.0],            # NaN corner
+                    [1.0, np.inf, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.0],            # +inf
+                    [1.0, 0.2, 0.0], [-np.inf, 0.5, 0.5], [1.5, 1.0, 0.3],           # -inf
+                    [3e38, 0.2, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.3],              # finite, but edges overflow fp32
+                    [1.0, 0.2, 0.0], [1.0, -2e37, 0.5], [1.5, 1.0, 0.3]], np.float32)
+    dirty.add_mesh(bad, np.tile([0, 1, 0], (len(bad), 1)), None, np.arange(len(bad)), 0)
+    W, H = 96, 96
+    cfg = ptc.make_config(W, H, max_bounces=4, bvh_build=kind)
+    camera = standins.make_camera(cam, W, H)
+    a, b = hostemu.scene(clean, cfg), hostemu.scene(dirty, cfg)
+    assert b.bvh_info()["triangles"] == a.bvh_info()["triangles"] + 5                      # the five triangles are in the tree's arrays, just never hit
+    u = camera.uniforms(frame=1)
+    ra, rb = a.render_frame(u), b.render_frame(u)
+    for k in ("hit_id", "color", "depth", "normal", "albedo"):
+        assert np.array_equal(ra[k], rb[k], equal_nan=True), k
+    assert ra["rays"] == rb["rays"]
+    # rays aimed straight at where the finite corners of the inactive triangles are: same answers too
+    from conftest import random_rays
+    rays = random_rays(4000, seed=11, extent=2.5)
+    ha, ia = a.trace_rays(rays)
+    hb, ib = b.trace_rays(rays)
+    assert np.array_equal(ha, hb) and np.array_equal(ia, ib)
+    assert int((ib[:, 0] == len(dirty.meshes) - 1).sum()) == 0

@@ -411,3 +411,72 @@ def test_ptrender_loads_a_textured_obj(ptc, standins, tmp_path, env_format):
     step.destroy()
     assert np.array_equal(got, ref)
     assert len(np.unique(np.round(got[..., :3], 3).reshape(-1, 3), axis=0)) > 500          # textured, not flat
+
+
+# ---- hostile headers and the mutation fuzzer (tools/fuzz_decode.cpp) -----------------------------------------------------
+def test_headers_that_promise_more_than_the_file_holds(ptc):
+    """Scene files are untrusted: a few bytes must not make the library allocate gigabytes, overflow its size arithmetic
+    or throw across the C ABI (each case below was found by tools/fuzz.sh or by reading the size arithmetic)."""
+    import resource
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body) & 0xFFFFFFFF)
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    # PNG: 30000 x 30000 RGBA16 (7.2 GB of scan-lines) behind 11 bytes of image data
+    huge_png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 30000, 30000, 16, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 3)) + chunk(b"IEND", b"")
+    rc, msg = lib_decode(ptc, huge_png)
+    assert rc != 0 and "too short" in msg, msg
+    # PFM: dimensions whose product wraps around 2^64 to a small number
+    for header in (b"PF\n9223372036854775807 9223372036854775807\n-1\n", b"PF\n4294967296 4294967296\n-1\n", b"PF\n99999999999999999999 3\n-1\n"):
+        rc, msg = lib_decode(ptc, header + b"\0" * 64)
+        assert rc != 0 and "PFM" in msg, msg
+    # OpenEXR: a dataWindow of 2^31 x 2^31 (the product overflows int64 arithmetic), and one of 30000 x 30000 in a 400-byte file
+    def exr(dw, compression):
+        def attr(name, typ, val):
+            return name + b"\0" + typ + b"\0" + struct.pack("<I", len(val)) + val
+        chlist = b"".join(n + b"\0" + struct.pack("<IBBBBII", 2, 0, 0, 0, 0, 1, 1) for n in (b"B", b"G", b"R")) + b"\0"
+        head = struct.pack("<II", 20000630, 2) + attr(b"channels", b"chlist", chlist) + attr(b"compression", b"compression", bytes([compression])) \
+            + attr(b"dataWindow", b"box2i", struct.pack("<iiii", *dw)) + b"\0"
+        return head + b"\0" * 256
+    rc, msg = lib_decode(ptc, exr((-2 ** 31, -2 ** 31, 2 ** 31 - 1, 2 ** 31 - 1), 0))
+    assert rc != 0 and "bad OpenEXR header" in msg, msg
+    for compression in (0, 3, 4):
+        rc, msg = lib_decode(ptc, exr((0, 0, 29999, 29999), compression))
+        assert rc != 0 and ("too short" in msg or "truncated" in msg), msg
+    # none of the refusals allocated the promised image (ru_maxrss is in KB)
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 512 * 1024
+
+
+def _fuzz_build(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fuzz_decode")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", f"-I{cuda}/include",
+           "-x", "c++", os.path.join(root, "wgpu-pathtracer_b200", "csrc", "img_decode.cu"), "-x", "c++", os.path.join(root, "tools", "fuzz_decode.cpp"),
+           "-o", exe, f"-L{cuda}/lib64", "-lcudart", "-lz", "-ldl", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no AddressSanitizer build of the decoders here: " + r.stderr[-300:])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:max_allocation_size_mb=2048", LD_LIBRARY_PATH=f"{cuda}/lib64:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return root, exe, env
+
+
+def test_decoders_under_the_mutation_fuzzer(ptc, tmp_path):
+    """The seed corpus (tools/fuzz_seeds.py: every PNG colour type / bit depth / Adam7, EXR NONE / ZIPS / ZIP / PIZ in HALF and
+    FLOAT with both wavelets, both PFM flavours) decodes through the built library, and 30 000 structure-aware mutations of
+    it run through an AddressSanitizer + UBSan build of the same decoders without a report.  Long runs: tools/fuzz.sh."""
+    _cv2_exr()
+    import importlib.util
+    root, exe, env = _fuzz_build(tmp_path)
+    spec = importlib.util.spec_from_file_location("fuzz_seeds", os.path.join(root, "tools", "fuzz_seeds.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    names = mod.main(str(tmp_path / "seeds"))
+    assert len(names) >= 39
+    for n in names:
+        rc, got = lib_decode(ptc, open(tmp_path / "seeds" / n, "rb").read())
+        assert rc == 0, (n, got)
+    files = [str(tmp_path / "seeds" / n) for n in names]
+    r = subprocess.run([exe, "30000", "7"] + files, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert "0 sanitizer reports" in r.stdout and " 30000 inputs" in r.stdout
+    decoded = int(r.stdout.split(" inputs, ")[1].split(" decoded")[0])
+    assert 1000 < decoded < 29000        # the mutations neither all bounce off a checksum nor all pass through unchanged

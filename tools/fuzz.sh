@@ -1,0 +1,33 @@
+#!/bin/bash
+# fuzz.sh <decode|obj|scene|all> [iterations-per-seed] [rng-seeds...] — AddressSanitizer + UBSan builds of the library's
+# host code that reads untrusted input, driven by the mutation fuzzers next to this script.  No GPU needed.
+#   decode : csrc/img_decode.cu (PNG, OpenEXR, PFM; compiled as host C++ — the file holds no device code; nvJPEG parses JPEG
+#            itself and is not exercised)                                      tools/fuzz_decode.cpp + tools/fuzz_seeds.py
+#   obj    : csrc/pt_host.cpp (OBJ / MTL text -> scene arrays, tobj-4.0.3 semantics)            tools/fuzz_obj.cpp
+#   scene  : csrc/scene_prep.cpp + csrc/bvh_build.cpp + the traversal of pt_device.cuh on the host (hostile scene views:
+#            broken tables, degenerate / coincident / non-finite geometry, three builders)       tools/fuzz_scene.cpp
+# A sanitizer report or a violated invariant ends the run with a non-zero exit code.  Last long run: profiles/r02zn_fuzz.log
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"; root="$(dirname "$here")"; csrc="$root/wgpu-pathtracer_b200/csrc"
+work="${FUZZ_DIR:-/tmp/ptc_fuzz}"; mkdir -p "$work"
+what="${1:-all}"; shift || true
+iters="${1:-}"; shift || true
+seeds=("$@"); [ ${#seeds[@]} -eq 0 ] && seeds=(1 2 3)
+cuda="${CUDA_HOME:-/usr/local/cuda}"
+san="-std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer -pthread"
+export LD_LIBRARY_PATH="$cuda/lib64:${LD_LIBRARY_PATH:-}" ASAN_OPTIONS=detect_leaks=1:max_allocation_size_mb=2048
+
+if [ "$what" = decode ] || [ "$what" = all ]; then
+    g++ $san -I"$cuda/include" -x c++ "$csrc/img_decode.cu" -x c++ "$here/fuzz_decode.cpp" -o "$work/fuzz_decode" -L"$cuda/lib64" -lcudart -lz -ldl
+    python "$here/fuzz_seeds.py" "$work/seeds"
+    for s in "${seeds[@]}"; do "$work/fuzz_decode" "${iters:-300000}" "$s" "$work"/seeds/*; done
+fi
+if [ "$what" = obj ] || [ "$what" = all ]; then
+    g++ $san -I"$cuda/include" "$csrc/pt_host.cpp" -x c++ "$csrc/img_decode.cu" -x c++ "$here/fuzz_obj.cpp" -o "$work/fuzz_obj" -L"$cuda/lib64" -lcudart -lz -ldl
+    for s in "${seeds[@]}"; do "$work/fuzz_obj" "${iters:-200000}" "$s"; done
+fi
+if [ "$what" = scene ] || [ "$what" = all ]; then
+    # -ffp-contract=off -mavx2 -mfma: the flags of tests/hostemu (explicit fmaf only, as in the device build)
+    g++ $san -ffp-contract=off -mavx2 -mfma -Wno-unused-function "$here/fuzz_scene.cpp" "$csrc/scene_prep.cpp" "$csrc/bvh_build.cpp" -o "$work/fuzz_scene"
+    for s in "${seeds[@]}"; do "$work/fuzz_scene" "${iters:-5000}" "$s"; done
+fi

@@ -24,6 +24,10 @@ constexpr size_t kTopNodes = 128;        // inner nodes numbered breadth-first a
 
 struct Prim { float lo[3], hi[3], c[3]; uint32_t id; };
 
+// bin of a scaled centroid offset; coordinates near FLT_MAX make the scale 0 or the offset infinite, and a NaN or an
+// out-of-range value must not reach the float -> int conversion (undefined): those land in bin 0 / the last bin
+inline int bin_of(float x) { return x >= 0.0f ? (x < (float)kBins ? (int)x : kBins - 1) : 0; }
+
 // f(begin, end) over [0, n) on the host threads: the per-triangle and per-node loops around the build proper
 template <class F>
 void par_for(uint64_t n, int nthreads, F f) {
@@ -85,7 +89,7 @@ struct Builder {
             for (int b = 0; b < kBins; ++b) { bb[b].reset(); bn[b] = 0; }
             float k = (float)kBins / ext;
             for (uint32_t i = first; i < first + count; ++i) {
-                int b = (int)((prims[i].c[a] - cb.lo[a]) * k); if (b > kBins - 1) b = kBins - 1;
+                const int b = bin_of((prims[i].c[a] - cb.lo[a]) * k);
                 bb[b].grow(prims[i].lo, prims[i].hi); bn[b]++;
             }
             float right_area[kBins]; uint32_t right_n[kBins];
@@ -112,8 +116,7 @@ struct Builder {
             if (count <= max_leaf && leaf_cost <= split_cost) return 0;
             float ext = cb.hi[best_axis] - cb.lo[best_axis], k = (float)kBins / ext, base = cb.lo[best_axis];
             auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
-                int b = (int)((p.c[best_axis] - base) * k); if (b > kBins - 1) b = kBins - 1;
-                return b <= best_split;
+                return bin_of((p.c[best_axis] - base) * k) <= best_split;
             });
             mid = (uint32_t)(it - prims.begin());
             if (mid == first || mid == first + count) mid = first + count / 2;
@@ -279,6 +282,8 @@ void emit_bvh2(const Bvh2& bvh, const float* tri_pos, DevBvh2& out) {
         for (int a = 0; a < 3; ++a) {
             double lo = ((double)b.lo[a] - (double)bvh.pad - (double)out.grid.base[a]) / step[a];
             double hi = ((double)b.hi[a] + (double)bvh.pad - (double)out.grid.base[a]) / step[a];
+            if (!(lo > -8.0)) lo = -8.0;                           // out of the grid or NaN: the whole axis (conservative), and the
+            if (!(hi < 40000.0)) hi = 40000.0;                     // conversion below stays defined
             long ql = (long)std::floor(lo) - 1, qh = (long)std::ceil(hi) + 1;
             ql = std::min(std::max(ql, 0l), 32767l); qh = std::min(std::max(qh, 0l), 32767l);
             d.w[c * 4 + a] = (0x8000u | (uint32_t)ql) | ((0x8000u | (uint32_t)qh) << 16);

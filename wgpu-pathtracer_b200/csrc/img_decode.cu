@@ -114,6 +114,9 @@ int decode_png(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
             raw_bytes += (size_t)h * (rowbytes_of(w) + 1);
         }
     }
+    // deflate never expands by more than 1032 : 1: an IHDR that promises more than the IDAT bytes can hold is refused before
+    // anything of the promised size is allocated (a 100-byte file cannot ask for gigabytes)
+    if (raw_bytes / 1040 > idat.size()) { err = "PNG image data too short for its IHDR"; return 1; }
     std::vector<uint8_t> raw(raw_bytes);
     {
         z_stream zs; std::memset(&zs, 0, sizeof(zs));
@@ -177,7 +180,7 @@ int decode_pfm(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
     if (!token(t)) { err = "bad PFM header"; return 1; }
     scale = std::atof(t.c_str());
     ++p;                                              // the single whitespace byte after the scale
-    if (vals[0] <= 0 || vals[1] <= 0 || (uint64_t)vals[0] * (uint64_t)vals[1] > (1ull << 30) || scale == 0.0) { err = "bad PFM header"; return 1; }
+    if (vals[0] <= 0 || vals[1] <= 0 || vals[0] > (1l << 30) || vals[1] > (1l << 30) || (uint64_t)vals[0] * (uint64_t)vals[1] > (1ull << 30) || scale == 0.0) { err = "bad PFM header"; return 1; }
     const size_t W = (size_t)vals[0], H = (size_t)vals[1];
     if (n < p || n - p < W * H * ch * 4) { err = "truncated PFM"; return 1; }
     const bool little = scale < 0.0;
@@ -414,7 +417,7 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
         else if (!std::strcmp(name, "dataWindow") && sz >= 16) for (int k = 0; k < 4; ++k) dw[k] = (int)le32(v + 4 * k);
     }
     const int64_t W = (int64_t)dw[2] - dw[0] + 1, H = (int64_t)dw[3] - dw[1] + 1;
-    if (ch.empty() || W <= 0 || H <= 0 || W * H > (1ll << 30)) { err = "bad OpenEXR header (channels / dataWindow)"; return 1; }
+    if (ch.empty() || W <= 0 || H <= 0 || W > (1ll << 30) || H > (1ll << 30) || W * H > (1ll << 30)) { err = "bad OpenEXR header (channels / dataWindow)"; return 1; }
     int lines;
     switch (compression) { case 0: case 2: lines = 1; break; case 3: lines = 16; break; case 4: lines = 32; break;
         default: err = "unsupported OpenEXR compression (only NONE, ZIPS, ZIP and PIZ)"; return 1; }
@@ -432,6 +435,9 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
     if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0) { err = "OpenEXR image without R, G, B (or Y) channels"; return 1; }
     std::vector<size_t> chan_off(ch.size());
     { size_t o = 0; for (size_t c = 0; c < ch.size(); ++c) { chan_off[c] = o; o += (size_t)W * (ch[c].type == 1 ? 2 : 4); } }
+    // same plausibility bound as for PNG: stored rows need their own size in the file, deflate stays below 1032 : 1 and PIZ's
+    // run-length codes below 408 : 1, so a dataWindow the file cannot fill is refused before the image is allocated
+    if ((uint64_t)row_bytes * (uint64_t)H / (compression == 0 ? 1u : 1040u) > n) { err = "OpenEXR file too short for its dataWindow"; return 1; }
     out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA32F;
     out.texels.assign((size_t)W * H * 16, 0);
     float* px = reinterpret_cast<float*>(out.texels.data());

@@ -628,8 +628,10 @@ int ingest_unchecked(ptc_scene* s, const std::vector<TobjModel>& models, const s
 extern "C" {
 
 PTC_API int ptc_scene_new(const char* envmap_path, ptc_scene** out) {                     // scene.rs:77-122
+    return ptc::guarded("ptc_scene_new", [&]() -> int {
     if (!out) { set_error("null argument"); return PTC_ERR_INVALID; }
-    ptc_scene* s = new ptc_scene();
+    std::unique_ptr<ptc_scene> owner(new ptc_scene());
+    ptc_scene* s = owner.get();
     push_color(s, 1.0f, 1.0f, 1.0f, 1.0f);      // 0 albedo default
     push_scalar(s, 0.99f);                      // 1 roughness default
     push_color(s, 0.5f, 0.5f, 0.5f, 1.0f);      // 2 specular default
@@ -644,8 +646,9 @@ PTC_API int ptc_scene_new(const char* envmap_path, ptc_scene** out) {           
     m.albedo_texture_idx = 0; m.roughness_texture_idx = 1; m.specular_texture_idx = 2; m.metallic_texture_idx = 3;
     m.emissive_texture_idx = 4; m.sheen_texture_idx = 5; m.normal_texture_idx = 6; m.transmission_texture_idx = 7; m.ior_texture_idx = 8;
     s->materials.push_back(m);
-    *out = s;
+    *out = owner.release();
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_scene_set_fix_normals(ptc_scene* s, int enable) {
@@ -654,15 +657,18 @@ PTC_API int ptc_scene_set_fix_normals(ptc_scene* s, int enable) {
 }
 
 PTC_API int ptc_scene_load_obj_text(ptc_scene* s, const char* obj_text, const char* mtl_text, const char* obj_dir) {
+    return ptc::guarded("ptc_scene_load_obj_text", [&]() -> int {
     if (!s || !obj_text) { set_error("null argument"); return PTC_ERR_INVALID; }
     std::vector<TobjModel> models; std::vector<TobjMaterial> mats;
     std::string dir = obj_dir ? obj_dir : "";
     int rc = parse_obj(obj_text, mtl_text ? mtl_text : "", mtl_text != nullptr, dir, models, mats);
     if (rc) return rc;
     return ingest(s, models, mats, dir);
+    });
 }
 
 PTC_API int ptc_scene_load_obj(ptc_scene* s, const char* obj_path) {                      // scene.rs:124-128
+    return ptc::guarded("ptc_scene_load_obj", [&]() -> int {
     if (!s || !obj_path) { set_error("null argument"); return PTC_ERR_INVALID; }
     std::ifstream f(obj_path, std::ios::binary);
     if (!f) { set_error(std::string("Failed to load OBJ ") + obj_path); return PTC_ERR_IO; }
@@ -674,6 +680,7 @@ PTC_API int ptc_scene_load_obj(ptc_scene* s, const char* obj_path) {            
     int rc = parse_obj(text, "", false, dir, models, mats);
     if (rc) return rc;
     return ingest(s, models, mats, dir);
+    });
 }
 
 PTC_API uint64_t ptc_scene_num_textures(const ptc_scene* s) { return s ? s->textures.size() : 0; }
@@ -689,12 +696,14 @@ PTC_API int ptc_scene_texture_info_at(const ptc_scene* s, uint64_t i, ptc_scene_
 }
 
 PTC_API int ptc_scene_set_texels(ptc_scene* s, uint64_t i, uint32_t w, uint32_t h, uint32_t format, const void* texels) {
+    return ptc::guarded("ptc_scene_set_texels", [&]() -> int {
     if (!s || !texels || i >= s->textures.size() || w == 0 || h == 0 || format > PTC_TEXEL_RGBA32F) { set_error("bad texel upload"); return PTC_ERR_INVALID; }
     SceneTexture& t = s->textures[i];
     size_t bytes = (size_t)w * h * (format == PTC_TEXEL_RGBA8 ? 4 : 16);
     t.texels.assign((const uint8_t*)texels, (const uint8_t*)texels + bytes);
     t.width = w; t.height = h; t.format = format;
     return PTC_OK;
+    });
 }
 
 // Texture::load for every file-backed texture that has no texels yet (texture.rs:232-243), on n_threads host threads as
@@ -722,6 +731,7 @@ static int decode_bytes(const uint8_t* data, size_t n, int cuda_device, std::uni
     }
 }
 PTC_API int ptc_scene_decode_textures(ptc_scene* s, int cuda_device, int n_threads) {
+    return ptc::guarded("ptc_scene_decode_textures", [&]() -> int {
     if (!s) { set_error("null scene"); return PTC_ERR_INVALID; }
     std::vector<size_t> todo;
     for (size_t i = 0; i < s->textures.size(); ++i) if (s->textures[i].source == PTC_TEX_FILE && s->textures[i].texels.empty()) todo.push_back(i);
@@ -738,22 +748,29 @@ PTC_API int ptc_scene_decode_textures(ptc_scene* s, int cuda_device, int n_threa
             if (k >= todo.size()) break;
             SceneTexture& t = s->textures[todo[k]];
             ptc::DecodedImage img; std::string err;
-            int rc = read_file(t.path, bytes);
-            if (rc) err = "cannot read the file";
-            else rc = decode_bytes(bytes.data(), bytes.size(), cuda_device, jpeg, img, err);
+            int rc = 1;
+            try {                                                 // a worker thread must not let an exception escape (std::terminate)
+                rc = read_file(t.path, bytes);
+                if (rc) err = "cannot read the file";
+                else rc = decode_bytes(bytes.data(), bytes.size(), cuda_device, jpeg, img, err);
+            } catch (const std::bad_alloc&) { rc = 1; err = "out of host memory"; }
+            catch (const std::exception& e) { rc = 1; err = e.what(); }
             if (rc) { std::lock_guard<std::mutex> l(mu); if (first_error.empty()) first_error = "texture " + t.path + ": " + err; continue; }
             t.texels.swap(img.texels); t.width = img.width; t.height = img.height; t.format = img.format;
         }
     };
     std::vector<std::thread> th;
-    for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
+    try { for (int i = 1; i < n_threads; ++i) th.emplace_back(worker); }
+    catch (const std::exception&) {}                              // fewer threads than asked for: the started ones and this one finish the list
     worker();
     for (auto& x : th) x.join();
     if (!first_error.empty()) { set_error(first_error); return PTC_ERR_INVALID; }
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_decode_image(const void* data, size_t bytes, int cuda_device, uint32_t* width, uint32_t* height, uint32_t* format, void** texels) {
+    return ptc::guarded("ptc_decode_image", [&]() -> int {
     if (!data || !width || !height || !format || !texels) { set_error("null argument"); return PTC_ERR_INVALID; }
     std::unique_ptr<ptc::JpegDecoder> jpeg; ptc::DecodedImage img; std::string err;
     if (decode_bytes((const uint8_t*)data, bytes, cuda_device, jpeg, img, err)) { set_error(err); return PTC_ERR_INVALID; }
@@ -762,10 +779,12 @@ PTC_API int ptc_decode_image(const void* data, size_t bytes, int cuda_device, ui
     std::memcpy(p, img.texels.data(), img.texels.size());
     *width = img.width; *height = img.height; *format = img.format; *texels = p;
     return PTC_OK;
+    });
 }
 PTC_API void ptc_free(void* p) { std::free(p); }
 
 PTC_API int ptc_scene_get_view(const ptc_scene* cs, ptc_scene_view* out) {
+    return ptc::guarded("ptc_scene_get_view", [&]() -> int {
     ptc_scene* s = const_cast<ptc_scene*>(cs);
     if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
     s->descs.resize(s->textures.size());
@@ -782,6 +801,7 @@ PTC_API int ptc_scene_get_view(const ptc_scene* cs, ptc_scene_view* out) {
     out->materials = s->materials.data(); out->num_materials = s->materials.size();
     out->textures = s->descs.data(); out->num_textures = s->descs.size();
     return PTC_OK;
+    });
 }
 
 PTC_API void ptc_scene_free(ptc_scene* s) { delete s; }

@@ -482,10 +482,11 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
     if (ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return PTC_ERR_NO_DEVICE; }
     if (cuda_device < 0 || cuda_device >= ndev) { set_error("cuda_device out of range"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(cuda_device));
-    ptc_step* s = new ptc_step();
+    ptc_step* s = new (std::nothrow) ptc_step();
+    if (!s) { set_error("ptc_create: out of host memory"); return PTC_ERR_OOM; }
     s->device = cuda_device; s->cfg = *config;
     int rc = PTC_OK;
-    do {
+    try { do {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);         // numerically lower = higher priority
         { const char* e = getenv("PTC_PARTS"); if (e && atoi(e) >= 1) s->want_parts = (uint32_t)atoi(e); }
@@ -530,7 +531,10 @@ PTC_API int ptc_create(const ptc_scene_view* scene, const ptc_config* config, in
             e = getenv("PTC_SHADE_CTAS"); if (e && atoi(e) >= 1) s->shade_grid = std::min(s->shade_grid, sms * atoi(e));
         }
         if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("create: stream sync failed"); rc = PTC_ERR_CUDA; break; }
-    } while (0);
+    } while (0); }
+    // host-side allocations (scene preparation, BVH build) must not throw across the C ABI
+    catch (const std::bad_alloc&) { set_error("ptc_create: out of host memory"); rc = PTC_ERR_OOM; }
+    catch (const std::exception& e) { set_error(std::string("ptc_create: ") + e.what()); rc = PTC_ERR_INVALID; }
     if (rc != PTC_OK) { destroy_step(s); return rc; }
     *out = s;
     return PTC_OK;
@@ -644,6 +648,7 @@ PTC_API int ptc_poll(ptc_step* s, int wait) {
 }
 
 PTC_API int ptc_resize(ptc_step* s, uint32_t w, uint32_t h) {
+    return ptc::guarded("ptc_resize", [&]() -> int {
     if (!s) { set_error("null step"); return PTC_ERR_INVALID; }
     // validate BEFORE anything is freed: a bad size leaves the step exactly as it was
     if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull) { set_error("bad frame size"); return PTC_ERR_INVALID; }
@@ -666,6 +671,7 @@ PTC_API int ptc_resize(ptc_step* s, uint32_t w, uint32_t h) {
     s->invalid = false;
     CK(cudaStreamSynchronize(s->stream));
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_set_output(ptc_step* s, void* device_rgba32f) {
@@ -762,6 +768,7 @@ PTC_API int ptc_write(ptc_step* s, int plane, const void* src, size_t pitch) {
 }
 
 PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
+    return ptc::guarded("ptc_read", [&]() -> int {
     if (!s || !dst) { set_error("null argument"); return PTC_ERR_INVALID; }
     void* src; size_t pb;
     if (!plane_ptr(s, plane, &src, &pb)) { set_error("unknown plane, or a display-path plane that has not been produced yet"); return PTC_ERR_INVALID; }
@@ -788,6 +795,7 @@ PTC_API int ptc_read(ptc_step* s, int plane, void* dst, size_t pitch) {
     CK(cudaMemcpy2DAsync(dst, pitch ? pitch : row, src, row, row, H, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_read_async(ptc_step* s, int plane, void* dst_pinned) {
@@ -888,6 +896,7 @@ static int upload_rays(ptc_step* s, const float* rays, uint64_t n, F4** d_o, F4*
 }
 
 PTC_API int ptc_trace_rays(ptc_step* s, const float* rays, uint64_t n, uint32_t* hits, uint32_t* ids) {
+    return ptc::guarded("ptc_trace_rays", [&]() -> int {
     if (!s || !rays || !hits) { set_error("null argument"); return PTC_ERR_INVALID; }
     if (n == 0) return PTC_OK;
     if (n > 0x7fffffffull) { set_error("too many rays"); return PTC_ERR_INVALID; }
@@ -917,9 +926,11 @@ PTC_API int ptc_trace_rays(ptc_step* s, const float* rays, uint64_t n, uint32_t*
     for (uint64_t i = 0; i < n; ++i)
         if (hits[i * 4 + 3] == 0xFFFFFFFFu) hits[i * 4] = hits[i * 4 + 1] = hits[i * 4 + 2] = 0;   // miss: t,b1,b2 reported as 0
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_trace_rays_any(ptc_step* s, const float* rays, uint64_t n, uint8_t* occluded) {
+    return ptc::guarded("ptc_trace_rays_any", [&]() -> int {
     if (!s || !rays || !occluded) { set_error("null argument"); return PTC_ERR_INVALID; }
     if (n == 0) return PTC_OK;
     if (n > 0x7fffffffull) { set_error("too many rays"); return PTC_ERR_INVALID; }
@@ -939,6 +950,7 @@ PTC_API int ptc_trace_rays_any(ptc_step* s, const float* rays, uint64_t n, uint8
     }
     cudaFree(d_o); cudaFree(d_d); cudaFree(d_occ); cudaFree(d_cur);
     return rc;
+    });
 }
 
 PTC_API int ptc_debug_math(int cuda_device, int fn, const float* a, const float* b, float* out, uint64_t n) {
@@ -1059,6 +1071,7 @@ static uint64_t fnv1a(const void* p, size_t n) {
     return h;
 }
 PTC_API int ptc_debug_bvh_hash(ptc_step* s, uint64_t out[2]) {
+    return ptc::guarded("ptc_debug_bvh_hash", [&]() -> int {
     if (!s || !out) { set_error("null argument"); return PTC_ERR_INVALID; }
     CK(cudaSetDevice(s->device));
     std::vector<unsigned char> nodes((size_t)s->bvh_info[2]), tris((size_t)s->bvh_info[3]);
@@ -1066,6 +1079,7 @@ PTC_API int ptc_debug_bvh_hash(ptc_step* s, uint64_t out[2]) {
     if (!tris.empty()) CK(cudaMemcpy(tris.data(), s->d_tris, tris.size(), cudaMemcpyDeviceToHost));
     out[0] = fnv1a(nodes.data(), nodes.size()); out[1] = fnv1a(tris.data(), tris.size());
     return PTC_OK;
+    });
 }
 
 PTC_API int ptc_debug_unorm8(int cuda_device, float* out512) {
