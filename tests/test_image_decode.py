@@ -480,3 +480,32 @@ def test_decoders_under_the_mutation_fuzzer(ptc, tmp_path):
     assert "0 sanitizer reports" in r.stdout and " 30000 inputs" in r.stdout
     decoded = int(r.stdout.split(" inputs, ")[1].split(" decoded")[0])
     assert 1000 < decoded < 29000        # the mutations neither all bounce off a checksum nor all pass through unchanged
+
+
+def test_host_allocation_failure_is_a_status_not_an_exception(ptc):
+    """No C++ exception crosses the C ABI ('never abort/throw across the ABI'): with the address space capped, a
+    valid 16000 x 16000 PNG whose 1 GB RGBA8 image cannot be allocated comes back as PTC_ERR_OOM with a message, and the
+    process lives on.  Run in a child process (ctypes only) so the limit does not touch the test session."""
+    import sys
+    lib = ptc._lib.lib()._name
+    script = r'''
+import ctypes as C, resource, struct, zlib, sys
+L = C.CDLL(sys.argv[1]); L.ptc_last_error.restype = C.c_char_p
+def chunk(t, d): return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+W = H = 16000
+raw = (b"\0" + b"\0" * W) * H
+png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 1)) + chunk(b"IEND", b"")
+del raw
+vm = int(open("/proc/self/statm").read().split()[0]) * resource.getpagesize()
+resource.setrlimit(resource.RLIMIT_AS, (vm + (700 << 20), vm + (700 << 20)))
+w, h, f, p = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_void_p()
+rc = L.ptc_decode_image(png, len(png), 0, C.byref(w), C.byref(h), C.byref(f), C.byref(p))
+print("RC", rc, L.ptc_last_error().decode())
+small = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 1, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0\x10\x20")) + chunk(b"IEND", b"")
+rc = L.ptc_decode_image(small, len(small), 0, C.byref(w), C.byref(h), C.byref(f), C.byref(p))
+print("AFTER", rc, w.value, h.value)
+'''
+    r = subprocess.run([sys.executable, "-c", script, lib], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert f"RC {ptc.types.ERR_OOM} ptc_decode_image: out of host memory" in r.stdout, r.stdout
+    assert "AFTER 0 2 1" in r.stdout                                   # the library still works afterwards
