@@ -93,6 +93,14 @@ def main(out):
             for iname, img in (("noise", noise), ("ramp", ramp)):
                 assert cv2.imwrite(os.path.join(out, f"{iname}_{cname}{half}.exr"), img, [cv2.IMWRITE_EXR_TYPE, t, cv2.IMWRITE_EXR_COMPRESSION, c])
     assert cv2.imwrite(os.path.join(out, "wide_piz1.exr"), wide, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION, comp["piz"]])
+    # 160 rows x 128 x RGBA float = 320 KB of scan-lines: above the size from which decode_exr spreads its chunks over threads
+    big = np.zeros((160, 128, 4), np.float32)
+    big[..., 0] = np.tile(np.arange(128, dtype=np.float32) / 128, (160, 1))
+    big[..., 1] = np.tile((np.arange(160, dtype=np.float32) / 160)[:, None], (1, 128))
+    big[..., 2] = big[..., 0] * big[..., 1]
+    big[..., 3] = 1.0
+    for cname in ("piz", "zip", "zips"):
+        assert cv2.imwrite(os.path.join(out, f"big_{cname}0.exr"), big, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, comp[cname]])
     assert cv2.imwrite(os.path.join(out, "grey_zip1.exr"), noise[..., 0].copy(), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION, comp["zip"]])
 
     put("rgb_le.pfm", b"PF\n5 3\n-1.0\n" + rng.random(45, dtype=np.float32).tobytes())

@@ -8,10 +8,12 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace ptc {
 
@@ -441,13 +443,14 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
     out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA32F;
     out.texels.assign((size_t)W * H * 16, 0);
     float* px = reinterpret_cast<float*>(out.texels.data());
-    std::vector<uint8_t> raw;
-    for (int64_t k = 0; k < nchunks; ++k) {
+    // chunks (1, 16 or 32 scan-lines) are independent: the large ones — the reference's environment map is 64 PIZ blocks of
+    // 4096 x 32 x 4 floats — are decoded on several host threads, each with its own scratch block
+    auto decode_chunk = [&](int64_t k, std::vector<uint8_t>& raw) -> const char* {
         const uint64_t at = le64(d + p + (size_t)k * 8);
-        if (at > n || n - at < 8) { err = "bad OpenEXR chunk offset"; return 1; }
+        if (at > n || n - at < 8) return "bad OpenEXR chunk offset";
         const int64_t y0 = (int64_t)(int32_t)le32(d + at) - dw[1];
         const uint32_t csz = le32(d + at + 4);
-        if (y0 < 0 || y0 >= H || (uint64_t)csz > n - at - 8) { err = "bad OpenEXR chunk"; return 1; }
+        if (y0 < 0 || y0 >= H || (uint64_t)csz > n - at - 8) return "bad OpenEXR chunk";
         const int rows = (int)std::min<int64_t>(lines, H - y0);
         const size_t want = row_bytes * (size_t)rows;
         raw.resize(want);
@@ -457,7 +460,7 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
         else if (compression == 2 || compression == 3) ok = zip_block(src, csz, raw.data(), want);
         else if (compression == 4) ok = piz_block(src, csz, raw.data(), want, (int)W, rows, ch);
         else ok = false;
-        if (!ok) { err = "OpenEXR chunk does not decompress"; return 1; }
+        if (!ok) return "OpenEXR chunk does not decompress";
         for (int r = 0; r < rows; ++r) {
             const uint8_t* row = raw.data() + (size_t)r * row_bytes;
             float* o = px + ((size_t)(y0 + r) * W) * 4;
@@ -468,7 +471,40 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
                 else for (int64_t x = 0; x < W; ++x) { const uint32_t u = le32(cp + x * 4); std::memcpy(&o[x * 4 + c4], &u, 4); }
             }
         }
+        return nullptr;
+    };
+    // two chunks that name the same rows would be written by two threads at once: such a file is decoded by one thread
+    // (last chunk wins, as before); a well-formed file names every block of rows exactly once
+    int nthreads = 1;
+    if (nchunks >= 4 && (uint64_t)row_bytes * (uint64_t)H >= (256u << 10)) {
+        std::vector<uint8_t> seen((size_t)nchunks, 0); bool distinct = true;
+        for (int64_t k = 0; k < nchunks && distinct; ++k) {
+            const uint64_t at = le64(d + p + (size_t)k * 8);
+            if (at > n || n - at < 8) { distinct = false; break; }
+            const int64_t y0 = (int64_t)(int32_t)le32(d + at) - dw[1];
+            if (y0 < 0 || y0 >= H || y0 % lines != 0 || seen[(size_t)(y0 / lines)]++) distinct = false;
+        }
+        if (distinct) nthreads = (int)std::min<int64_t>(std::min<int64_t>(nchunks, 16), std::max(1u, std::thread::hardware_concurrency()));
     }
+    std::atomic<int64_t> next{0};
+    std::atomic<const char*> failure{nullptr};
+    auto worker = [&] {
+        try {
+            std::vector<uint8_t> raw;
+            for (;;) {
+                const int64_t k = next.fetch_add(1);
+                if (k >= nchunks || failure.load() != nullptr) break;
+                if (const char* why = decode_chunk(k, raw)) { failure.store(why); break; }
+            }
+        } catch (const std::exception&) { failure.store("out of memory while decoding an OpenEXR chunk"); }
+    };
+    {
+        std::vector<std::thread> th;
+        try { for (int t = 1; t < nthreads; ++t) th.emplace_back(worker); } catch (const std::exception&) {}   // fewer threads: still correct
+        worker();
+        for (auto& t : th) t.join();
+    }
+    if (const char* why = failure.load()) { err = why; return 1; }
     return 0;
 }
 
