@@ -509,3 +509,33 @@ print("AFTER", rc, w.value, h.value)
     assert r.returncode == 0, r.stderr[-2000:]
     assert f"RC {ptc.types.ERR_OOM} ptc_decode_image: out of host memory" in r.stdout, r.stdout
     assert "AFTER 0 2 1" in r.stdout                                   # the library still works afterwards
+
+
+def test_png_reference_texture_sets(ptc):
+    """The reference's own PNG textures (res/san_miguel: 323 files, res/bistro: 622, and the small scenes; 1 GB in all, present
+    only where /root/reference is): 8-bit rgb / rgba / grey / palette and 1-bit palette / grey, two of them with a tRNS colour
+    key.  Every 9th file plus both colour-keyed ones decode to exactly OpenCV's (libpng) pixels — Pillow's for the colour-keyed
+    files, since OpenCV ignores tRNS on grey images while the reference's `image` crate expands it to alpha.  The whole set
+    was compared once the same way: 955 of 955 identical."""
+    import glob
+    import cv2
+    from PIL import Image
+    files = sorted(glob.glob("/root/reference/res/**/*.png", recursive=True))
+    if len(files) < 900:
+        pytest.skip("the reference checkout with its texture sets is not present")
+    keyed = [f for f in files if os.path.basename(f) in ("Paris_LiquorBottle_01_Labels_BaseColor.png", "Paris_Table_cloth_01_BaseColor.png")]
+    assert len(keyed) == 2
+    kinds = set()
+    for f in files[::9] + keyed:
+        data = open(f, "rb").read()
+        rc, got = lib_decode(ptc, data)
+        assert rc == 0, (f, got)
+        kinds.add((data[24], data[25]))
+        if f in keyed:
+            exp = np.asarray(Image.open(f).convert("RGBA"))
+            assert (exp[..., 3] == 0).any()
+        else:
+            im = cv2.imread(f, cv2.IMREAD_UNCHANGED)                  # BGR(A) or grey
+            exp = expected_rgba(im if im.ndim == 2 else im[..., [2, 1, 0] + ([3] if im.shape[2] == 4 else [])])
+        assert exp.shape == got.shape and np.array_equal(exp, got), f
+    assert {(8, 2), (8, 6), (8, 3), (1, 3)} <= kinds
