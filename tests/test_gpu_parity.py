@@ -752,3 +752,29 @@ def test_resize_failure_keeps_the_step_usable(ptc, standins, oracle):
     step.update(camera.uniforms(frame=2)); step.render(); step.poll(True)
     assert (step.read(T.PLANE_COLOR)[..., 3] == 2).all()
     step.destroy()
+
+
+@pytest.mark.parametrize("build", [0, 1, 2], ids=["sah", "lbvh", "ploc"])
+def test_inactive_triangles_gpu(ptc, standins, oracle, build):
+    """A mesh whose triangles have NaN / infinite / beyond-1e37 corners is inactive (never hit, as in the acceleration structures
+    the reference builds; csrc/scene_prep.cpp): the kernels render the Cornell box with such a mesh appended exactly as the
+    oracle renders the box without it, under the host SAH build and both device builds; mesh numbering is unchanged."""
+    from test_hostemu_parity import _inactive_mesh
+    clean, cam = standins.cornell()
+    dirty, _ = standins.cornell()
+    bad = _inactive_mesh()
+    dirty.add_mesh(bad, np.tile([0, 1, 0], (len(bad), 1)), None, np.arange(len(bad)), 0)
+    W, H = 160, 120
+    cfg = ptc.make_config(W, H, max_bounces=4, bvh_build=build)
+    camera = standins.make_camera(cam, W, H)
+    step = ptc.RTStep.create(dirty, cfg, device=0)
+    orc = oracle.OracleScene(clean, cfg)
+    ref = None
+    for f in (1, 2):
+        u = camera.uniforms(frame=f)
+        step.update(u); step.render()
+        ref = orc.render_frame(u, None if ref is None else ref["color"])
+    step.poll(True)
+    check_all_planes(ptc, step, ref)
+    assert step.bvh_info()["triangles"] == len(dirty.indices) // 3
+    step.destroy()

@@ -253,6 +253,15 @@ def test_packet_traversal_same_hits(ptc, standins, oracle, hostemu, which):
         assert stats[0] / (len(rays) / 32) < 90                          # even at this low resolution a tile visits ~2x what one ray does (1.2x at 1080p)
 
 
+def _inactive_mesh():
+    """five triangles in front of the Cornell camera, each with one corner no tree builder can place"""
+    return np.array([[np.nan, 0.5, 0.0], [1.0, 0.5, 0.5], [1.0, 1.0, 0.0],            # NaN corner
+                     [1.0, np.inf, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.0],            # +inf
+                     [1.0, 0.2, 0.0], [-np.inf, 0.5, 0.5], [1.5, 1.0, 0.3],           # -inf
+                     [3e38, 0.2, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.3],              # finite, but edges overflow fp32
+                     [1.0, 0.2, 0.0], [1.0, -2e37, 0.5], [1.5, 1.0, 0.3]], np.float32)
+
+
 @pytest.mark.parametrize("build", ["sah", "lbvh", "ploc"])
 def test_inactive_triangles_do_not_change_the_image(ptc, standins, hostemu, build):
     """Triangles with a NaN / infinite / beyond-1e37 corner are inactive, as in the acceleration structures the reference
@@ -263,11 +272,7 @@ def test_inactive_triangles_do_not_change_the_image(ptc, standins, hostemu, buil
     kind = {"sah": T.BVH_SAH_HOST, "lbvh": T.BVH_LBVH_DEVICE, "ploc": T.BVH_PLOC_DEVICE}[build]
     clean, cam = standins.cornell()
     dirty, _ = standins.cornell()
-    bad = np.array([[np.nan, 0.5, 0.0], [1.0, 0.5, 0.5], [1.0, 1.0, 0.0],            # NaN corner
-                    [1.0, np.inf, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.0],            # +inf
-                    [1.0, 0.2, 0.0], [-np.inf, 0.5, 0.5], [1.5, 1.0, 0.3],           # -inf
-                    [3e38, 0.2, 0.0], [1.0, 0.5, 0.5], [1.5, 1.0, 0.3],              # finite, but edges overflow fp32
-                    [1.0, 0.2, 0.0], [1.0, -2e37, 0.5], [1.5, 1.0, 0.3]], np.float32)
+    bad = _inactive_mesh()
     dirty.add_mesh(bad, np.tile([0, 1, 0], (len(bad), 1)), None, np.arange(len(bad)), 0)
     W, H = 96, 96
     cfg = ptc.make_config(W, H, max_bounces=4, bvh_build=kind)
