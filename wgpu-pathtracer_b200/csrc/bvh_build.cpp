@@ -22,7 +22,23 @@ constexpr float kTraversalCost = 1.2f;   // relative to one triangle test
 constexpr uint32_t kTaskGrain = 8192;
 constexpr size_t kTopNodes = 128;        // inner nodes numbered breadth-first at the top of the tree    // subtrees below this many triangles are built inline by one thread
 
-struct Prim { float lo[3], hi[3], c[3]; uint32_t id; };
+// Four floats at a time (GCC / Clang vector extension: SSE on x86-64, NEON on aarch64).  vmin / vmax are std::min(acc, x) /
+// std::max(acc, x) lane by lane — the same value in every case, signed zeros and NaN included — so the vectorised build
+// makes exactly the tree the scalar one made (order and node hashes compared on five scenes, 36 to 10.7 M triangles).
+typedef float v4f __attribute__((vector_size(16)));
+inline v4f vmin(v4f acc, v4f x) { return x < acc ? x : acc; }
+inline v4f vmax(v4f acc, v4f x) { return acc < x ? x : acc; }
+inline v4f vset(float x) { return v4f{x, x, x, x}; }
+
+// 48 bytes, three aligned 16-byte rows; the fourth lane of each row is never read as a coordinate (lo's carries the id)
+struct alignas(16) Prim { float lo[3]; uint32_t id; float hi[3]; uint32_t pad0; float c[3]; uint32_t pad1; };
+inline v4f row(const float* p) { return *reinterpret_cast<const v4f*>(p); }
+struct Box4 {
+    v4f lo, hi;
+    void reset() { lo = vset(std::numeric_limits<float>::infinity()); hi = vset(-std::numeric_limits<float>::infinity()); }
+    void grow(v4f l, v4f h) { lo = vmin(lo, l); hi = vmax(hi, h); }
+    float half_area() const { const v4f d = hi - lo; return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]; }
+};
 
 // bin of a scaled centroid offset; coordinates near FLT_MAX make the scale 0 or the offset infinite, and a NaN or an
 // out-of-range value must not reach the float -> int conversion (undefined): those land in bin 0 / the last bin
@@ -54,8 +70,8 @@ struct Box {
 };
 
 struct Builder {
-    std::vector<Prim> prims;
-    std::vector<BuildNode>* nodes;
+    std::vector<Prim, NoInitAlloc<Prim>> prims;
+    std::vector<BuildNode, NoInitAlloc<BuildNode>>* nodes;
     std::atomic<uint32_t> next_node{1};
     std::atomic<uint32_t> max_depth{0};
     uint32_t max_leaf;
@@ -73,33 +89,49 @@ struct Builder {
     }
 
     // Splits [first, first+count); returns mid or 0 when the range stays a leaf.
+    // Two passes over the range: bounds and centroid bounds, then the bins of all three axes at once (a primitive is
+    // loaded once and its box goes to one bin per axis with two vector min / max each); the sweeps over the 16 bins per
+    // axis evaluate the same costs in the same order as ever.  (Splitting the top ranges of a large scene with all threads
+    // together — chunked bounds / bins, stable partition through a scratch array — was built and measured: the root split
+    // of 4 M primitives went from 156 to 82 ms on 8 cores, the next three levels did not move, 1.13 s against 1.16 s for the
+    // whole build: those passes are bound by memory bandwidth, not by cores.  Not kept.)
     uint32_t split(uint32_t node, uint32_t first, uint32_t count) {
-        Box bounds, cb; bounds.reset(); cb.reset();
-        for (uint32_t i = first; i < first + count; ++i) { bounds.grow(prims[i].lo, prims[i].hi); cb.grow(prims[i].c, prims[i].c); }
+        Box4 bounds4, cb4; bounds4.reset(); cb4.reset();
+        for (uint32_t i = first; i < first + count; ++i) { const Prim& p = prims[i]; bounds4.grow(row(p.lo), row(p.hi)); const v4f c = row(p.c); cb4.grow(c, c); }
+        Box bounds, cb;
+        for (int a = 0; a < 3; ++a) { bounds.lo[a] = bounds4.lo[a]; bounds.hi[a] = bounds4.hi[a]; cb.lo[a] = cb4.lo[a]; cb.hi[a] = cb4.hi[a]; }
         BuildNode& n = (*nodes)[node];
         std::memcpy(n.lo, bounds.lo, 12); std::memcpy(n.hi, bounds.hi, 12);
         n.left = 0xFFFFFFFFu; n.first = first; n.count = count;
         if (count == 1) return 0;
 
+        bool valid[3]; float scale[3];
+        for (int a = 0; a < 3; ++a) { const float ext = cb.hi[a] - cb.lo[a]; valid[a] = ext > 0.0f; scale[a] = valid[a] ? (float)kBins / ext : 0.0f; }
+        Box4 bb[3][kBins]; uint32_t bn[3][kBins];
+        for (int a = 0; a < 3; ++a) if (valid[a]) for (int b = 0; b < kBins; ++b) { bb[a][b].reset(); bn[a][b] = 0; }
+        if (valid[0] && valid[1] && valid[2]) {
+            for (uint32_t i = first; i < first + count; ++i) {
+                const Prim& p = prims[i]; const v4f l = row(p.lo), h = row(p.hi);
+                const int b0 = bin_of((p.c[0] - cb.lo[0]) * scale[0]), b1 = bin_of((p.c[1] - cb.lo[1]) * scale[1]), b2 = bin_of((p.c[2] - cb.lo[2]) * scale[2]);
+                bb[0][b0].grow(l, h); bn[0][b0]++; bb[1][b1].grow(l, h); bn[1][b1]++; bb[2][b2].grow(l, h); bn[2][b2]++;
+            }
+        } else {
+            for (uint32_t i = first; i < first + count; ++i) {
+                const Prim& p = prims[i]; const v4f l = row(p.lo), h = row(p.hi);
+                for (int a = 0; a < 3; ++a) if (valid[a]) { const int b = bin_of((p.c[a] - cb.lo[a]) * scale[a]); bb[a][b].grow(l, h); bn[a][b]++; }
+            }
+        }
         float best = std::numeric_limits<float>::infinity(); int best_axis = -1, best_split = -1;
         for (int a = 0; a < 3; ++a) {
-            float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.0f)) continue;
-            Box bb[kBins]; uint32_t bn[kBins];
-            for (int b = 0; b < kBins; ++b) { bb[b].reset(); bn[b] = 0; }
-            float k = (float)kBins / ext;
-            for (uint32_t i = first; i < first + count; ++i) {
-                const int b = bin_of((prims[i].c[a] - cb.lo[a]) * k);
-                bb[b].grow(prims[i].lo, prims[i].hi); bn[b]++;
-            }
+            if (!valid[a]) continue;
             float right_area[kBins]; uint32_t right_n[kBins];
-            Box acc; acc.reset(); uint32_t cnt = 0;
-            for (int b = kBins - 1; b >= 1; --b) { if (bn[b]) { acc.grow(bb[b].lo, bb[b].hi); }
-                cnt += bn[b]; right_n[b] = cnt; right_area[b] = cnt ? acc.half_area() : 0.0f; }
+            Box4 acc; acc.reset(); uint32_t cnt = 0;
+            for (int b = kBins - 1; b >= 1; --b) { acc.grow(bb[a][b].lo, bb[a][b].hi);          // an empty bin is (+inf, -inf): growing by it changes nothing
+                cnt += bn[a][b]; right_n[b] = cnt; right_area[b] = cnt ? acc.half_area() : 0.0f; }
             acc.reset(); cnt = 0;
             for (int b = 0; b < kBins - 1; ++b) {
-                if (bn[b]) { acc.grow(bb[b].lo, bb[b].hi); }
-                cnt += bn[b];
+                acc.grow(bb[a][b].lo, bb[a][b].hi);
+                cnt += bn[a][b];
                 if (!cnt || !right_n[b + 1]) continue;
                 float cost = acc.half_area() * (float)cnt + right_area[b + 1] * (float)right_n[b + 1];
                 if (cost < best) { best = cost; best_axis = a; best_split = b; }
@@ -184,7 +216,7 @@ void build_bvh2(const float* tri_pos, uint32_t ntri, uint32_t max_leaf, int nthr
         par_for(ntri, nthreads, [&](uint64_t i0, uint64_t i1) {
             Box local; local.reset();
             for (uint64_t i = i0; i < i1; ++i) {
-                Prim& p = b.prims[i]; p.id = (uint32_t)i;
+                Prim& p = b.prims[i]; p.id = (uint32_t)i; p.pad0 = p.pad1 = 0u;
                 const float* v = tri_pos + (size_t)i * 9;
                 for (int a = 0; a < 3; ++a) {
                     p.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));

@@ -8,6 +8,8 @@
 // instances are all identity transforms, so flattening loses nothing).
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <vector>
 
 namespace ptc {
@@ -18,8 +20,19 @@ struct BuildNode {
     uint32_t first, count;   // leaf: range in `order`
 };
 
+// std::allocator that leaves trivially constructible elements uninitialised: resize() of a 10 M-triangle node or
+// primitive array is then an allocation, not a single-threaded pass over hundreds of megabytes that the build threads
+// overwrite a moment later (the pages are first touched by the threads that fill them).
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(static_cast<A&&>(a)...);
+    }
+};
+
 struct Bvh2 {
-    std::vector<BuildNode> nodes;    // nodes[0] is the root
+    std::vector<BuildNode, NoInitAlloc<BuildNode>> nodes;    // nodes[0] is the root
     std::vector<uint32_t> order;     // leaf-ordered global triangle ids
     uint32_t max_depth = 0;
     float pad = 0.0f;                // conservative padding to apply to every box when emitting device nodes
