@@ -71,9 +71,15 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
 
     // BVH over every triangle
     std::vector<float> pos((size_t)ntri * 9);
+    auto finite9 = [](const float* p) { for (int k = 0; k < 9; ++k) if (!(std::fabs(p[k]) <= 1e37f)) return false; return true; };
+    std::atomic<bool> any_inactive(false);
     parallel_for(ntri, [&](uint64_t b, uint64_t e) {
-        for (uint64_t t = b; t < e; ++t)
+        bool seen = false;
+        for (uint64_t t = b; t < e; ++t) {
             for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], v->vertices[v->indices[(size_t)t * 3 + k]].position, 12);
+            seen = seen || !finite9(&pos[(size_t)t * 9]);
+        }
+        if (seen) any_inactive = true;
     });
     // A triangle with a non-finite corner is INACTIVE, as in the acceleration structures the reference builds (Vulkan: a
     // NaN position makes a triangle inactive, it is never hit; pt.rs:391-433 hands the vertex buffer to the driver as it is).
@@ -82,17 +88,12 @@ int prepare_scene(const ptc_scene_view* v, const ptc_config& cfg, PreparedScene&
     // and its box neither poisons the bounds nor the Morton keys.  The same goes for coordinates beyond 1e37: edge vectors,
     // box extents and the quantisation grid overflow fp32 there, and no ray (tmax = 10000) resolves them.
     // Triangle numbering and shading records are unchanged.
-    {
-        auto finite9 = [](const float* p) { for (int k = 0; k < 9; ++k) if (!(std::fabs(p[k]) <= 1e37f)) return false; return true; };
-        float anchor[3] = {0.0f, 0.0f, 0.0f}; bool have_anchor = false, any_inactive = false;
-        for (uint32_t t = 0; t < ntri; ++t) {
-            if (finite9(&pos[(size_t)t * 9])) { if (!have_anchor) { std::memcpy(anchor, &pos[(size_t)t * 9], 12); have_anchor = true; if (any_inactive) break; } }
-            else { any_inactive = true; if (have_anchor) break; }
-        }
-        if (any_inactive)
-            parallel_for(ntri, [&](uint64_t b, uint64_t e) {
-                for (uint64_t t = b; t < e; ++t) if (!finite9(&pos[(size_t)t * 9])) for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], anchor, 12);
-            });
+    if (any_inactive) {
+        float anchor[3] = {0.0f, 0.0f, 0.0f};
+        for (uint32_t t = 0; t < ntri; ++t) if (finite9(&pos[(size_t)t * 9])) { std::memcpy(anchor, &pos[(size_t)t * 9], 12); break; }
+        parallel_for(ntri, [&](uint64_t b, uint64_t e) {
+            for (uint64_t t = b; t < e; ++t) if (!finite9(&pos[(size_t)t * 9])) for (int k = 0; k < 3; ++k) std::memcpy(&pos[(size_t)t * 9 + k * 3], anchor, 12);
+        });
     }
     const bool ploc = cfg.bvh_build == PTC_BVH_PLOC_DEVICE && ntri > 4;
     const bool lbvh = ploc || (cfg.bvh_build == PTC_BVH_LBVH_DEVICE && ntri > PTC_LBVH_MAX_LEAF);

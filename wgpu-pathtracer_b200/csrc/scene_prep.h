@@ -15,7 +15,7 @@ namespace ptc {
 
 struct PreparedScene {
     DevBvh2 bvh;                          // device-layout nodes + leaf-ordered triangles
-    std::vector<TriShade> shade;          // global triangle order
+    std::vector<TriShade, NoInitAlloc<TriShade>> shade;   // global triangle order; every word is written by prepare_scene (no zero-fill first)
     std::vector<MatDev> mats;
     std::vector<ptc_triangle> lights;     // never empty (dummy entry, pt.rs:232-239); _pad0 = the light's global triangle id
     std::vector<uint32_t> light_of_tri;   // global triangle -> index into lights (0xFFFFFFFF: not emissive)
