@@ -110,3 +110,72 @@ def test_display_path_gpu(ptc, standins, oracle):
     ref2, _ = oracle.blit(rep2.reshape(H, W, 4))
     assert np.abs(step.read(T.PLANE_DISPLAY).astype(np.int32) - ref2.astype(np.int32)).max() <= DISPLAY_TOL_LSB
     step.destroy()
+
+
+def test_blit_against_an_independent_restatement(oracle, hostemu):
+    """blit.wgsl:36-41 + color.wgsl:2-27 written again in numpy float64 from the WGSL (no code shared with oracle/ or csrc/),
+    followed by the sRGB transfer function an *Srgb surface applies on store (IEC 61966-2-1) and round-to-nearest to 8 bits.
+    The oracle and the product's host build agree with it within 1 LSB on random HDR pixels, greys around both knees
+    (x = 2 F90 and p = 0.8 - F90) and the extremes."""
+    F90 = 0.04
+    rng = np.random.RandomState(17)
+    rgb = np.concatenate([rng.rand(4000, 3) ** 3 * 6.0, np.repeat(np.linspace(0.0, 1.5, 400)[:, None], 3, 1),
+                          np.array([[0.08, 0.08, 0.08], [0.76, 0.76, 0.76], [0.8, 0.1, 0.05], [50.0, 40.0, 30.0], [1e-4, 2e-4, 3e-4]])])
+    img = np.ones((len(rgb), 1, 4), np.float32)
+    img[:, 0, :3] = rgb
+    c = img[:, 0, :3].astype(np.float64)
+    k_s, k_d = 0.8 - F90, 0.15
+    x = c.min(axis=1, keepdims=True)
+    f = np.where(x <= 2.0 * F90, x - x * x / (4.0 * F90), F90)
+    p = (c - f).max(axis=1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p_n = 1.0 - (1.0 - k_s) ** 2 / (p + 1.0 - 2.0 * k_s)
+        g = 1.0 / (k_d * (p - p_n) + 1.0)
+        out = np.where(p <= k_s, c - f, (c - f) * (p_n / p) * g + p_n * (1.0 - g))
+    out = np.clip(out, 0.0, 1.0)
+    srgb = np.where(out <= 0.0031308, out * 12.92, 1.055 * np.power(out, 1.0 / 2.4) - 0.055)
+    want = np.floor(srgb * 255.0 + 0.5).astype(np.int32)
+    ref, _ = oracle.blit(img)
+    got = hostemu.blit(img)
+    assert np.abs(ref[:, 0, :3].astype(np.int32) - want).max() <= DISPLAY_TOL_LSB
+    assert np.abs(got[:, 0, :3].astype(np.int32) - want).max() <= DISPLAY_TOL_LSB
+    assert (want.max(axis=1) - want.min(axis=1)).max() > 100 and want.min() == 0 and want.max() >= 250       # the sample spans the range
+
+
+def test_rayproject_against_an_independent_restatement(ptc, standins, oracle):
+    """rayproject.wgsl:45-74 written again in numpy float64 from the WGSL.  Destination pixels are integers produced by
+    round(): the fp32 oracle may land on the neighbouring pixel where the float64 position sits within 1e-3 of a half;
+    everywhere else (> 99 % of the pixels) the two agree exactly, and never by more than one pixel."""
+    W, H = 96, 64
+    a, b = _cams(standins, ptc, W, H)
+    rng = np.random.RandomState(4)
+    depth = rng.uniform(0.5, 6.0, (H, W)).astype(np.float32)
+    prev, cur = a.uniforms(frame=3), b.uniforms(frame=4)
+    ref = oracle.rayproject(cur, prev, depth).reshape(H, W)
+
+    def v3(x):
+        return np.array([x[0], x[1], x[2]], np.float64)
+    pc, cc = prev.camera, cur.camera
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    origin = v3(pc.first_pixel_pos) + xs[..., None] * v3(pc.pixel_space_x) + ys[..., None] * v3(pc.pixel_space_y)
+    d = origin - v3(pc.position)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    to_old = origin + d * depth[..., None].astype(np.float64) - v3(cc.position)
+    on_plane = to_old / (to_old @ (v3(cc.lookat) - v3(cc.position)))[..., None]
+    psx, psy = v3(cc.pixel_space_x), v3(cc.pixel_space_y)
+    rx = (on_plane @ (psx / np.linalg.norm(psx))) / np.linalg.norm(psx) + W * 0.5 + 0.5
+    ry = (on_plane @ (psy / np.linalg.norm(psy))) / np.linalg.norm(psy) + H * 0.5 + 0.5
+    qx, qy = np.floor(rx + 0.5), np.floor(ry + 0.5)                           # WGSL round(): halves are the uncertain cases below
+    qx, qy = np.maximum(qx, 0.0), np.maximum(qy, 0.0)                         # u32() of a negative float clamps to 0 (WGSL value conversion):
+    inside = (qx < W) & (qy < H)                                              # what leaves to the left / top lands in column / row 0
+    hit = ref != 0xFFFFFFFF
+    near_half = (np.abs(rx - np.floor(rx) - 0.5) < 1e-3) | (np.abs(ry - np.floor(ry) - 0.5) < 1e-3)
+    near_edge = (np.abs(rx + 0.5 - W) < 1e-3) | (np.abs(ry + 0.5 - H) < 1e-3)
+    sure = ~near_half & ~near_edge
+    assert sure.mean() > 0.99
+    assert np.array_equal(hit[sure], inside[sure])
+    both = sure & hit
+    assert both.mean() > 0.5
+    assert np.array_equal((ref[both] % W).astype(np.float64), qx[both]) and np.array_equal((ref[both] // W).astype(np.float64), qy[both])
+    rest = hit & inside & ~sure
+    assert (np.abs((ref[rest] % W) - qx[rest]) <= 1).all() and (np.abs((ref[rest] // W) - qy[rest]) <= 1).all()
