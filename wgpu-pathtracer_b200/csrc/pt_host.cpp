@@ -698,6 +698,7 @@ PTC_API int ptc_scene_texture_info_at(const ptc_scene* s, uint64_t i, ptc_scene_
 PTC_API int ptc_scene_set_texels(ptc_scene* s, uint64_t i, uint32_t w, uint32_t h, uint32_t format, const void* texels) {
     return ptc::guarded("ptc_scene_set_texels", [&]() -> int {
     if (!s || !texels || i >= s->textures.size() || w == 0 || h == 0 || format > PTC_TEXEL_RGBA32F) { set_error("bad texel upload"); return PTC_ERR_INVALID; }
+    if ((uint64_t)w * h > (1ull << 30)) { set_error("texture larger than 2^30 texels"); return PTC_ERR_INVALID; }      // the decoders' bound; keeps the byte count inside 64 bits
     SceneTexture& t = s->textures[i];
     size_t bytes = (size_t)w * h * (format == PTC_TEXEL_RGBA8 ? 4 : 16);
     t.texels.assign((const uint8_t*)texels, (const uint8_t*)texels + bytes);
