@@ -10,6 +10,7 @@ C++ oracle against it pixel by pixel: the same radiance within a stated toleranc
 path (i.e. the same number of random draws in the same order), and the same first-hit depth / normal-mapped normal / albedo
 planes (pathtracer/pathtracer.wgsl:208-223, 270-273; a first hit on an emitter leaves them zero).  One fixture is textured:
 file-backed RGBA8 albedo and normal maps and a float roughness map, uv from -0.6 to 2.7 (Repeat on both sides of zero).
+The reference's dormant light branch (SEND_TO_LIGHT_PROBABILITY > 0) is restated too and compared at 0.5.
 
 Tolerances: fixtures whose radiance is a smooth function of the random numbers must agree to 1e-5 (relative to the pixel's
 magnitude) on EVERY pixel; the multi-bounce diffuse fixture is chaotic (an ulp in a transcendental moves a later hit across
@@ -93,14 +94,20 @@ def mix(a, b, t):
 
 # ---- scene access ------------------------------------------------------------------------------------------------------
 class World:
-    def __init__(self, scene, max_bounces):
-        self.sc, self.max_bounces = scene, max_bounces
+    def __init__(self, scene, max_bounces, p_light=0.0):
+        self.sc, self.max_bounces, self.p_light = scene, max_bounces, F(p_light)
         idx = scene.indices.reshape(-1, 3)
         P = scene.vertices["position"].astype(np.float64)
         self.v0, self.e1, self.e2 = P[idx[:, 0]], P[idx[:, 1]] - P[idx[:, 0]], P[idx[:, 2]] - P[idx[:, 0]]
         self.tri_mesh = np.zeros(len(idx), np.int64)
         for m, mesh in enumerate(scene.meshes):
             self.tri_mesh[mesh["index_offset"] // 3:(mesh["index_offset"] + mesh["index_count"]) // 3] = m
+        # pt.rs:206-243: emissive triangles in global order (emissive_texture_idx != 4), one all-zero dummy when there is none
+        Pf = scene.vertices["position"].astype(F)
+        self.lights = [(Pf[i0], Pf[i1], Pf[i2]) for t, (i0, i1, i2) in enumerate(idx)
+                       if scene.materials[scene.meshes[self.tri_mesh[t]]["material_index"]]["emissive_texture_idx"] != 4]
+        if not self.lights:
+            self.lights = [(v(0, 0, 0), v(0, 0, 0), v(0, 0, 0))]
 
     def closest(self, ro, rd):
         """rayQuery closest hit, t in (0.01, 10000), two-sided, no culling — float64 Moeller-Trumbore over every triangle."""
@@ -201,11 +208,26 @@ def ray_color(world, rng, ro, rd):                                     # pathtra
         uv = (vtx[0]["uv"] * w0 + vtx[1]["uv"] * b1 + vtx[2]["uv"] * b2).astype(F)
         mat = sample_material(world, sc.materials[sc.meshes[world.tri_mesh[tri]]["material_index"]], uv)
         hit_light = dot(mat["emissive"], v(1, 1, 1)) > 0
-        assert rng.float() < F(1.0)                                    # :170, always consumed; < 1 - 0.0 unless the draw is exactly 1
         p = (rd * t + ro).astype(F)                                    # fma(rd, t, ro)
         n = normalize((vtx[0]["normal"] * w0 + vtx[1]["normal"] * b1 + vtx[2]["normal"] * b2).astype(F))
-        colour, pdf, ro_next, origin = None, None, None, None
-        colour, pdf, direction, origin = disney_bsdf(rng, p, rd, n, mat)
+        to_light = None
+        if not (rng.float() < F(1.0) - world.p_light):                 # :170 (always consumed) / :175-191, the dormant light branch
+            l0, l1, l2 = world.lights[rng.int() % len(world.lights)]   # :176
+            r1 = rng.float(); r2 = rng.float()                         # random_point_on_triangle, helpers.wgsl:7-18
+            s1 = F(np.sqrt(r1))
+            to_point = (l0 * (F(1.0) - s1) + l1 * s1 * (F(1.0) - r2) + l2 * s1 * r2).astype(F)
+            ln = vtx[0]["normal"].astype(F)                            # light_scatter :59 — vertex 0's normal, not the interpolated one
+            to_p_dir = normalize((to_point - p).astype(F))
+            # triangle_pdf :22 traces a probe ray here whatever should_hit says; its result (`importance`) is never applied
+            # to the throughput and it draws no random number, so oracle and kernels omit it — it is not counted here either
+            if dot(to_p_dir, ln) > 0:
+                to_light = (to_p_dir, ln)
+        if to_light is not None:                                       # origin p without offset, attenuation = albedo, pdf unused
+            direction, sn_raw = to_light
+            colour, pdf, origin = mat["albedo"], F(1.0), p
+        else:
+            colour, pdf, direction, origin = disney_bsdf(rng, p, rd, n, mat)
+            sn_raw = None
         prev_rd = rd
         ro, rd = origin, direction
         acc = (acc + mat["emissive"] * mask).astype(F)                 # :200
@@ -213,7 +235,7 @@ def ray_color(world, rng, ro, rd):                                     # pathtra
         if hit_light:                                                  # :204-206 — BEFORE the aux block: a first hit on a light leaves the planes 0
             break
         if i == 0:                                                     # :208-223, with scatter's n = faceForward(n, rd, n) (:91)
-            sn = face_forward(n, prev_rd, n)
+            sn = face_forward(n, prev_rd, n) if sn_raw is None else sn_raw
             tangent = normalize(cross(sn, (-prev_rd).astype(F)))
             bitangent = normalize(cross(sn, tangent))
             tsn = mat["tsn"]
@@ -297,12 +319,12 @@ def fixture(ptc, standins, which):
     raise KeyError(which)
 
 
-def compare(ptc, standins, oracle, which, W=40, H=30, frames=(1, 7), stride=5):
+def compare(ptc, standins, oracle, which, W=40, H=30, frames=(1, 7), stride=5, p_light=0.0):
     sc, cam, bounces = fixture(ptc, standins, which)
-    cfg = ptc.make_config(W, H, max_bounces=bounces)
+    cfg = ptc.make_config(W, H, max_bounces=bounces, send_to_light_probability=p_light)
     camera = standins.make_camera(cam, W, H)
     orc = oracle.OracleScene(sc, cfg)
-    world = World(sc, bounces)
+    world = World(sc, bounces, p_light)
     rows = []
     for frame in frames:
         un = camera.uniforms(frame=frame)
@@ -347,6 +369,19 @@ def test_chaotic_multi_bounce_fixture(ptc, standins, oracle):
     assert same.mean() >= 0.95, f"only {same.mean():.3f} of the paths end in the same RNG state"
     assert r[same, 0].max() <= 2e-4, f"radiance differs by {r[same, 0].max():.2e} on paths with identical draws"
     assert r[:, 3].mean() >= 2.5                                       # several segments per path on average
+
+
+def test_dormant_light_branch(ptc, standins, oracle):
+    """SEND_TO_LIGHT_PROBABILITY = 0.5 (the reference ships 0.0: pathtracer/pathtracer.wgsl:21-73,127-140,170-191 never run
+    there): light choice by rand_int() % num_lights, two draws for the point on the light, vertex 0's normal as the
+    shading normal, attenuation = albedo, origin without offset, fallback to the regular branch when the light is behind
+    the surface.  Chaotic fixture, same bars as above."""
+    r = compare(ptc, standins, oracle, "diffuse_corner", p_light=0.5)
+    same = r[:, 1].astype(bool) & r[:, 2].astype(bool)
+    assert same.mean() >= 0.95, f"only {same.mean():.3f} of the paths end in the same RNG state with the same ray count"
+    assert r[same, 0].max() <= 2e-4 and r[same, 4].max() <= 2e-5, (r[same, 0].max(), r[same, 4].max())
+    plain = compare(ptc, standins, oracle, "diffuse_corner")
+    assert not np.array_equal(plain[:, 3], r[:, 3])                    # the branch really changes the paths
 
 
 def test_rng_against_the_reference_known_answers():
