@@ -94,8 +94,8 @@ def mix(a, b, t):
 
 # ---- scene access ------------------------------------------------------------------------------------------------------
 class World:
-    def __init__(self, scene, max_bounces, p_light=0.0):
-        self.sc, self.max_bounces, self.p_light = scene, max_bounces, F(p_light)
+    def __init__(self, scene, max_bounces, p_light=0.0, spp=1):
+        self.sc, self.max_bounces, self.p_light, self.spp = scene, max_bounces, F(p_light), spp
         idx = scene.indices.reshape(-1, 3)
         P = scene.vertices["position"].astype(np.float64)
         self.v0, self.e1, self.e2 = P[idx[:, 0]], P[idx[:, 1]] - P[idx[:, 0]], P[idx[:, 2]] - P[idx[:, 0]]
@@ -251,8 +251,11 @@ def pixel(world, un, x, y):                                            # pathtra
     jx = F(x) + F(0.5) * rng.float()
     jy = F(y) + F(0.5) * rng.float()
     rd = normalize(((fp + psx * jx + psy * jy) - pos).astype(F))
-    col, rays, aux = ray_color(world, rng, pos, rd)
-    return col, rng, rays, aux
+    col, rays, aux = v(0, 0, 0), 0, None
+    for _ in range(world.spp):                                         # :258-266: the SAME rd for every sample, planes of the last one
+        c1, r1, aux = ray_color(world, rng, pos, rd)
+        col, rays = (col + c1).astype(F), rays + r1
+    return (col / F(world.spp)).astype(F), rng, rays, aux
 
 
 # ---- fixtures ------------------------------------------------------------------------------------------------------------
@@ -319,12 +322,12 @@ def fixture(ptc, standins, which):
     raise KeyError(which)
 
 
-def compare(ptc, standins, oracle, which, W=40, H=30, frames=(1, 7), stride=5, p_light=0.0):
+def compare(ptc, standins, oracle, which, W=40, H=30, frames=(1, 7), stride=5, p_light=0.0, spp=1):
     sc, cam, bounces = fixture(ptc, standins, which)
-    cfg = ptc.make_config(W, H, max_bounces=bounces, send_to_light_probability=p_light)
+    cfg = ptc.make_config(W, H, max_bounces=bounces, send_to_light_probability=p_light, samples_per_pixel=spp)
     camera = standins.make_camera(cam, W, H)
     orc = oracle.OracleScene(sc, cfg)
-    world = World(sc, bounces, p_light)
+    world = World(sc, bounces, p_light, spp)
     rows = []
     for frame in frames:
         un = camera.uniforms(frame=frame)
@@ -369,6 +372,13 @@ def test_chaotic_multi_bounce_fixture(ptc, standins, oracle):
     assert same.mean() >= 0.95, f"only {same.mean():.3f} of the paths end in the same RNG state"
     assert r[same, 0].max() <= 2e-4, f"radiance differs by {r[same, 0].max():.2e} on paths with identical draws"
     assert r[:, 3].mean() >= 2.5                                       # several segments per path on average
+
+
+def test_samples_per_pixel_loop(ptc, standins, oracle):
+    """SAMPLES_PER_PIXEL = 3 (pathtracer/pathtracer.wgsl:258-266): one primary direction, three paths, the mean."""
+    r = compare(ptc, standins, oracle, "glass_slab", spp=3, stride=7)
+    assert r[:, 1].all() and r[:, 2].all() and r[:, 0].max() <= 1e-5 and r[:, 4].max() <= 2e-5, (r[:, 0].max(), r[:, 4].max())
+    assert r[:, 3].min() >= 3
 
 
 def test_dormant_light_branch(ptc, standins, oracle):
