@@ -381,6 +381,35 @@ def test_samples_per_pixel_loop(ptc, standins, oracle):
     assert r[:, 3].min() >= 3
 
 
+def test_running_mean_accumulation(ptc, standins, oracle):
+    """main, pathtracer.wgsl:21-43: prev = max(0, output); new = (prev.rgb * prev.a + color) / (prev.a + 1), a + 1 — or
+    (color, 1) while the cursor is grabbed.  Three frames of the oracle's output texture against this file's pixels."""
+    W, H = 24, 18
+    sc, cam, bounces = fixture(ptc, standins, "single_triangle")
+    cfg = ptc.make_config(W, H, max_bounces=bounces)
+    camera = standins.make_camera(cam, W, H)
+    orc = oracle.OracleScene(sc, cfg)
+    world = World(sc, bounces)
+    img, mine = None, np.zeros((H, W, 4), F)
+    for frame, grabbed in ((1, 0), (2, 0), (3, 0), (4, 1), (5, 0)):
+        un = camera.uniforms(frame=frame)
+        un.is_grabbed = grabbed
+        img = orc.render_frame(un, img)["color"]
+        for y in range(0, H, 3):
+            for x in range(0, W, 3):
+                col = pixel(world, un, x, y)[0]
+                prev = np.maximum(F(0.0), mine[y, x])
+                if grabbed == 0:
+                    mine[y, x, :3] = (prev[:3] * prev[3] + col) / F(prev[3] + F(1.0))
+                    mine[y, x, 3] = prev[3] + F(1.0)
+                else:
+                    mine[y, x] = (col[0], col[1], col[2], F(1.0))
+        got, want = mine[::3, ::3], img[::3, ::3]
+        assert np.array_equal(got[..., 3], want[..., 3]), frame
+        assert np.abs(got[..., :3] - want[..., :3]).max() <= 1e-5 * max(1.0, float(np.abs(want[..., :3]).max())), frame
+    assert (img[..., 3] == 2).all()                                    # 3 frames, a grabbed one (-> 1), one more
+
+
 def test_dormant_light_branch(ptc, standins, oracle):
     """SEND_TO_LIGHT_PROBABILITY = 0.5 (the reference ships 0.0: pathtracer/pathtracer.wgsl:21-73,127-140,170-191 never run
     there): light choice by rand_int() % num_lights, two draws for the point on the light, vertex 0's normal as the
