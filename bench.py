@@ -27,7 +27,9 @@ reduce_check (N > 1) rank 0 checks the image ptc_reduce received: sample count =
 other_workloads  BASELINE configs[3] (classroom, also with the shadow-ray/any-hit mode) and configs[4] (San Miguel
          3840x2160, with the NCCL reduce at N > 1), measured after the headline with fewer steps.
 cpu_baseline / --impl reference   the oracle (CPU restatement of the WGSL; kind "port") on the box's host cores; the
-         reference's own wgpu path cannot run here (no Rust toolchain, no Vulkan ICD).
+         reference's own wgpu path cannot run here (no Rust toolchain, no Vulkan ICD).  The reference arm runs
+         exactly --steps timed steps after --warmup untimed ones; a step is one frame, or a centred band of rows of one
+         frame when full frames would not fit its time budget (PTC_REFERENCE_BUDGET_S, default 120 s).
 Multi-GPU: frames are sharded over ranks (rank r renders frames r+1, r+1+N, ...), scene replicated, per-rank SUM
          accumulation, one NCCL reduce of the image inside the timed region.  scaling = "weak".
 """
@@ -176,27 +178,39 @@ def run_reference(args):
     if rank != 0:
         return
     pkg, st, w, scene, camera = build_workload(args.workload)
-    # each step = one full frame on the CPU; bounded so that the whole run ends within a few minutes
-    steps, warm = min(args.steps, 8), min(args.warmup, 1)
+    # EXACTLY --steps timed steps after --warmup untimed ones, like the other arm.  A step is one frame on the CPU when the
+    # whole run then fits the time budget (about two minutes), otherwise a centred band of rows of each frame, sized from
+    # one untimed probe frame so that it does: a bounded sample of the same workload, said so in `sample`.
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    budget_s = float(os.environ.get("PTC_REFERENCE_BUDGET_S", "120"))
     oracle = oracle_module()
     cfg = pkg.make_config(w["width"], w["height"], max_bounces=w["max_bounces"], light_sampling=w.get("light_sampling", 0))
     orc = oracle.OracleScene(scene, cfg)
     cores = os.cpu_count() or 1
-    color = np.zeros((w["height"], w["width"], 4), np.float32)
-    for f in range(warm):
-        orc.render_frame(camera.uniforms(frame=1 + f), color, nthreads=cores, want_aux=False)
+    H = w["height"]
+    color = np.zeros((H, w["width"], 4), np.float32)
+    t0 = time.perf_counter()
+    orc.render_frame(camera.uniforms(frame=1), color, nthreads=cores, want_aux=False)          # probe (untimed; the first warm-up)
+    t_frame = time.perf_counter() - t0
+    rows = None
+    if (steps + warm) * t_frame > budget_s:
+        n = min(H, max(16, int(H * budget_s / ((steps + warm) * t_frame))))
+        rows = ((H - n) // 2, (H - n) // 2 + n)
+    for f in range(1, warm):
+        orc.render_frame(camera.uniforms(frame=1 + f), color, nthreads=cores, want_aux=False, rows=rows)
     rays = 0
     t0 = time.perf_counter()
     for f in range(steps):
-        rays += orc.render_frame(camera.uniforms(frame=1 + warm + f), color, nthreads=cores, want_aux=False)["rays"]
+        rays += orc.render_frame(camera.uniforms(frame=1 + max(warm, 1) + f), color, nthreads=cores, want_aux=False, rows=rows)["rays"]
     dt = time.perf_counter() - t0
+    per_step = "1 full frame" if rows is None else f"rows {rows[0]}..{rows[1] - 1} of 1 frame ({rows[1] - rows[0]} of {H} rows, sized from a {t_frame:.2f} s probe frame for a {budget_s:.0f} s run)"
     v = rays / dt / 1e6
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "spp_per_s": steps / dt,
+            "data": "synthetic", "spp_per_s": steps / dt * (1.0 if rows is None else (rows[1] - rows[0]) / H),
             "config": {"workload": workload_string(w, scene.num_triangles), "baseline_config_index": w["config_index"]},
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full frame(s) per run on {cores} host threads; CPU restatement of the reference's WGSL path "
+                             "sample": f"{steps} steps of {per_step} on {cores} host threads; CPU restatement of the reference's WGSL path "
                                        "(reference wgpu/Vulkan binary cannot be built or run here)"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
