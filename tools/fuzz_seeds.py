@@ -69,6 +69,8 @@ def main(out):
                 if ctype == 2:
                     extra = [chunk(b"tRNS", struct.pack(">HHH", 1, 2, 3))]
             put(f"c{ctype}d{depth}.png", png(w, h, depth, ctype, rows, extra=extra, split=1 + depth % 3))
+    put("grey8_plain.png", png(29, 17, 8, 0, packed_rows(rng, 29, 17, 8, 1)))          # no colour key: the decoder's straight 8-bit loops
+    put("rgb8_plain.png", png(29, 17, 8, 2, packed_rows(rng, 29, 17, 8, 3), split=2))
     put("adam7_rgb8.png", png(29, 17, 8, 2, adam7_rows(rng, 29, 17, 8, 3), interlace=1))
     put("adam7_g1.png", png(13, 9, 1, 0, adam7_rows(rng, 13, 9, 1, 1), interlace=1))
     put("adam7_rgba16.png", png(5, 3, 16, 6, adam7_rows(rng, 5, 3, 16, 4), interlace=1))
