@@ -1,11 +1,14 @@
 #!/bin/bash
-# fuzz.sh <decode|obj|scene|all> [iterations-per-seed] [rng-seeds...] — AddressSanitizer + UBSan builds of the library's
+# fuzz.sh <decode|obj|scene|all|tsan> [iterations-per-seed] [rng-seeds...] — AddressSanitizer + UBSan builds of the library's
 # host code that reads untrusted input, driven by the mutation fuzzers next to this script.  No GPU needed.
 #   decode : csrc/img_decode.cu (PNG, OpenEXR, PFM; compiled as host C++ — the file holds no device code; nvJPEG parses JPEG
 #            itself and is not exercised)                                      tools/fuzz_decode.cpp + tools/fuzz_seeds.py
 #   obj    : csrc/pt_host.cpp (OBJ / MTL text -> scene arrays, tobj-4.0.3 semantics)            tools/fuzz_obj.cpp
 #   scene  : csrc/scene_prep.cpp + csrc/bvh_build.cpp + the traversal of pt_device.cuh on the host (hostile scene views:
 #            broken tables, degenerate / coincident / non-finite geometry, three builders)       tools/fuzz_scene.cpp
+#   tsan   : the same three fuzzers (short runs; the OBJ scan cut into 64-byte chunks, the > 256 KB OpenEXR seeds) and
+#            tools/prepare_threads.cpp (120 000 triangles through prepare_scene and the three host builders) under
+#            ThreadSanitizer instead
 # A sanitizer report or a violated invariant ends the run with a non-zero exit code.  Last long run: profiles/r02zn_fuzz.log
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"; root="$(dirname "$here")"; csrc="$root/wgpu-pathtracer_b200/csrc"
@@ -30,4 +33,17 @@ if [ "$what" = scene ] || [ "$what" = all ]; then
     # -ffp-contract=off -mavx2 -mfma: the flags of tests/hostemu (explicit fmaf only, as in the device build)
     g++ $san -ffp-contract=off -mavx2 -mfma -Wno-unused-function "$here/fuzz_scene.cpp" "$csrc/scene_prep.cpp" "$csrc/bvh_build.cpp" -o "$work/fuzz_scene"
     for s in "${seeds[@]}"; do "$work/fuzz_scene" "${iters:-5000}" "$s"; done
+fi
+if [ "$what" = tsan ]; then
+    tsan="-std=c++17 -O1 -g -fsanitize=thread -pthread"
+    export TSAN_OPTIONS=halt_on_error=1
+    g++ $tsan -I"$cuda/include" -x c++ "$csrc/img_decode.cu" -x c++ "$here/fuzz_decode.cpp" -o "$work/fuzz_decode_tsan" -L"$cuda/lib64" -lcudart -lz -ldl
+    python "$here/fuzz_seeds.py" "$work/seeds"
+    "$work/fuzz_decode_tsan" "${iters:-3000}" "${seeds[0]}" "$work"/seeds/big_*
+    g++ $tsan -I"$cuda/include" "$csrc/pt_host.cpp" -x c++ "$csrc/img_decode.cu" -x c++ "$here/fuzz_obj.cpp" -o "$work/fuzz_obj_tsan" -L"$cuda/lib64" -lcudart -lz -ldl
+    PTC_OBJ_CHUNK_BYTES=64 "$work/fuzz_obj_tsan" "${iters:-3000}" "${seeds[0]}"
+    g++ $tsan -ffp-contract=off -mavx2 -mfma -Wno-unused-function "$here/fuzz_scene.cpp" "$csrc/scene_prep.cpp" "$csrc/bvh_build.cpp" -o "$work/fuzz_scene_tsan"
+    "$work/fuzz_scene_tsan" 150 "${seeds[0]}"
+    g++ $tsan -ffp-contract=off -mavx2 -mfma -Wno-unused-function "$here/prepare_threads.cpp" "$csrc/scene_prep.cpp" "$csrc/bvh_build.cpp" -o "$work/prepare_threads_tsan"
+    "$work/prepare_threads_tsan"
 fi
