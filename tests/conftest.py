@@ -40,8 +40,10 @@ class HostEmu:
 
     def __init__(self, ptc):
         here = os.path.join(ROOT, "tests", "hostemu")
-        so = os.path.join(here, "libpt_hostemu.so")
-        subprocess.check_call(["make", "-C", here, "libpt_hostemu.so"], stdout=subprocess.DEVNULL)
+        so = os.environ.get("PTC_HOSTEMU_LIB")          # another build of the same sources, e.g. the sanitizer build of `tools/fuzz.sh hostemu`
+        if not so:
+            so = os.path.join(here, "libpt_hostemu.so")
+            subprocess.check_call(["make", "-C", here, "libpt_hostemu.so"], stdout=subprocess.DEVNULL)
         T = ptc.types
         L = C.CDLL(so)
         vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
