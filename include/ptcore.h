@@ -250,7 +250,7 @@ PTC_API int ptc_scene_texture_info_at(const ptc_scene* scene, uint64_t index, pt
 PTC_API int ptc_scene_set_texels(ptc_scene* scene, uint64_t index, uint32_t width, uint32_t height, uint32_t format, const void* texels);
 /* Texture::load for every FILE texture without texels (texture.rs:232-243: image::open + to_rgba32f), on n_threads host
  * threads (0 = all; the reference spawns 32, scene.rs:239-254).  PNG (all colour types, bit depths, Adam7), OpenEXR
- * (single-part scan-line, HALF / FLOAT, NONE / ZIPS / ZIP / PIZ) and PFM are decoded on the host; JPEG (baseline and
+ * (single-part scan-line, HALF / FLOAT, NONE / ZIPS / ZIP / PIZ), Radiance HDR (RGBE, run-length or flat) and PFM are decoded on the host; JPEG (baseline and
  * progressive) by nvJPEG on `cuda_device`, bound at run time — without libnvjpeg or a GPU only JPEG textures fail.
  * 8-bit sources stay RGBA8, 16-bit become RGBA32F = v / 65535, float sources stay float.  Returns the
  * first failure (ptc_last_error names the file); textures that did decode keep their texels. */

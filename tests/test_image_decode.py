@@ -470,7 +470,7 @@ def test_decoders_under_the_mutation_fuzzer(ptc, tmp_path):
     spec = importlib.util.spec_from_file_location("fuzz_seeds", os.path.join(root, "tools", "fuzz_seeds.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     names = mod.main(str(tmp_path / "seeds"))
-    assert len(names) >= 44
+    assert len(names) >= 47
     for n in names:
         rc, got = lib_decode(ptc, open(tmp_path / "seeds" / n, "rb").read())
         assert rc == 0, (n, got)
@@ -539,3 +539,45 @@ def test_png_reference_texture_sets(ptc):
             exp = expected_rgba(im if im.ndim == 2 else im[..., [2, 1, 0] + ([3] if im.shape[2] == 4 else [])])
         assert exp.shape == got.shape and np.array_equal(exp, got), f
     assert {(8, 2), (8, 6), (8, 3), (1, 3)} <= kinds
+
+
+def test_radiance_hdr(ptc, tmp_path):
+    """Radiance RGBE (.hdr): run-length encoded and flat scan-lines written by OpenCV decode to exactly OpenCV's floats
+    (value = mantissa * 2^(e - 136), the `image` crate's rule too); the 1991 repeat marker by hand; damaged files are errors."""
+    import cv2
+    rng = np.random.default_rng(3)
+    for (h, w) in [(5, 3), (7, 8), (9, 40), (3, 200)]:
+        img = (rng.random((h, w, 3), dtype=np.float32) ** 4 * 50).astype(np.float32)
+        img[0, :min(w, 20)] = 0.25                                          # a run
+        path = str(tmp_path / f"t_{h}x{w}.hdr")
+        assert cv2.imwrite(path, img)
+        data = open(path, "rb").read()
+        rc, got = lib_decode(ptc, data)
+        assert rc == 0, got
+        ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)[..., ::-1]
+        assert got.dtype == np.float32 and np.array_equal(got[..., :3], ref) and (got[..., 3] == 1).all()
+    # flat pixels with an old-style repeat: (9, 9, 9, 130) followed by (1, 1, 1, 3) = that pixel four times in all
+    flat = b"".join(bytes([10 + x, 20, 30 + y, 128]) for y in range(3) for x in range(4))
+    data = b"#?RGBE\nFORMAT=32-bit_rle_rgbe\n\n-Y 4 +X 4\n" + flat + bytes([9, 9, 9, 130, 1, 1, 1, 3])
+    rc, got = lib_decode(ptc, data)
+    assert rc == 0, got
+    assert np.array_equal(got[3, :, :3], np.full((4, 3), 9 * 2.0 ** (130 - 136), np.float32))
+    assert np.array_equal(got[1, 2, :3], np.array([12, 20, 31], np.float32) * np.float32(2.0 ** (128 - 136)))
+    for bad, why in [(data[:-3], "truncated"), (data.replace(b"-Y 4 +X 4", b"+Y 4 +X 4"), "orientation"),
+                     (data.replace(b"-Y 4 +X 4", b"-Y 30000 +X 30000"), "too short"), (data.replace(b"-Y 4 +X 4", b"-Y 99999 +X 99999"), "image size"), (data.replace(b"32-bit_rle_rgbe", b"32-bit_rle_xyze"), "pixel format"),
+                     (data[:-4] + bytes([1, 1, 1, 9]), "repeat")]:
+        rc, msg = lib_decode(ptc, bad)
+        assert rc != 0 and why in msg, (why, msg)
+
+
+def test_radiance_hdr_reference_environment_map(ptc):
+    """The reference ships one Radiance file, res/bistro/san_giuseppe_bridge_4k.hdr (4096 x 2048, run-length RGBE, 24 MB; only
+    where /root/reference is present): it decodes to exactly OpenCV's floats."""
+    import cv2
+    path = "/root/reference/res/bistro/san_giuseppe_bridge_4k.hdr"
+    if not os.path.exists(path):
+        pytest.skip("the reference checkout is not present")
+    rc, got = lib_decode(ptc, open(path, "rb").read())
+    assert rc == 0, got
+    ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)[..., ::-1]
+    assert got.shape == (2048, 4096, 4) and np.array_equal(got[..., :3], ref) and float(got[..., :3].max()) == 98304.0

@@ -1,4 +1,4 @@
-// fuzz_decode.cpp — mutation fuzzer for the library's image decoders (csrc/img_decode.cu: PNG, OpenEXR, PFM), built with
+// fuzz_decode.cpp — mutation fuzzer for the library's image decoders (csrc/img_decode.cu: PNG, OpenEXR, Radiance HDR, PFM), built with
 // AddressSanitizer + UBSan by tools/fuzz.sh.  Test infrastructure, not part of libptcore.
 //
 // Scene files are untrusted input (Texture::load decodes whatever the MTL names, reference src/texture.rs:232-243), so a
@@ -8,6 +8,7 @@
 //         bytes, length) and deflated again half of the time, and mutated in its compressed form the other half
 //   EXR : header attributes, the offset table, chunk headers and chunk payloads are mutated in place (no checksums);
 //         ZIP / ZIPS payloads are also re-deflated from a mutated raw block so the predictor / interleave code sees them
+//   HDR : header and resolution line (hostile sizes), scan-line markers, run counts
 //   PFM : text header and payload length
 // usage: fuzz_decode <iterations> <seed> file...      exit code 0 = no sanitizer report (a report aborts the process)
 #include "../wgpu-pathtracer_b200/csrc/img_decode.h"
@@ -230,6 +231,25 @@ Bytes mutate_pfm(const Bytes& seed, Rng& r) {
     return f;
 }
 
+// Radiance HDR: text header (FORMAT / resolution line) and run-length encoded scan-lines, no checksums
+Bytes mutate_hdr(const Bytes& seed, Rng& r) {
+    Bytes f = seed;
+    size_t hend = 0;                                                // end of the resolution line
+    for (size_t i = 1, blank = 0; i < f.size(); ++i) if (f[i] == '\n') { if (blank) { hend = i + 1; break; } if (f[i - 1] == '\n') blank = 1; }
+    switch (r.below(6)) {
+        case 0: mutate_bytes(f, r, 0, hend); break;
+        case 1: {                                                    // hostile sizes in the resolution line
+            const char* R[] = {"-Y 99999999 +X 99999999\n", "-Y 1 +X 1073741824\n", "+Y 4 +X 4\n", "-Y 0 +X 0\n", "-Y 3 +X 32768\n", "-Y -5 +X 7\n", "-Y 2 +X 8\n", "-Y 40000 +X 9\n"};
+            const char* t = R[r.below(8)];
+            size_t a = 0; for (size_t i = 1; i < f.size(); ++i) if (f[i] == '\n' && f[i - 1] == '\n') { a = i + 1; break; }
+            if (a && hend > a) { f.erase(f.begin() + a, f.begin() + hend); f.insert(f.begin() + a, t, t + std::strlen(t)); }
+        } break;
+        case 2: resize_random(f, r); break;
+        default: mutate_bytes(f, r, hend); break;                    // scan-line markers, run counts, literals
+    }
+    return f;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -241,10 +261,11 @@ int main(int argc, char** argv) {
         std::ifstream in(argv[k], std::ios::binary);
         Bytes b((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
         const ptc::ImageKind kind = ptc::sniff_image(b.data(), b.size());
-        if (kind != ptc::IMG_PNG && kind != ptc::IMG_EXR && kind != ptc::IMG_PFM) { std::fprintf(stderr, "skipping %s (not PNG / EXR / PFM)\n", argv[k]); continue; }
+        if (kind != ptc::IMG_PNG && kind != ptc::IMG_EXR && kind != ptc::IMG_PFM && kind != ptc::IMG_HDR) { std::fprintf(stderr, "skipping %s (not PNG / EXR / HDR / PFM)\n", argv[k]); continue; }
         // every seed must decode as it is: a fuzzer over files the decoder refuses explores nothing
         ptc::DecodedImage img; std::string err;
-        const int rc = kind == ptc::IMG_PNG ? ptc::decode_png(b.data(), b.size(), img, err) : kind == ptc::IMG_EXR ? ptc::decode_exr(b.data(), b.size(), img, err) : ptc::decode_pfm(b.data(), b.size(), img, err);
+        const int rc = kind == ptc::IMG_PNG ? ptc::decode_png(b.data(), b.size(), img, err) : kind == ptc::IMG_EXR ? ptc::decode_exr(b.data(), b.size(), img, err)
+                     : kind == ptc::IMG_HDR ? ptc::decode_hdr(b.data(), b.size(), img, err) : ptc::decode_pfm(b.data(), b.size(), img, err);
         if (rc != 0) { std::fprintf(stderr, "seed %s does not decode: %s\n", argv[k], err.c_str()); return 2; }
         seeds.push_back(b); kinds.push_back(kind);
     }
@@ -252,7 +273,7 @@ int main(int argc, char** argv) {
     long ok = 0, bad = 0; uint64_t texel_bytes = 0;
     for (long it = 0; it < iters; ++it) {
         const uint32_t s = r.below((uint32_t)seeds.size());
-        const Bytes f = kinds[s] == ptc::IMG_PNG ? mutate_png(seeds[s], r) : kinds[s] == ptc::IMG_EXR ? mutate_exr(seeds[s], r) : mutate_pfm(seeds[s], r);
+        const Bytes f = kinds[s] == ptc::IMG_PNG ? mutate_png(seeds[s], r) : kinds[s] == ptc::IMG_EXR ? mutate_exr(seeds[s], r) : kinds[s] == ptc::IMG_HDR ? mutate_hdr(seeds[s], r) : mutate_pfm(seeds[s], r);
         // exact-size heap copy: AddressSanitizer then sees a read one byte past the file
         uint8_t* copy = (uint8_t*)std::malloc(f.size() ? f.size() : 1);
         std::memcpy(copy, f.data(), f.size());
@@ -262,6 +283,7 @@ int main(int argc, char** argv) {
             case ptc::IMG_PNG: rc = ptc::decode_png(copy, f.size(), img, err); break;
             case ptc::IMG_EXR: rc = ptc::decode_exr(copy, f.size(), img, err); break;
             case ptc::IMG_PFM: rc = ptc::decode_pfm(copy, f.size(), img, err); break;
+            case ptc::IMG_HDR: rc = ptc::decode_hdr(copy, f.size(), img, err); break;
             default: rc = 1; err = "unrecognised"; break;
         }
         std::free(copy);

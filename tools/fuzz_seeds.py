@@ -1,6 +1,7 @@
 """fuzz_seeds.py <dir> — the seed corpus of tools/fuzz_decode.cpp: small PNG / OpenEXR / PFM files that together reach
 every branch of the decoders in csrc/img_decode.cu (all PNG colour types and bit depths, tRNS, Adam7, the five row filters;
-EXR NONE / ZIPS / ZIP / PIZ with HALF and FLOAT channels, the 14-bit and the 16-bit wavelet; both PFM flavours).
+EXR NONE / ZIPS / ZIP / PIZ with HALF and FLOAT channels, the 14-bit and the 16-bit wavelet; Radiance HDR run-length, flat
+and old-style repeats; both PFM flavours).
 PNGs are framed by hand over zlib so the corpus does not depend on an encoder's choices; EXRs come from OpenCV's OpenEXR."""
 import os
 import struct
@@ -105,6 +106,14 @@ def main(out):
         assert cv2.imwrite(os.path.join(out, f"big_{cname}0.exr"), big, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, comp[cname]])
     assert cv2.imwrite(os.path.join(out, "grey_zip1.exr"), noise[..., 0].copy(), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION, comp["zip"]])
 
+    # Radiance HDR: run-length encoded scan-lines (OpenCV's writer), a width below 8 (flat pixels), and a hand-made flat file
+    # with the 1991 repeat marker (1, 1, 1, count)
+    hdr = (rng.random((12, 40, 3), dtype=np.float32) ** 4 * 50).astype(np.float32)
+    hdr[0, :25] = 0.25
+    assert cv2.imwrite(os.path.join(out, "rle.hdr"), hdr)
+    assert cv2.imwrite(os.path.join(out, "narrow.hdr"), hdr[:, :5].copy())
+    flat = b"".join(bytes([10 + x, 20, 30 + y, 128]) for y in range(3) for x in range(4))
+    put("flat_repeat.hdr", b"#?RGBE\nFORMAT=32-bit_rle_rgbe\n\n-Y 4 +X 4\n" + flat + bytes([9, 9, 9, 130, 1, 1, 1, 3]))
     put("rgb_le.pfm", b"PF\n5 3\n-1.0\n" + rng.random(45, dtype=np.float32).tobytes())
     put("grey_be.pfm", b"Pf\n5 3\n1.0\n" + rng.random(15, dtype=np.float32).astype(">f4").tobytes())
     return sorted(os.listdir(out))

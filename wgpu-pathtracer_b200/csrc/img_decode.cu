@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -23,6 +24,7 @@ ImageKind sniff_image(const uint8_t* d, size_t n) {
     if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return IMG_JPEG;
     if (n >= 3 && d[0] == 'P' && (d[1] == 'F' || d[1] == 'f') && (d[2] == '\n' || d[2] == ' ' || d[2] == '\r')) return IMG_PFM;
     if (n >= 8 && d[0] == 0x76 && d[1] == 0x2F && d[2] == 0x31 && d[3] == 0x01) return IMG_EXR;
+    if (n >= 10 && (std::memcmp(d, "#?RADIANCE", 10) == 0 || std::memcmp(d, "#?RGBE", 6) == 0)) return IMG_HDR;
     return IMG_UNKNOWN;
 }
 
@@ -537,6 +539,92 @@ int decode_exr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) 
         for (auto& t : th) t.join();
     }
     if (const char* why = failure.load()) { err = why; return 1; }
+    return 0;
+}
+
+// ---- Radiance RGBE (.hdr) -----------------------------------------------------------------------------------------------
+// Text header lines up to an empty line, then "-Y <height> +X <width>", then per scan-line either four bytes (2, 2, w >> 8,
+// w & 255) followed by the four channels run-length encoded one after the other (count > 128: a run of count - 128 copies
+// of the next byte; else count literal bytes), or — widths below 8 or above 32767, and old files — flat RGBE pixels, in
+// which (1, 1, 1, k) repeats the previous pixel k << shift times (the 1991 run-length form).
+int decode_hdr(const uint8_t* d, size_t n, DecodedImage& out, std::string& err) {
+    if (sniff_image(d, n) != IMG_HDR) { err = "not a Radiance HDR file"; return 1; }
+    size_t p = 0; bool blank = false;
+    while (p < n && !blank) {                                       // header: lines until an empty one
+        size_t e = p; while (e < n && d[e] != '\n') ++e;
+        if (e >= n) { err = "truncated Radiance header"; return 1; }
+        const std::string line((const char*)d + p, e - p);
+        if (line.empty()) blank = true;
+        else if (line.compare(0, 7, "FORMAT=") == 0) {
+            if (line != "FORMAT=32-bit_rle_rgbe") { err = "unsupported Radiance pixel format (only 32-bit_rle_rgbe)"; return 1; }
+        }                                                           // files without a FORMAT line are RGBE by default
+        p = e + 1;
+    }
+    if (!blank) { err = "truncated Radiance header"; return 1; }
+    size_t e = p; while (e < n && d[e] != '\n') ++e;
+    if (e >= n) { err = "truncated Radiance header"; return 1; }
+    const std::string res((const char*)d + p, e - p); p = e + 1;
+    long H = 0, W = 0; char ys = 0, xs = 0, ya = 0, xa = 0;
+    if (std::sscanf(res.c_str(), "%c%c %ld %c%c %ld", &ys, &ya, &H, &xs, &xa, &W) != 6 || ya != 'Y' || xa != 'X' || ys != '-' || xs != '+') {
+        err = "unsupported Radiance orientation (only -Y h +X w)"; return 1;
+    }
+    if (H <= 0 || W <= 0 || H > (1l << 30) || W > (1l << 30) || (uint64_t)H * (uint64_t)W > (1ull << 30)) { err = "bad Radiance image size"; return 1; }
+    // a scan-line costs at least 4 bytes however well it compresses (run-length: 8 per 127 pixels and channel): a header that
+    // promises more rows than the file has bytes for is refused before the image is allocated
+    if ((uint64_t)H * 4u > n - p || (uint64_t)W * (uint64_t)H / 60u > n - p) { err = "Radiance file too short for its size"; return 1; }
+    out.width = (uint32_t)W; out.height = (uint32_t)H; out.format = PTC_TEXEL_RGBA32F;
+    out.texels.assign((size_t)W * (size_t)H * 16, 0);
+    float* px = reinterpret_cast<float*>(out.texels.data());
+    std::vector<uint8_t> line((size_t)W * 4);
+    for (long y = 0; y < H; ++y) {
+        if (n - p >= 4 && W >= 8 && W <= 32767 && d[p] == 2 && d[p + 1] == 2 && !(d[p + 2] & 0x80)) {        // new run-length form
+            if ((((long)d[p + 2]) << 8 | d[p + 3]) != W) { err = "Radiance scan-line length differs from the image width"; return 1; }
+            p += 4;
+            for (int c = 0; c < 4; ++c) {
+                long x = 0;
+                while (x < W) {
+                    if (p >= n) { err = "truncated Radiance scan-line"; return 1; }
+                    int count = d[p++];
+                    if (count > 128) {
+                        count -= 128;
+                        if (p >= n || x + count > W) { err = "bad Radiance run"; return 1; }
+                        const uint8_t v = d[p++];
+                        for (int k = 0; k < count; ++k) line[(size_t)(x + k) * 4 + c] = v;
+                    } else {
+                        if (count == 0 || (size_t)count > n - p || x + count > W) { err = "bad Radiance run"; return 1; }
+                        for (int k = 0; k < count; ++k) line[(size_t)(x + k) * 4 + c] = d[p + k];
+                        p += (size_t)count;
+                    }
+                    x += count;
+                }
+            }
+        } else {                                                    // flat pixels, with the old repeat markers
+            long x = 0; int shift = 0;
+            while (x < W) {
+                if (n - p < 4) { err = "truncated Radiance scan-line"; return 1; }
+                const uint8_t* q = d + p; p += 4;
+                if (q[0] == 1 && q[1] == 1 && q[2] == 1) {
+                    if (x == 0 && y == 0) { err = "bad Radiance repeat marker"; return 1; }
+                    if (shift > 24) { err = "bad Radiance repeat marker"; return 1; }
+                    const long rep = (long)q[3] << shift;
+                    if (rep <= 0 || x + rep > W) { err = "bad Radiance repeat marker"; return 1; }
+                    uint8_t prev[4];
+                    if (x > 0) std::memcpy(prev, &line[(size_t)(x - 1) * 4], 4);
+                    else {                                          // repeats the last pixel of the previous scan-line: re-encode is not
+                        err = "bad Radiance repeat marker"; return 1;   // possible from floats, and no writer emits it
+                    }
+                    for (long k = 0; k < rep; ++k) std::memcpy(&line[(size_t)(x + k) * 4], prev, 4);
+                    x += rep; shift += 8;
+                } else { std::memcpy(&line[(size_t)x * 4], q, 4); ++x; shift = 0; }
+            }
+        }
+        float* o = px + (size_t)y * (size_t)W * 4;
+        for (long x = 0; x < W; ++x) {
+            const uint8_t* q = &line[(size_t)x * 4];
+            const float f = q[3] ? std::ldexp(1.0f, (int)q[3] - 136) : 0.0f;
+            o[x * 4] = (float)q[0] * f; o[x * 4 + 1] = (float)q[1] * f; o[x * 4 + 2] = (float)q[2] * f; o[x * 4 + 3] = 1.0f;
+        }
+    }
     return 0;
 }
 

@@ -6,6 +6,9 @@
 //          link dependency on it and a box without libnvjpeg only loses JPEG textures
 //   EXR  : decoded here: single-part scan-line files with HALF / FLOAT channels, compression NONE / ZIPS / ZIP / PIZ — what the
 //          reference's environment map (res/knob/envmap.exr: 4096 x 2048 FLOAT RGBA, PIZ) needs
+//   HDR  : Radiance RGBE (.hdr, "#?RADIANCE" / "#?RGBE"): flat and run-length encoded scan-lines, the -Y +X orientation every
+//          writer produces (the reference ships one with its Bistro scene, res/bistro/san_giuseppe_bridge_4k.hdr); value =
+//          mantissa * 2^(e - 136) as the `image` crate computes it (no + 0.5)
 //   PFM  : raw float maps
 // Output follows decode_image of the Python mirror: 8-bit sources stay RGBA8 (the kernels apply v / 255, no sRGB
 // decode), 16-bit sources become RGBA32F = v / 65535, float sources stay float; grey -> rgb, missing alpha -> 1.
@@ -22,13 +25,14 @@ struct DecodedImage {
     std::vector<uint8_t> texels;         // width * height * (4 or 16) bytes
 };
 
-enum ImageKind { IMG_UNKNOWN = 0, IMG_PNG, IMG_JPEG, IMG_PFM, IMG_EXR };
+enum ImageKind { IMG_UNKNOWN = 0, IMG_PNG, IMG_JPEG, IMG_PFM, IMG_EXR, IMG_HDR };
 ImageKind sniff_image(const uint8_t* data, size_t n);
 
 // 0 on success, else `err` says why
 int decode_png(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
 int decode_pfm(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
 int decode_exr(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
+int decode_hdr(const uint8_t* data, size_t n, DecodedImage& out, std::string& err);
 
 // nvJPEG decoder: one per host thread (own handle, state, stream and device buffer).
 class JpegDecoder {

@@ -725,10 +725,11 @@ static int decode_bytes(const uint8_t* data, size_t n, int cuda_device, std::uni
         case ptc::IMG_PNG: return ptc::decode_png(data, n, img, err);
         case ptc::IMG_PFM: return ptc::decode_pfm(data, n, img, err);
         case ptc::IMG_EXR: return ptc::decode_exr(data, n, img, err);
+        case ptc::IMG_HDR: return ptc::decode_hdr(data, n, img, err);
         case ptc::IMG_JPEG:
             if (!jpeg) jpeg.reset(new ptc::JpegDecoder(cuda_device));
             return jpeg->decode(data, n, img, err);
-        default: err = "unknown image format (this library decodes PNG, JPEG, OpenEXR and PFM)"; return 1;
+        default: err = "unknown image format (this library decodes PNG, JPEG, OpenEXR, Radiance HDR and PFM)"; return 1;
     }
 }
 PTC_API int ptc_scene_decode_textures(ptc_scene* s, int cuda_device, int n_threads) {
