@@ -41,7 +41,7 @@ int main(int argc, char** argv) {
         else if (a == "--lights-mis") mis = true;
         else if (a == "--out") { need(1); out = argv[++i]; }
         else if (a == "--help" || a == "-h") {
-            printf("ptrender --obj scene.obj [--env sky.exr|sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
+            printf("ptrender --obj scene.obj [--env sky.exr|sky.hdr|sky.pfm | --env-raw sky.f32 W H] [--size WxH] [--frames N] [--bounces B] [--pos x y z] [--look x y z] [--fov deg] [--lbvh] [--lights-mis] [--out prefix]\n");
             return 0;
         } else { fprintf(stderr, "ptrender: unknown argument %s\n", a.c_str()); return 2; }
     }
