@@ -113,3 +113,48 @@ def test_transcendentals_accuracy(oracle):
     y, xx = rng.uniform(-1, 1, 20000).astype(np.float32), rng.uniform(-1, 1, 20000).astype(np.float32)
     got, want = oracle.math_fn("atan2", y, xx), np.arctan2(y.astype(np.float64), xx.astype(np.float64))
     assert (np.abs(got - want) < 6e-7).all()
+
+
+def test_camera_against_an_independent_restatement(ptc):
+    """Camera::new + Camera::update (reference src/camera.rs:31-79) written again in numpy float32, sharing nothing with
+    oracle/ or csrc/: note the order — the basis is built from the CURRENT lookat, and only then is lookat moved to where
+    theta_x / theta_y point, so a new pose takes effect one update later.  Random poses, several updates; numpy's float32
+    tan / sin / cos may differ from libm's in the last place, hence 1e-6 relative instead of bytes."""
+    F = np.float32
+    rng = np.random.RandomState(11)
+
+    def norm(a):
+        return (a * (F(1.0) / F(np.sqrt(np.dot(a, a))))).astype(F)                  # glam: v * length_recip
+
+    def update(c):
+        vh = F(2.0) * F(np.tan(F(c["fov"] * F(np.pi / 180.0)) / F(2.0)))
+        vw = F(vh * (F(c["w"]) / F(c["h"])))
+        vz = norm((c["pos"] - c["lookat"]).astype(F))
+        vx = norm(np.cross(np.array([0, 1, 0], F), vz).astype(F))
+        vy = np.cross(vz, vx).astype(F)
+        xv, yv = (vx * vw).astype(F), (-vy * vh).astype(F)
+        c["psx"], c["psy"] = (xv / F(c["w"])).astype(F), (yv / F(c["h"])).astype(F)
+        top_left = (c["pos"] - vz - xv / F(2.0) - yv / F(2.0)).astype(F)
+        c["first"] = (top_left + F(0.5) * (c["psx"] + c["psy"])).astype(F)
+        tx, ty = F(c["tx"]), F(c["ty"])
+        c["lookat"] = np.array([c["pos"][0] + F(np.cos(tx)) * F(np.cos(ty)), c["pos"][1] + F(np.sin(ty)), c["pos"][2] + F(np.sin(tx)) * F(np.cos(ty))], F)
+
+    for _ in range(40):
+        w, h = int(rng.randint(16, 4000)), int(rng.randint(16, 2200))
+        fov = float(rng.uniform(20, 110))
+        pos = rng.uniform(-20, 20, 3).astype(F)
+        tx, ty = float(rng.uniform(-3.1, 3.1)), float(rng.uniform(-1.4, 1.4))
+        mine = {"w": w, "h": h, "fov": F(fov), "pos": pos, "lookat": (pos + np.array([0, 0, 1], F)).astype(F), "tx": 0.0, "ty": 0.0}
+        update(mine)                                                                # Camera::new ends with update()
+        cam = ptc.Camera((w, h), fov, tuple(float(x) for x in pos))
+        mine["tx"], mine["ty"] = tx, ty
+        cam.set(theta_x=tx, theta_y=ty)
+        for _ in range(2):
+            update(mine)
+            cam.update()
+        got = cam.uniforms(frame=5).camera
+        for name, want in (("pixel_space_x", mine["psx"]), ("pixel_space_y", mine["psy"]), ("first_pixel_pos", mine["first"]), ("lookat", mine["lookat"])):
+            have = np.array(list(getattr(got, name)), F)
+            scale = max(1e-3, float(np.abs(want).max()))
+            assert np.abs(have - want).max() <= 2e-6 * scale + 1e-7, (name, have, want)
+        assert got.width == w and got.height == h and got.frame == 5
