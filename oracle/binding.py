@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpt_oracle.so")
+LIB_PATH = os.environ.get("PTC_ORACLE_LIB") or os.path.join(_HERE, "libpt_oracle.so")   # another build of pt_oracle.cpp: the sanitizer build of tools/fuzz.sh
 _lib = None
 
 

@@ -9,8 +9,8 @@
 #   tsan   : the same three fuzzers (short runs; the OBJ scan cut into 64-byte chunks, the > 256 KB OpenEXR seeds) and
 #            tools/prepare_threads.cpp (120 000 triangles through prepare_scene and the three host builders) under
 #            ThreadSanitizer instead
-#   hostemu: tests/hostemu (the device functions of pt_device.cuh compiled for the host) built with ASan + UBSan and run
-#            through tests/test_hostemu_parity.py and tests/test_display_path.py
+#   hostemu: tests/hostemu (the device functions of pt_device.cuh compiled for the host) AND the oracle built with ASan +
+#            UBSan and run through tests/test_hostemu_parity.py, test_display_path.py and test_oracle_fixtures.py
 # A sanitizer report or a violated invariant ends the run with a non-zero exit code.  Last long run: profiles/r02zn_fuzz.log
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"; root="$(dirname "$here")"; csrc="$root/wgpu-pathtracer_b200/csrc"
@@ -53,7 +53,9 @@ if [ "$what" = hostemu ]; then
     g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -mavx2 -mfma -Wno-unused-function -fvisibility=hidden -pthread \
         -fsanitize=address,undefined -fno-sanitize-recover=undefined -shared -o "$work/libpt_hostemu_asan.so" \
         "$root/tests/hostemu/hostemu.cpp" "$root/tests/hostemu/warpsim.cpp" "$csrc/scene_prep.cpp" "$csrc/bvh_build.cpp"
-    PTC_HOSTEMU_LIB="$work/libpt_hostemu_asan.so" LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
+    g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -mavx2 -mfma -Wno-unused-function -fvisibility=hidden -pthread \
+        -fsanitize=address,undefined -fno-sanitize-recover=undefined -shared -o "$work/libpt_oracle_asan.so" "$root/oracle/pt_oracle.cpp"
+    PTC_ORACLE_LIB="$work/libpt_oracle_asan.so" PTC_HOSTEMU_LIB="$work/libpt_hostemu_asan.so" LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
         ASAN_OPTIONS=detect_leaks=0:verify_asan_link_order=0 \
-        python -m pytest "$root/tests/test_hostemu_parity.py" "$root/tests/test_display_path.py" -x -q -m "not gpu" -p no:cacheprovider
+        python -m pytest "$root/tests/test_hostemu_parity.py" "$root/tests/test_display_path.py" "$root/tests/test_oracle_fixtures.py" -x -q -m "not gpu" -p no:cacheprovider
 fi
